@@ -1,0 +1,106 @@
+"""Generate tests/golden/* by running the REAL reference modules (authoring container).
+
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden
+Each fixture = a JSON manifest (state-dict keys/shapes/dtypes of the reference
+module = the checkpoint-compatibility contract) + an .npz with the reference's
+fp32 outputs.  Weights and inputs are NOT stored: they are regenerated from
+oracle/synth.py (platform-independent), so fixtures stay small.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import refload, synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _load_sd(module, seed):
+    man = refload.manifest_of(module)
+    sd = synth.fill_state_dict(man, seed)
+    module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    module.eval()
+    return man
+
+
+def _save(name, manifest, meta, **arrays):
+    with open(os.path.join(OUT, name + ".json"), "w") as f:
+        json.dump({"meta": meta, "manifest": manifest}, f, indent=0, separators=(",", ":"))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+    print("wrote", name, {k: v.shape for k, v in arrays.items()})
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = refload.load()
+    torch.set_grad_enabled(False)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # ---- SFC: ResUnet_VB(dim=16) (BASELINE config 1 shape, reduced resolution)
+    for tag, dim, H, W, B in (("resunet16_64x96", 16, 64, 96, 2), ("resunet8_32x48", 8, 32, 48, 1)):
+        m = ref.resunet.ResUnet_VB(channels=3, dim=dim, out_dim=5)
+        man = _load_sd(m, seed=1)
+        x = synth.frames(tag, B, H, W, seed=1)
+        _save(tag, man, {"kind": "resunet", "dim": dim, "B": B, "H": H, "W": W, "seed": 1, "classes": 5},
+              logits=m(_t(x)).numpy())
+
+    # ---- fusion heads alone
+    N = 5
+    for K in (3, 5):
+        for variant, cls in (("large", ref.multiframe.MultiFrameNetLarge), ("basic", ref.multiframe.MultiFrameNetBasic)):
+            tag = f"fusion_{variant}_k{K}_48x64"
+            m = cls(N, K, False, with_optflow=True, with_depth=True)
+            man = _load_sd(m, seed=2)
+            B, H, W = 2, 48, 64
+            x = np.concatenate([synth.normal(tag + "/seg", (B, N * K, H, W), 2, std=2.0),
+                                synth.flow(tag, B, H, W, 2).repeat(K - 1, axis=1) * np.linspace(1, 2, 2 * (K - 1), dtype=np.float32)[None, :, None, None],
+                                synth.uniform(tag + "/dep", (B, K, H, W), 2)], axis=1).astype(np.float32)
+            arrays = {"out": m(_t(x)).numpy()}
+            if variant == "basic":
+                arrays["warped"] = m.warp_segmentation_and_depth(_t(x)).numpy()
+            _save(tag, man, {"kind": "fusion", "variant": variant, "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 2}, **arrays)
+
+    # ---- full MFCNet with ResUNet-16 base: the reference has no ResUNetMulti class
+    # (SURVEY.md D2); oracle = reference HRNetMulti{Large,Basic} with base_model swapped.
+    for variant, cls in (("large", ref.multiframe.HRNetMultiLarge), ("basic", ref.multiframe.HRNetMultiBasic)):
+        K, B, H, W = 3, 1, 64, 96
+        tag = f"mfcnet_resunet16_{variant}_k{K}_64x96"
+        m = cls(num_classes=N, num_frames=K, pretrained=False, loadpath=None, optflow_inputs=True, depth_inputs=True)
+        m.base_model = ref.resunet.ResUnet_VB(channels=3, dim=16, out_dim=N)
+        man = _load_sd(m, seed=3)
+        xs = [synth.frames(f"{tag}/{i}", B, H, W, 3) for i in range(K)]
+        fl = [synth.flow(f"{tag}/{i}", B, H, W, 3) for i in range(K - 1)]
+        dp = [synth.depth(f"{tag}/{i}", B, H, W, 3) for i in range(K)]
+        out = m([_t(a) for a in xs], optflow=[_t(a) for a in fl], depth=[_t(a) for a in dp])
+        _save(tag, man, {"kind": "mfcnet", "base": "resunet16", "variant": variant, "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 3},
+              out=out.numpy())
+
+    # ---- the 576x720 grid buffer itself
+    g = ref.multiframe.MultiFrameNetBasic(N, 3, False, True, True).grid.numpy()
+    assert np.array_equal(g, synth.mesh_grid_576x720()), "synth grid != reference grid"
+
+    # ---- localisation: reference centroid_error on synthetic blob heatmaps
+    from . import localize_cases
+    loc = ref.localization
+    cases = localize_cases.cases()
+    res = {}
+    for name, prob in cases.items():
+        class A:  # the reference reads args.num_classes only
+            num_classes = 5
+        gt = torch.zeros(1, prob.shape[2], prob.shape[3], dtype=torch.int64)
+        *_, c_pred = loc.centroid_error(_t(prob), gt, A)
+        res[name] = [[(None if (isinstance(v, float) and np.isnan(v)) else int(v)) for v in lst] for lst in c_pred]
+    with open(os.path.join(OUT, "localize_centroids.json"), "w") as f:
+        json.dump(res, f)
+    print("wrote localize_centroids", {k: v for k, v in list(res.items())[:3]})
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,111 @@
+"""Deterministic synthetic tensors, bit-identical on every platform.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  No transcendental functions and
+no library RNG streams are used, so the container that writes the golden
+fixtures and the GPU box that replays them produce the same bits.
+
+Values are a 4-term Irwin-Hall approximation of a unit normal built from a
+splitmix64 counter hash: exact integer arithmetic, then a handful of exactly
+rounded float64 operations.
+"""
+import zlib
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def _key(name, seed):
+    return np.uint64((zlib.crc32(name.encode()) << 16) ^ (seed * 0x1000193 + 12345))
+
+
+def uniform(name, shape, seed=0, lo=0.0, hi=1.0):
+    """U[lo,hi) float32 tensor keyed by (name, seed)."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    with np.errstate(over="ignore"):
+        ctr = np.arange(n, dtype=np.uint64) * np.uint64(4) + (_key(name, seed) << np.uint64(20))
+        bits = _splitmix64(ctr)
+    u = (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (lo + (hi - lo) * u).astype(np.float32).reshape(shape)
+
+
+def normal(name, shape, seed=0, std=1.0, mean=0.0):
+    """Approximately N(mean, std^2) float32 tensor keyed by (name, seed)."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    acc = np.zeros(n, dtype=np.float64)
+    with np.errstate(over="ignore"):
+        base = np.arange(n, dtype=np.uint64) * np.uint64(4) + (_key(name, seed) << np.uint64(20))
+        for j in range(4):
+            bits = _splitmix64(base + np.uint64(j))
+            acc += (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    z = (acc - 2.0) * 1.7320508075688772  # var of 4 uniforms = 1/3
+    return (mean + std * z).astype(np.float32).reshape(shape)
+
+
+def fill_state_dict(manifest, seed=0):
+    """Build a state dict {name: np.ndarray} for a manifest [(name, shape, dtype)].
+
+    Rules (chosen so every fold path is exercised):
+      *.running_mean       U(-0.5, 0.5)
+      *.running_var        U(0.5, 1.5)
+      *.num_batches_tracked  int64 zero
+      grid                 the (1,2,576,720) normalised mesh of
+                           models/multiframe_model.py:172-185
+      norm / bn weight     1 + 0.1 N(0,1)      (1-D '.weight' tensors)
+      1-D bias             0.1 N(0,1)
+      conv weight (4-D)    N(0, 1/fan_in)  scaled by 1.0 (He-like without gain)
+    """
+    out = {}
+    for name, shape, dtype in manifest:
+        shape = tuple(shape)
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            out[name] = np.zeros(shape, dtype=np.int64)
+        elif leaf == "running_mean":
+            out[name] = uniform(name, shape, seed, -0.5, 0.5)
+        elif leaf == "running_var":
+            out[name] = uniform(name, shape, seed, 0.5, 1.5)
+        elif leaf == "grid":
+            out[name] = mesh_grid_576x720()
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            out[name] = normal(name, shape, seed, std=float(1.0 / np.sqrt(fan_in)))
+        elif len(shape) == 1 and leaf == "weight":
+            out[name] = normal(name, shape, seed, std=0.1, mean=1.0)
+        else:
+            out[name] = normal(name, shape, seed, std=0.1)
+        assert out[name].shape == shape, (name, shape)
+    return out
+
+
+def mesh_grid_576x720():
+    """`MultiFrameNetBasic._create_mesh_grid` (models/multiframe_model.py:172-185):
+    x,y in [-1,1] for a fixed 576x720 image, stacked (x, y), float32.
+    The reference computes 2.0*idx/(N-1)-1.0 on int64 tensors in float32."""
+    H, W = 576, 720
+    ys = (np.float32(2.0) * np.arange(H, dtype=np.float32) / np.float32(H - 1) - np.float32(1.0)).astype(np.float32)
+    xs = (np.float32(2.0) * np.arange(W, dtype=np.float32) / np.float32(W - 1) - np.float32(1.0)).astype(np.float32)
+    gy = np.repeat(ys[:, None], W, axis=1)
+    gx = np.repeat(xs[None, :], H, axis=0)
+    return np.stack([gx, gy], 0)[None].astype(np.float32)
+
+
+def frames(tag, B, H, W, seed=0):
+    """ImageNet-normalised-like RGB frames."""
+    return normal("frame/" + tag, (B, 3, H, W), seed)
+
+
+def depth(tag, B, H, W, seed=0):
+    return uniform("depth/" + tag, (B, 1, H, W), seed)
+
+
+def flow(tag, B, H, W, seed=0, scale=4.0):
+    return normal("flow/" + tag, (B, 2, H, W), seed, std=scale)

@@ -1,0 +1,187 @@
+"""fp32 functional restatement of the reference modules on the hot path.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Every function takes a plain
+``state_dict`` (the reference's own key names) and tensors, and recomputes
+what the reference ``nn.Module`` computes, in fp32 on whatever device the
+tensors live on (CPU for the oracle / CPU baseline).  It is written against
+the state-dict *keys*, not as a module tree, so it doubles as a check that a
+checkpoint alone determines the result.
+
+Pinned by tests/test_oracle_vs_reference.py (live reference, authoring
+container) and tests/test_oracle_golden.py (committed reference outputs).
+"""
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------
+# ResUnet_VB  (models/resunet.py:97-180)
+# ----------------------------------------------------------------------------
+def weight_standardize(w, eps=1e-5):
+    """models/resunet.py:56-62: per-out-channel (w-mean)*rsqrt(biased var+eps);
+    eps is 1e-5 for fp32 inputs (1e-3 otherwise)."""
+    flat = w.reshape(w.shape[0], -1)
+    mu = flat.mean(dim=1).reshape(-1, 1, 1, 1)
+    var = flat.var(dim=1, unbiased=False).reshape(-1, 1, 1, 1)
+    return (w - mu) * torch.rsqrt(var + eps)
+
+
+def _ws_gn_silu(sd, p, x, groups):
+    """`Block.forward` (models/resunet.py:75-80): WS-conv3x3 -> GroupNorm -> SiLU."""
+    y = F.conv2d(x, weight_standardize(sd[p + "proj.weight"]), sd[p + "proj.bias"], padding=1)
+    y = F.group_norm(y, groups, sd[p + "norm.weight"], sd[p + "norm.bias"], eps=1e-5)
+    return F.silu(y)
+
+
+def _resnet_block(sd, p, x, groups):
+    """`ResnetBlock.forward` (models/resunet.py:90-95)."""
+    h = _ws_gn_silu(sd, p + "block1.", x, groups)
+    h = _ws_gn_silu(sd, p + "block2.", h, groups)
+    if p + "res_conv.weight" in sd:
+        x = F.conv2d(x, sd[p + "res_conv.weight"], sd[p + "res_conv.bias"])
+    return h + x
+
+
+def _pixel_unshuffle2(x):
+    """einops 'b c (h p1) (w p2) -> b (c p1 p2) h w', p1=p2=2 (models/resunet.py:47)."""
+    b, c, h, w = x.shape
+    x = x.reshape(b, c, h // 2, 2, w // 2, 2).permute(0, 1, 3, 5, 2, 4)
+    return x.reshape(b, c * 4, h // 2, w // 2)
+
+
+def resunet_forward(sd, x, groups=8, prefix=""):
+    """`ResUnet_VB.forward` (models/resunet.py:153-180) -> raw logits."""
+    g = lambda k: sd[prefix + k]
+    sub = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)} if prefix else sd
+    n_levels = 1 + max(int(k.split(".")[1]) for k in sub if k.startswith("downs."))
+    x = F.conv2d(x, sub["init_conv.weight"], sub["init_conv.bias"], padding=3)
+    stem = x
+    skips = []
+    for i in range(n_levels):
+        x = _resnet_block(sub, f"downs.{i}.0.", x, groups)
+        skips.append(x)
+        if f"downs.{i}.1.1.weight" in sub:      # Downsample = unshuffle + 1x1 (models/resunet.py:45-49)
+            x = F.conv2d(_pixel_unshuffle2(x), sub[f"downs.{i}.1.1.weight"], sub[f"downs.{i}.1.1.bias"])
+        else:                                    # last level: plain 3x3 (models/resunet.py:134)
+            x = F.conv2d(x, sub[f"downs.{i}.1.weight"], sub[f"downs.{i}.1.bias"], padding=1)
+    x = _resnet_block(sub, "mid_block.", x, groups)
+    for i in range(n_levels):
+        x = torch.cat((x, skips.pop()), dim=1)
+        x = _resnet_block(sub, f"ups.{i}.0.", x, groups)
+        if f"ups.{i}.1.1.weight" in sub:        # Upsample = nearest x2 + 3x3 (models/resunet.py:39-43)
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+            x = F.conv2d(x, sub[f"ups.{i}.1.1.weight"], sub[f"ups.{i}.1.1.bias"], padding=1)
+        else:
+            x = F.conv2d(x, sub[f"ups.{i}.1.weight"], sub[f"ups.{i}.1.bias"], padding=1)
+    x = torch.cat((x, stem), dim=1)
+    x = _resnet_block(sub, "final_res_block.", x, groups)
+    return F.conv2d(x, sub["output_layer.weight"], sub["output_layer.bias"])
+
+
+# ----------------------------------------------------------------------------
+# MultiFrameNet{Basic,Large}  (models/multiframe_model.py:51-205)
+# ----------------------------------------------------------------------------
+def _bn_eval(sd, p, x, eps=1e-5):
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
+                        training=False, eps=eps)
+
+
+def fusion_stack(sd, x, prefix="multiframe_net."):
+    """The 4-conv Sequential shared by Basic and Large
+    (models/multiframe_model.py:62-73 and :191-202): 11x11(p5) BN ReLU 3x3 BN ReLU 3x3 BN ReLU 1x1."""
+    p = prefix
+    x = F.relu(_bn_eval(sd, p + "1.", F.conv2d(x, sd[p + "0.weight"], padding=5)))
+    x = F.relu(_bn_eval(sd, p + "4.", F.conv2d(x, sd[p + "3.weight"], padding=1)))
+    x = F.relu(_bn_eval(sd, p + "7.", F.conv2d(x, sd[p + "6.weight"], padding=1)))
+    return F.conv2d(x, sd[p + "9.weight"])
+
+
+def flow_warp_single(m, flow, grid):
+    """`_warp_single_map` (models/multiframe_model.py:141-170): the stored 576x720
+    normalised grid is *cropped* to HxW, the flow is normalised by (W-1)/2,(H-1)/2,
+    then grid_sample(bilinear, zeros, align_corners=True)."""
+    H, W = m.shape[-2:]
+    g = grid[:, :, :H, :W]
+    fx = flow[:, 0] / ((W - 1) / 2.0)
+    fy = flow[:, 1] / ((H - 1) / 2.0)
+    new = (g + torch.stack((fx, fy), dim=1)).permute(0, 2, 3, 1)
+    return F.grid_sample(m, new, mode="bilinear", padding_mode="zeros", align_corners=True)
+
+
+def warp_seg_and_depth(x, grid, N, K, with_depth):
+    """`warp_segmentation_and_depth` (models/multiframe_model.py:89-139)."""
+    seg = x[:, : N * K]
+    flo = x[:, N * K : N * K + 2 * K - 2]
+    dep = x[:, N * K + 2 * K - 2 :] if with_depth else None
+    segs = [seg[:, :N]]
+    deps = [dep[:, 0:1]] if with_depth else []
+    for i in range(1, K):
+        f = flo[:, 2 * (i - 1) : 2 * i]
+        for j in range(N):
+            segs.append(flow_warp_single(seg[:, i * N + j : i * N + j + 1], f, grid))
+        if with_depth:
+            deps.append(flow_warp_single(dep[:, i : i + 1], f, grid))
+    return torch.cat(segs + deps, dim=1)
+
+
+def fusion_large_forward(sd, x, prefix=""):
+    """`MultiFrameNetLarge.forward` (models/multiframe_model.py:204-205)."""
+    return fusion_stack(sd, x, prefix + "multiframe_net.")
+
+
+def fusion_basic_forward(sd, x, N, K, with_optflow, with_depth, prefix=""):
+    """`MultiFrameNetBasic.forward` (models/multiframe_model.py:84-87)."""
+    if with_optflow:
+        x = warp_seg_and_depth(x, sd[prefix + "grid"], N, K, with_depth)
+    return fusion_stack(sd, x, prefix + "multiframe_net.")
+
+
+def mfcnet_forward(sd, frames, optflow, depth, *, base, variant, N, head="logits"):
+    """`XMulti{Basic,Large}.forward` (models/multiframe_model.py:424-438 for HRNet;
+    :224-239 for Ternaus which feeds exp(log-probs)).  `base` is a callable
+    (sub_state_dict, frame) -> per-frame class maps; `head` selects the family's
+    convention: 'logits' (HRNet/ResUNet) or 'exp' (Ternaus)."""
+    K = len(frames)
+    bsd = {k[len("base_model."):]: v for k, v in sd.items() if k.startswith("base_model.")}
+    fsd = {k[len("multiframe_net."):]: v for k, v in sd.items() if k.startswith("multiframe_net.")}
+    maps = []
+    for f in frames:
+        y = base(bsd, f)
+        maps.append(y.exp() if head == "exp" else y)
+    if optflow is not None:
+        maps += list(optflow)
+    if depth is not None:
+        maps += list(depth)
+    x = torch.cat(maps, dim=1)
+    if variant == "large":
+        return fusion_large_forward(fsd, x)
+    return fusion_basic_forward(fsd, x, N, K, optflow is not None, depth is not None)
+
+
+# ----------------------------------------------------------------------------
+# heatmap head  (call sites: src/engine.py:65,141;
+# scripts/test_multiframe_segmentation_on_videos_v3.py:281,289)
+# ----------------------------------------------------------------------------
+def heatmap_head(logits):
+    """log-softmax over classes, its exp (the 'probabilities' the video script
+    uses), and numpy-first-max argmax of the probabilities."""
+    logp = F.log_softmax(logits, dim=1)
+    prob = torch.exp(logp)
+    return logp, prob, prob.cpu().numpy().argmax(axis=1)
+
+
+# ----------------------------------------------------------------------------
+# correlation  (models/unflow_correlation.py:10-105, 282-337) -- fast torch form;
+# the summation-order-exact restatement is oracle/corr_oracle.c
+# ----------------------------------------------------------------------------
+def correlation(first, second, max_disp=20, stride2=2):
+    B, C, H, W = first.shape
+    D = 2 * (max_disp // stride2) + 1
+    pad = F.pad(second, (max_disp,) * 4)
+    out = first.new_zeros(B, D * D, H, W)
+    for iy in range(D):
+        for ix in range(D):
+            dy = (iy - D // 2) * stride2 + max_disp
+            dx = (ix - D // 2) * stride2 + max_disp
+            out[:, iy * D + ix] = (first * pad[:, :, dy : dy + H, dx : dx + W]).sum(1) / C
+    return out

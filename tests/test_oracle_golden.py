@@ -1,0 +1,59 @@
+"""The torch oracle restatement must reproduce the outputs the REAL reference
+modules produced (tests/golden, written by oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, torch_oracle as TO
+from tests import golden_util as G
+
+TOL = 2e-5  # same fp32 ops; allows a different CPU conv kernel choice on another host
+
+
+@pytest.mark.parametrize("tag", ["resunet16_64x96", "resunet8_32x48"])
+def test_resunet_matches_reference_output(tag):
+    meta, man, arr = G.load(tag)
+    sd = G.state_dict(man, meta["seed"])
+    x = torch.from_numpy(synth.frames(tag, meta["B"], meta["H"], meta["W"], meta["seed"]))
+    with torch.no_grad():
+        y = TO.resunet_forward(sd, x)
+    assert y.shape == arr["logits"].shape
+    assert np.abs(y.numpy() - arr["logits"]).max() < TOL
+
+
+@pytest.mark.parametrize("K", [3, 5])
+@pytest.mark.parametrize("variant", ["large", "basic"])
+def test_fusion_matches_reference_output(variant, K):
+    tag = f"fusion_{variant}_k{K}_48x64"
+    meta, man, arr = G.load(tag)
+    sd = G.state_dict(man, meta["seed"])
+    x = G.fusion_input(tag, meta)
+    with torch.no_grad():
+        if variant == "large":
+            y = TO.fusion_large_forward(sd, x)
+        else:
+            w = TO.warp_seg_and_depth(x, sd["grid"], meta["N"], K, True)
+            assert np.abs(w.numpy() - arr["warped"]).max() < TOL
+            y = TO.fusion_basic_forward(sd, x, meta["N"], K, True, True)
+    assert np.abs(y.numpy() - arr["out"]).max() < TOL
+
+
+@pytest.mark.parametrize("variant", ["large", "basic"])
+def test_mfcnet_resunet_matches_reference_output(variant):
+    tag = f"mfcnet_resunet16_{variant}_k3_64x96"
+    meta, man, arr = G.load(tag)
+    sd = G.state_dict(man, meta["seed"])
+    xs, fl, dp = G.mfcnet_inputs(tag, meta)
+    with torch.no_grad():
+        y = TO.mfcnet_forward(sd, xs, fl, dp, base=TO.resunet_forward, variant=variant, N=meta["N"])
+    assert np.abs(y.numpy() - arr["out"]).max() < TOL
+
+
+def test_synth_is_stable():
+    """Known-answer check of the platform-independent generator itself."""
+    a = synth.normal("kat", (4,), seed=5)
+    b = synth.uniform("kat", (3,), seed=5)
+    assert a.dtype == np.float32 and b.dtype == np.float32
+    assert np.array_equal(a, synth.normal("kat", (4,), seed=5))
+    assert abs(float(synth.normal("stat", (200000,), 1).std()) - 1.0) < 0.01
+    assert abs(float(synth.uniform("stat", (200000,), 1).mean()) - 0.5) < 0.01
