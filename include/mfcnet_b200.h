@@ -1,0 +1,305 @@
+/*
+ * mfcnet_b200.h -- C ABI of libmfcnet_b200.so, the B200 (sm_100a) implementation of
+ * mfcnet-tracker's multi-frame inference hot path.
+ *
+ * Boundary contract
+ * -----------------
+ *  - plain C: raw device pointers, ints and a cudaStream_t passed as void*; no torch types.
+ *  - every entry point returns 0 on success or a negative MFC_E* code; the message of the
+ *    last error on the calling thread is returned by mfc_last_error().
+ *  - no allocation, no synchronisation and no global mutable state inside the hot calls:
+ *    the caller owns every buffer (inputs, outputs, workspaces) and the stream.
+ *  - there is no CPU fallback: on a device that is not sm_100 every launch returns
+ *    MFC_EARCH.
+ *
+ * The reference is pure Python/PyTorch; its only FFI on this path is the CuPy
+ * RawKernel launch in models/unflow_correlation.py:296-329 (raw data_ptr()s + stream).
+ * Each entry point below names the reference code it replaces (paths relative to the
+ * reference checkout).  The reference-side binding a maintainer would add (ctypes) is
+ * shown in INTEGRATION.md.
+ *
+ * Activation layout ("C8"): [B][ceil(C/8)][H][W][8] of fp16 (default) or bf16 -- channel
+ * chunks of 8 are planes, so a pixel's 8 channels are one 16-byte vector, channel concat
+ * is a list of plane pointers (zero-copy) and a plane is directly the K-major, no-swizzle
+ * shared-memory image a tcgen05.mma A-operand descriptor walks.
+ */
+#ifndef MFCNET_B200_H_
+#define MFCNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFC_ABI_VERSION 1
+
+/* error codes */
+#define MFC_OK 0
+#define MFC_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define MFC_EARCH (-2)    /* device is not sm_100 (B200)                 */
+#define MFC_ECUDA (-3)    /* CUDA runtime error (see mfc_last_error())   */
+#define MFC_ENOMEM (-4)   /* caller-provided workspace too small         */
+
+/* element types of C8 activations / packed weights */
+#define MFC_F16 0
+#define MFC_BF16 1
+
+#define MFC_MAX_SRC 8
+
+int mfc_abi_version(void);
+const char* mfc_last_error(void);
+/* 0 if `device` can run the kernels (compute capability 10.x), else MFC_EARCH. */
+int mfc_device_check(int device);
+
+/* ------------------------------------------------------------------------------------
+ * Layout conversion.  Replaces the implicit NCHW tensors + torch.cat of
+ * models/multiframe_model.py:424-436 (frames, flows and depths enter as separate NCHW
+ * fp32 tensors and are concatenated on channels).
+ * ---------------------------------------------------------------------------------- */
+
+/* Gather up to 8 fp32 NCHW channel planes into ONE C8 plane (chunk) of `dst`.
+ * plane[j] points at channel j's H*W plane of sample 0 (NULL -> zeros);
+ * plane_bstride[j] = elements between consecutive samples of that source. */
+typedef struct MfcGather {
+  const float* plane[8];
+  long long plane_bstride[8];
+} MfcGather;
+int mfc_gather_nchw_to_c8(const MfcGather* g, void* dst_chunk, long long dst_bstride_bytes,
+                          int B, int H, int W, int dtype, void* stream);
+
+/* C8 (first `C` channels) -> fp32 NCHW [B][C][H][W]. */
+int mfc_c8_to_nchw(const void* src, long long src_bstride_bytes, float* dst, int B, int C, int H, int W,
+                   int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Weight preparation (run once per checkpoint load, results cached by the caller).
+ * ---------------------------------------------------------------------------------- */
+
+/* Weight standardisation of models/resunet.py:56-62: per output channel
+ * (w - mean) * rsqrt(biased_var + eps) over (Cin,kh,kw).  w, out: fp32 [Cout][fan_in]. */
+int mfc_weight_standardize(const float* w, float* out, int Cout, int fan_in, float eps, void* stream);
+
+/* Eval-mode BatchNorm as a per-channel affine (the BN after every conv in
+ * models/multiframe_model.py:62-73 and models/hrnet.py): scale = g*rsqrt(var+eps),
+ * shift = b - mean*scale, optionally composed with a conv bias (shift += bias*scale). */
+int mfc_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                const float* conv_bias /*or NULL*/, float eps, float* scale, float* shift, int C, void* stream);
+
+/* Geometry the conv kernel derives from a descriptor (needed to size buffers). */
+typedef struct MfcConvInfo {
+  int nb;              /* output channels per N-block (multiple of 16, <= 256)        */
+  int nblk;            /* number of N-blocks; padded Cout = nb*nblk                   */
+  int cin_chunks;      /* total 8-channel input planes (sum of src[].nchunks)         */
+  int ksteps;          /* ceil(cin_chunks/2): 16-channel MMA K-steps per tap          */
+  int tile_h, tile_w;  /* output tile                                                 */
+  int tiles_per_image; /* tiles in one sample: stats partials are [B*tiles][nb*nblk][2] */
+  int runs;            /* 128-row MMA runs per tile                                   */
+  int kstages;         /* channel stages of the K loop                                */
+  int smem_bytes;      /* dynamic shared memory per CTA                               */
+  int tmem_cols;       /* TMEM columns allocated per CTA                              */
+  long long packed_weight_bytes;
+} MfcConvInfo;
+
+typedef struct MfcSrc {
+  const void* ptr;         /* C8 planes [B][nchunks][Hin][Win][8] (device)                      */
+  const float* affine;     /* NULL, or [B][nchunks*8][2] (scale,shift): x -> silu(x*scale+shift) */
+  long long batch_stride;  /* bytes between samples                                             */
+  int nchunks;             /* 8-channel planes taken from this source                           */
+  int reserved;
+} MfcSrc;
+
+typedef struct MfcConvDesc {
+  int B, Hin, Win;         /* source size (before the optional nearest x2)        */
+  int Hout, Wout;
+  int Cout;                /* real output channels                                */
+  int kh, kw, stride, pad; /* stride 1 or 2                                       */
+  int upsample;            /* 1, or 2 = nearest-neighbour x2 fused into the loader */
+  int act;                 /* 0 none, 1 ReLU (after scale/shift and residual)     */
+  int dtype;               /* MFC_F16 / MFC_BF16 (inputs, weights, C8 outputs)    */
+  int nsrc;                /* channel-concat sources, in order                    */
+  MfcSrc src[MFC_MAX_SRC];
+} MfcConvDesc;
+
+int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info);
+
+/* OIHW fp32 (device) -> the packed tcgen05 B-operand image.
+ * chan_map[k] (device int32, length cin_chunks*8, or NULL = identity) gives, for padded
+ * input channel k of the concat (8 per plane), the index into the weight's Cin axis or -1. */
+int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w, const int* chan_map,
+                            void* packed, void* stream);
+
+/* Fused convolution.  Replaces every nn.Conv2d / WeightStandardizedConv2d +
+ * following BatchNorm/ReLU, the torch.cat skip-concats (models/resunet.py:168,174), the
+ * nearest Upsample (:39-43) and the pixel-unshuffle Downsample (:45-49, expressed as a
+ * k2 s2 conv) on the path:
+ *   acc  = sum_taps  W * T(src)                 T = optional silu(GroupNorm-affine) per source
+ *   v    = acc*scale[co] + shift[co]            (bias, folded BN)
+ *   v   += R(residual)                          R = optional silu(affine) of a C8 tensor
+ *   v    = act(v)
+ *   stats[b][tile][co] += (v, v*v)              optional per-channel partial sums for GroupNorm
+ *   y_c8 / y_nchw = v                           either or both
+ */
+typedef struct MfcConvIO {
+  const void* w_packed;
+  const float* scale;        /* [nb*nblk] or NULL (=1) */
+  const float* shift;        /* [nb*nblk] or NULL (=0) */
+  const void* residual;      /* C8 [B][ceil(Cout/8)][Hout][Wout][8] or NULL */
+  const float* res_affine;   /* NULL or [B][ceil(Cout/8)*8][2]               */
+  long long res_batch_stride;
+  void* y_c8;                /* C8 output or NULL                            */
+  long long y_batch_stride;  /* bytes                                        */
+  float* y_nchw;             /* fp32 [B][Cout][Hout][Wout] or NULL           */
+  float* stats;              /* [B][tiles_per_image][nb*nblk][2] or NULL     */
+} MfcConvIO;
+int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream);
+
+/* GroupNorm statistics -> per-(sample,channel) affine.  Replaces nn.GroupNorm
+ * (models/resunet.py:72,77) split in two: partial sums come from the producing conv's
+ * epilogue, this finalises them (fp64) into scale = g*rstd, shift = b - mean*g*rstd. */
+int mfc_gn_finalize(const float* stats, int B, int tiles_per_image, int cpad, int C, int groups,
+                    long long pixels, const float* gamma, const float* beta, float eps,
+                    float* affine /*[B][ceil(C/8)*8][2]*/, void* stream);
+
+/* out = silu(a*scale+shift) + r   (ResnetBlock tail with identity res_conv,
+ * models/resunet.py:90-95).  All C8 [B][chunks][H][W][8]. */
+int mfc_affine_silu_add(const void* a, const float* affine, const void* r, void* out,
+                        int B, int chunks, long long pixels, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Temporal fusion pieces.
+ * ---------------------------------------------------------------------------------- */
+
+/* Flow warp of MultiFrameNetBasic (models/multiframe_model.py:89-170): bilinear
+ * grid_sample(align_corners=True, zeros) of frame i>=1 class maps and depth at
+ *   grid[:,:,:H,:W] + flow/((W-1)/2,(H-1)/2)   (the stored 576x720 grid, cropped).
+ * seg: C8 plane per frame (nchunks_seg planes each); flow: fp32 NCHW (B,2,H,W) per frame;
+ * depth: fp32 NCHW (B,1,H,W) per frame or NULL.  Outputs: warped seg planes (frame 0 is
+ * passed through by the caller, zero-copy) and one C8 depth plane (d0, warped d1..dK-1). */
+typedef struct MfcWarpArgs {
+  int B, H, W, K;
+  int seg_chunks;                   /* planes per frame (ceil(N/8))              */
+  int grid_h, grid_w;               /* 576, 720                                  */
+  const float* grid;                /* (1,2,grid_h,grid_w) fp32                  */
+  const void* seg[MFC_MAX_SRC];     /* per frame i (i=0 unused), C8             */
+  long long seg_bstride[MFC_MAX_SRC];
+  const float* flow[MFC_MAX_SRC];   /* flow[i-1] for frame i: (B,2,H,W) fp32    */
+  long long flow_bstride[MFC_MAX_SRC];   /* elements between samples of flow[i]   */
+  const float* depth[MFC_MAX_SRC];  /* per frame (B,1,H,W) fp32 or NULL          */
+  long long depth_bstride[MFC_MAX_SRC];  /* elements between samples of depth[i]  */
+  void* seg_out[MFC_MAX_SRC];       /* per frame i>=1, C8                        */
+  long long seg_out_bstride[MFC_MAX_SRC];
+  void* depth_out;                  /* one C8 plane or NULL                      */
+  long long depth_out_bstride;
+  int dtype;
+} MfcWarpArgs;
+int mfc_flow_warp(const MfcWarpArgs* a, void* stream);
+
+/* Heat-map head (F.log_softmax call sites src/engine.py:65,141;
+ * scripts/test_multiframe_segmentation_on_videos_v3.py:281,289): one pass over fp32 NCHW
+ * logits -> log-probs and/or probs (exp of log-probs) and the first-max argmax (uint8). */
+int mfc_heatmap_head(const float* logits, int B, int N, long long pixels,
+                     float* logp /*or NULL*/, float* prob /*or NULL*/, uint8_t* argmax /*or NULL*/,
+                     void* stream);
+
+/* numpy.argmax(axis=1) of a (B,N,pixels) fp32 map as uint8: the first maximum wins
+ * (scripts/test_multiframe_segmentation_on_videos_v3.py:289, utils/localization_utils_v2.py:201). */
+int mfc_argmax_u8(const float* x, int B, int N, long long pixels, uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * UnFlow correlation cost volume (models/unflow_correlation.py:10-105,282-337).
+ * first/second: fp32 NCHW contiguous; out: fp32 [B][D*D][H][W], D = 2*(max_disp/stride2)+1,
+ * out[b,(iy*D+ix),y,x] = mean_c first[b,c,y,x]*second[b,c,y+dy,x+dx], zero outside.
+ * exact_order != 0 reproduces the reference's summation order bit-for-bit
+ * (32 strided partial FMA chains, serial lane add, one divide).
+ * ---------------------------------------------------------------------------------- */
+int mfc_correlation_fwd(const float* first, const float* second, float* out,
+                        int B, int C, int H, int W, int max_disp, int stride2, int exact_order,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Key-point extraction (utils/localization_utils_v2.py:5-40).
+ * ---------------------------------------------------------------------------------- */
+
+/* scipy.ndimage.gaussian_filter(heat, sigma) semantics: radius int(4*sigma+0.5), reflect
+ * boundary, axis 0 then axis 1, fp64 accumulation, fp32 store after each axis.
+ * weights: the 2*radius+1 fp64 taps (host computes them exactly as scipy does).
+ * tmp: fp32 scratch of the same size. */
+int mfc_gaussian_blur(const float* heat, float* tmp, float* out, int B, int H, int W,
+                      const double* weights_dev, int radius, void* stream);
+
+/* localmax = (maximum_filter(sm, footprint) == sm) & blob, as 0/255 uint8.
+ * footprint: fh x fw uint8 (device), scipy origin convention (centre = size//2), reflect. */
+int mfc_localmax_mask(const float* sm, const uint8_t* cls, int cls_id, const uint8_t* footprint,
+                      int fh, int fw, uint8_t* mask, int B, int H, int W, void* stream);
+
+/* (argmax == cls_id) as 0/255 uint8. */
+int mfc_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, long long n, void* stream);
+
+/* cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + contourArea + moments on ONE 0/255
+ * mask (H x W), restricted to what calc_centroids (utils/localization_utils_v2.py:15-33) needs.
+ * For every external contour one record of 6 doubles is appended (in no particular order):
+ *   {a00, a10, a01, first_x, first_y, npoints}
+ * a00/a10/a01 are the exact integer Green's-theorem sums of the closed border polygon, from
+ * which the caller derives, with OpenCV's own formulas,
+ *   contourArea = |a00| * 0.5,  m00 = a00 * (+-0.5),  m10 = a10 * (+-1/6),  m01 = a01 * (+-1/6)
+ * (sign of a00); (first_x, first_y) is the contour's first point = the component's raster-first
+ * pixel, so OpenCV's output order is "descending first_y*W+first_x".  *n_out (device int)
+ * receives the TOTAL number of external contours; records beyond max_contours are dropped.
+ * labels: int32 scratch [2*H*W]. */
+int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours,
+                       int* n_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Command list: one C call issues a whole pre-built forward (the per-frame SFC pass is
+ * ~60 launches).  Replaces the Python-level op-by-op dispatch of nn.Module.forward
+ * (models/resunet.py:153-180, models/multiframe_model.py:424-438).  The structs the
+ * commands point at are owned by the caller and must stay alive during the call only.
+ * ---------------------------------------------------------------------------------- */
+#define MFC_OP_CONV 1            /* a = MfcConvDesc*, b = MfcConvIO*  */
+#define MFC_OP_GN_FINALIZE 2     /* a = MfcGnArgs*                    */
+#define MFC_OP_AFFINE_SILU_ADD 3 /* a = MfcAddArgs*                   */
+#define MFC_OP_GATHER 4          /* a = MfcGatherArgs*                */
+#define MFC_OP_WARP 5            /* a = MfcWarpArgs*                  */
+
+typedef struct MfcGnArgs {
+  const float* stats;
+  const float* gamma;
+  const float* beta;
+  float* affine;
+  long long pixels;
+  int B, tiles_per_image, cpad, C, groups;
+  float eps;
+} MfcGnArgs;
+
+typedef struct MfcAddArgs {
+  const void* a;
+  const float* affine;
+  const void* r;
+  void* out;
+  long long pixels;
+  int B, chunks, dtype;
+  int reserved;
+} MfcAddArgs;
+
+typedef struct MfcGatherArgs {
+  MfcGather g;
+  void* dst;
+  long long dst_bstride_bytes;
+  int B, H, W, dtype;
+} MfcGatherArgs;
+
+typedef struct MfcCmd {
+  int op;
+  int reserved;
+  const void* a;
+  const void* b;
+} MfcCmd;
+
+int mfc_run_list(const MfcCmd* cmds, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFCNET_B200_H_ */

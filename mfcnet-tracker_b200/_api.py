@@ -1,0 +1,33 @@
+"""Public API of the package (re-exported by ``mfcnet_tracker_b200``)."""
+from . import abi, engine
+from .correlation import FunctionCorrelation, ModuleCorrelation, correlation
+from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
+from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxima_and_estimate_centroids, gaussian_blur,
+                      heatmap_head, predicted_keypoints)
+from .multiframe import ResUNetMultiBasic, ResUNetMultiLarge
+from .resunet import ResUnet_VB
+
+__all__ = ["abi", "engine", "ResUnet_VB", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
+           "FunctionCorrelation", "ModuleCorrelation", "correlation", "heatmap_head", "create_circular_mask", "calc_centroids",
+           "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
+           "get_tooltip_segmentation_model", "get_multiframe_segmentation_model"]
+
+
+def get_tooltip_segmentation_model(args):
+    """Factory with the reference's signature (models/__init__.py:23-52).  Model types served by
+    the B200 engine: 'ResUNet' (absent upstream)."""
+    if args.model_type == "ResUNet":
+        return ResUnet_VB(channels=3, dim=getattr(args, "resunet_dim", 16), out_dim=args.num_classes)
+    raise ValueError(f"Model type {args.model_type} not recognized")
+
+
+def get_multiframe_segmentation_model(args):
+    """Factory with the reference's signature (models/__init__.py:54-87)."""
+    kw = dict(num_classes=args.num_classes, num_frames=args.num_input_frames, pretrained=getattr(args, "pretrained", False),
+              loadpath=getattr(args, "load_wts_base_model", None), optflow_inputs=args.add_optflow_inputs,
+              depth_inputs=args.add_depth_inputs)
+    if args.model_type == "ResUNetMulti-Basic":
+        return ResUNetMultiBasic(**kw)
+    if args.model_type == "ResUNetMulti-Large":
+        return ResUNetMultiLarge(**kw)
+    raise ValueError(f"Model type {args.model_type} not recognized")

@@ -1,0 +1,148 @@
+"""ctypes binding of libmfcnet_b200.so (include/mfcnet_b200.h).
+
+This is the only place the Python host touches native code.  There is no fallback: if the
+library is missing (and cannot be built because nvcc is absent) or the device is not a B200,
+loading / calling raises.
+"""
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+MFC_F16, MFC_BF16 = 0, 1
+MFC_MAX_SRC = 8
+OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP = 1, 2, 3, 4, 5
+
+c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+
+class MfcGather(C.Structure):
+    _fields_ = [("plane", c_void_p * 8), ("plane_bstride", c_ll * 8)]
+
+
+class MfcConvInfo(C.Structure):
+    _fields_ = [("nb", c_int), ("nblk", c_int), ("cin_chunks", c_int), ("ksteps", c_int), ("tile_h", c_int),
+                ("tile_w", c_int), ("tiles_per_image", c_int), ("runs", c_int), ("kstages", c_int),
+                ("smem_bytes", c_int), ("tmem_cols", c_int), ("packed_weight_bytes", c_ll)]
+
+
+class MfcSrc(C.Structure):
+    _fields_ = [("ptr", c_void_p), ("affine", c_void_p), ("batch_stride", c_ll), ("nchunks", c_int), ("reserved", c_int)]
+
+
+class MfcConvDesc(C.Structure):
+    _fields_ = [("B", c_int), ("Hin", c_int), ("Win", c_int), ("Hout", c_int), ("Wout", c_int), ("Cout", c_int),
+                ("kh", c_int), ("kw", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int), ("act", c_int),
+                ("dtype", c_int), ("nsrc", c_int), ("src", MfcSrc * MFC_MAX_SRC)]
+
+
+class MfcConvIO(C.Structure):
+    _fields_ = [("w_packed", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("residual", c_void_p),
+                ("res_affine", c_void_p), ("res_batch_stride", c_ll), ("y_c8", c_void_p), ("y_batch_stride", c_ll),
+                ("y_nchw", c_void_p), ("stats", c_void_p)]
+
+
+class MfcWarpArgs(C.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("K", c_int), ("seg_chunks", c_int), ("grid_h", c_int),
+                ("grid_w", c_int), ("grid", c_void_p), ("seg", c_void_p * MFC_MAX_SRC), ("seg_bstride", c_ll * MFC_MAX_SRC),
+                ("flow", c_void_p * MFC_MAX_SRC), ("flow_bstride", c_ll * MFC_MAX_SRC), ("depth", c_void_p * MFC_MAX_SRC),
+                ("depth_bstride", c_ll * MFC_MAX_SRC), ("seg_out", c_void_p * MFC_MAX_SRC),
+                ("seg_out_bstride", c_ll * MFC_MAX_SRC), ("depth_out", c_void_p), ("depth_out_bstride", c_ll),
+                ("dtype", c_int)]
+
+
+class MfcGnArgs(C.Structure):
+    _fields_ = [("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("affine", c_void_p), ("pixels", c_ll),
+                ("B", c_int), ("tiles_per_image", c_int), ("cpad", c_int), ("C", c_int), ("groups", c_int), ("eps", c_float)]
+
+
+class MfcAddArgs(C.Structure):
+    _fields_ = [("a", c_void_p), ("affine", c_void_p), ("r", c_void_p), ("out", c_void_p), ("pixels", c_ll),
+                ("B", c_int), ("chunks", c_int), ("dtype", c_int), ("reserved", c_int)]
+
+
+class MfcGatherArgs(C.Structure):
+    _fields_ = [("g", MfcGather), ("dst", c_void_p), ("dst_bstride_bytes", c_ll), ("B", c_int), ("H", c_int),
+                ("W", c_int), ("dtype", c_int)]
+
+
+class MfcCmd(C.Structure):
+    _fields_ = [("op", c_int), ("reserved", c_int), ("a", c_void_p), ("b", c_void_p)]
+
+
+_SIGNATURES = {
+    "mfc_abi_version": ([], c_int),
+    "mfc_last_error": ([], C.c_char_p),
+    "mfc_device_check": ([c_int], c_int),
+    "mfc_gather_nchw_to_c8": ([C.POINTER(MfcGather), c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_c8_to_nchw": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_weight_standardize": ([c_void_p, c_void_p, c_int, c_int, c_float, c_void_p], c_int),
+    "mfc_bn_fold": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p], c_int),
+    "mfc_conv2d_query": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvInfo)], c_int),
+    "mfc_conv2d_pack_weights": ([C.POINTER(MfcConvDesc), c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
+    "mfc_conv2d_fwd": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p], c_int),
+    "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
+    "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p], c_int),
+    "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),
+    "mfc_heatmap_head": ([c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "mfc_argmax_u8": ([c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p], c_int),
+    "mfc_correlation_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_gaussian_blur": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p], c_int),
+    "mfc_localmax_mask": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_class_mask": ([c_void_p, c_int, c_void_p, c_ll, c_void_p], c_int),
+    "mfc_trace_contours": ([c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p], c_int),
+    "mfc_run_list": ([C.POINTER(MfcCmd), c_int, c_void_p], c_int),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class MfcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmfcnet_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if the .so is stale and nvcc exists) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if build_if_missing and _build.is_stale():
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc on the GPU box: the prebuilt .so must be there
+                if not os.path.exists(path):
+                    raise RuntimeError("libmfcnet_b200.so is missing and could not be built: %s" % e)
+        if not os.path.exists(path):
+            raise RuntimeError("libmfcnet_b200.so not found at %s; run `python __graft_entry__.py build`" % path)
+        lib = C.CDLL(path)
+        for name, (args, res) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.argtypes = args
+            fn.restype = res
+        if lib.mfc_abi_version() != 1:
+            raise RuntimeError("libmfcnet_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MfcError(rc, (_lib.mfc_last_error() or b"").decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,348 @@
+// api.cu -- the C ABI of libmfcnet_b200.so (include/mfcnet_b200.h): argument validation, the conv
+// planner cache, and dispatch into the kernel launchers.  No allocation, no synchronisation.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(MFC_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// 0 when the CURRENT device is compute capability 10.x.  Cached per device.
+int arch_ok() {
+  static int cache[64];  // 0 unknown, 1 ok, 2 bad
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= 64) return fail(MFC_EINVAL, "device index %d out of range", dev);
+  if (cache[dev] == 0) {
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    cache[dev] = (major == 10) ? 1 : 2;
+  }
+  if (cache[dev] != 1)
+    return fail(MFC_EARCH, "device %d is not sm_100 (B200); libmfcnet_b200 has no fallback path", dev);
+  return MFC_OK;
+}
+
+#define MFC_REQUIRE_ARCH()          \
+  do {                              \
+    int rc_ = arch_ok();            \
+    if (rc_ != MFC_OK) return rc_;  \
+  } while (0)
+
+#define MFC_LAUNCH(expr, what)                       \
+  do {                                               \
+    cudaError_t e_ = (expr);                         \
+    if (e_ != cudaSuccess) return cuda_fail(e_, what); \
+    return MFC_OK;                                   \
+  } while (0)
+
+inline bool dtype_ok(int dt) { return dt == MFC_F16 || dt == MFC_BF16; }
+
+// ---- conv planner cache ---------------------------------------------------------------------
+using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int, int, int, int>;
+std::mutex g_plan_mu;
+std::map<PlanKey, mfc::ConvTiling> g_plans;
+
+int validate_desc(const MfcConvDesc* d) {
+  if (!d) return fail(MFC_EINVAL, "conv: null descriptor");
+  if (d->B < 1 || d->Hin < 1 || d->Win < 1 || d->Hout < 1 || d->Wout < 1 || d->Cout < 1)
+    return fail(MFC_EINVAL, "conv: non-positive dimension");
+  if (d->kh < 1 || d->kw < 1 || d->kh > 11 || d->kw > 11) return fail(MFC_EINVAL, "conv: kernel %dx%d unsupported", d->kh, d->kw);
+  if (d->stride != 1 && d->stride != 2) return fail(MFC_EINVAL, "conv: stride %d unsupported", d->stride);
+  if (d->upsample != 1 && d->upsample != 2) return fail(MFC_EINVAL, "conv: upsample %d unsupported", d->upsample);
+  if (d->act != 0 && d->act != 1) return fail(MFC_EINVAL, "conv: act %d unsupported", d->act);
+  if (!dtype_ok(d->dtype)) return fail(MFC_EINVAL, "conv: dtype %d unsupported", d->dtype);
+  if (d->nsrc < 1 || d->nsrc > MFC_MAX_SRC) return fail(MFC_EINVAL, "conv: nsrc %d out of range", d->nsrc);
+  if (d->pad < 0 || d->pad > 5) return fail(MFC_EINVAL, "conv: pad %d unsupported", d->pad);
+  const int Hup = d->Hin * d->upsample, Wup = d->Win * d->upsample;
+  const int ho = (Hup + 2 * d->pad - d->kh) / d->stride + 1, wo = (Wup + 2 * d->pad - d->kw) / d->stride + 1;
+  if (ho != d->Hout || wo != d->Wout)
+    return fail(MFC_EINVAL, "conv: Hout/Wout %dx%d inconsistent with input %dx%d (expected %dx%d)", d->Hout, d->Wout, Hup, Wup, ho, wo);
+  for (int i = 0; i < d->nsrc; ++i)
+    if (d->src[i].nchunks < 1) return fail(MFC_EINVAL, "conv: source %d has no channel planes", i);
+  return MFC_OK;
+}
+
+int get_tiling(const MfcConvDesc* d, mfc::ConvTiling* out) {
+  int chunks = 0;
+  for (int i = 0; i < d->nsrc; ++i) chunks += d->src[i].nchunks;
+  PlanKey key{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks};
+  {
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) {
+      *out = it->second;
+      return MFC_OK;
+    }
+  }
+  mfc::ConvTiling t;
+  memset(&t, 0, sizeof(t));
+  if (!mfc::conv_choose_tiling(*d, t)) return fail(MFC_EINVAL, "conv: no tiling fits shared memory / TMEM for this shape");
+  {
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    g_plans[key] = t;
+  }
+  *out = t;
+  return MFC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mfc_abi_version(void) { return MFC_ABI_VERSION; }
+const char* mfc_last_error(void) { return g_err; }
+
+int mfc_device_check(int device) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (major != 10) return fail(MFC_EARCH, "device %d has compute capability major %d, need 10 (B200)", device, major);
+  return MFC_OK;
+}
+
+// ---- layout ------------------------------------------------------------------------------------
+int mfc_gather_nchw_to_c8(const MfcGather* g, void* dst_chunk, long long dst_bstride_bytes, int B, int H, int W, int dtype,
+                          void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!g || !dst_chunk || B < 1 || H < 1 || W < 1 || !dtype_ok(dtype)) return fail(MFC_EINVAL, "gather: bad argument");
+  MFC_LAUNCH(mfc::launch_gather(*g, dst_chunk, dst_bstride_bytes, B, H, W, dtype == MFC_BF16, (cudaStream_t)stream), "gather");
+}
+
+int mfc_c8_to_nchw(const void* src, long long src_bstride_bytes, float* dst, int B, int C, int H, int W, int dtype, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!src || !dst || B < 1 || C < 1 || H < 1 || W < 1 || !dtype_ok(dtype)) return fail(MFC_EINVAL, "c8_to_nchw: bad argument");
+  MFC_LAUNCH(mfc::launch_c8_to_nchw(src, src_bstride_bytes, dst, B, C, H, W, dtype == MFC_BF16, (cudaStream_t)stream), "c8_to_nchw");
+}
+
+// ---- weights -----------------------------------------------------------------------------------
+int mfc_weight_standardize(const float* w, float* out, int Cout, int fan_in, float eps, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!w || !out || Cout < 1 || fan_in < 1) return fail(MFC_EINVAL, "weight_standardize: bad argument");
+  MFC_LAUNCH(mfc::launch_weight_standardize(w, out, Cout, fan_in, eps, (cudaStream_t)stream), "weight_standardize");
+}
+
+int mfc_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps,
+                float* scale, float* shift, int C, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!gamma || !beta || !mean || !var || !scale || !shift || C < 1) return fail(MFC_EINVAL, "bn_fold: bad argument");
+  MFC_LAUNCH(mfc::launch_bn_fold(gamma, beta, mean, var, conv_bias, eps, scale, shift, C, (cudaStream_t)stream), "bn_fold");
+}
+
+int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info) {
+  int rc = validate_desc(d);
+  if (rc != MFC_OK) return rc;
+  if (!info) return fail(MFC_EINVAL, "conv_query: null info");
+  mfc::ConvTiling t;
+  rc = get_tiling(d, &t);
+  if (rc != MFC_OK) return rc;
+  info->nb = t.NB;
+  info->nblk = t.nblk;
+  info->cin_chunks = t.cin_chunks;
+  info->ksteps = t.ksteps;
+  info->tile_h = t.TH;
+  info->tile_w = t.TW;
+  info->tiles_per_image = t.tiles_x * t.tiles_y;
+  info->runs = t.R;
+  info->kstages = t.kstages;
+  info->smem_bytes = (int)t.smem_bytes;
+  info->tmem_cols = (int)t.tmem_cols;
+  info->packed_weight_bytes = (long long)t.nblk * t.ksteps * d->kh * d->kw * 2 * t.NB * 16;
+  return MFC_OK;
+}
+
+int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w, const int* chan_map, void* packed, void* stream) {
+  MFC_REQUIRE_ARCH();
+  int rc = validate_desc(d);
+  if (rc != MFC_OK) return rc;
+  if (!w_oihw || !packed || Cin_w < 1) return fail(MFC_EINVAL, "conv_pack: bad argument");
+  mfc::ConvTiling t;
+  rc = get_tiling(d, &t);
+  if (rc != MFC_OK) return rc;
+  MFC_LAUNCH(mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, d->kh * d->kw, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk, packed,
+                                      d->dtype == MFC_BF16, (cudaStream_t)stream),
+             "conv_pack");
+}
+
+int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
+  MFC_REQUIRE_ARCH();
+  int rc = validate_desc(d);
+  if (rc != MFC_OK) return rc;
+  if (!io || !io->w_packed) return fail(MFC_EINVAL, "conv: null io / weights");
+  if (!io->y_c8 && !io->y_nchw) return fail(MFC_EINVAL, "conv: no output buffer");
+  mfc::ConvParams p;
+  memset(&p, 0, sizeof(p));
+  rc = get_tiling(d, &p.t);
+  if (rc != MFC_OK) return rc;
+  p.B = d->B; p.Hin = d->Hin; p.Win = d->Win; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.upsample = d->upsample; p.act = d->act;
+  p.nsrc = d->nsrc;
+  int end = 0;
+  for (int i = 0; i < MFC_MAX_SRC; ++i) {
+    if (i < d->nsrc) {
+      if (!d->src[i].ptr) return fail(MFC_EINVAL, "conv: source %d is null", i);
+      if (((uintptr_t)d->src[i].ptr & 15) || (d->src[i].batch_stride & 15)) return fail(MFC_EINVAL, "conv: source %d not 16-byte aligned", i);
+      p.src_ptr[i] = (const uint8_t*)d->src[i].ptr;
+      p.src_aff[i] = d->src[i].affine;
+      p.src_bs[i] = d->src[i].batch_stride;
+      end += d->src[i].nchunks;
+    }
+    p.src_end[i] = end;
+  }
+  p.divP = mfc::make_fastdiv((uint32_t)p.t.P);
+  p.idesc = mfc::make_idesc_f16(p.t.NB, d->dtype == MFC_BF16);
+  p.w = (const uint8_t*)io->w_packed;
+  p.scale = io->scale;
+  p.shift = io->shift;
+  p.res = (const uint8_t*)io->residual;
+  p.res_aff = io->res_affine;
+  p.res_bs = io->res_batch_stride;
+  p.y = (uint8_t*)io->y_c8;
+  p.y_bs = io->y_batch_stride;
+  p.y_nchw = io->y_nchw;
+  p.stats = io->stats;
+  if (((uintptr_t)p.w & 15) || ((uintptr_t)p.y & 15) || ((uintptr_t)p.res & 15) || (p.y_bs & 15) || (p.res_bs & 15))
+    return fail(MFC_EINVAL, "conv: weights / output / residual not 16-byte aligned");
+  MFC_LAUNCH(mfc::launch_conv(p, d->dtype == MFC_BF16, (cudaStream_t)stream), "conv2d_fwd");
+}
+
+int mfc_gn_finalize(const float* stats, int B, int tiles_per_image, int cpad, int C, int groups, long long pixels, const float* gamma,
+                    const float* beta, float eps, float* affine, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!stats || !gamma || !beta || !affine || B < 1 || tiles_per_image < 1 || C < 1 || groups < 1 || C % groups || cpad < C || pixels < 1)
+    return fail(MFC_EINVAL, "gn_finalize: bad argument");
+  MFC_LAUNCH(mfc::launch_gn_finalize(stats, B, tiles_per_image, cpad, C, groups, pixels, gamma, beta, eps, affine, (cudaStream_t)stream),
+             "gn_finalize");
+}
+
+int mfc_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks, long long pixels, int dtype,
+                        void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!a || !affine || !r || !out || B < 1 || chunks < 1 || pixels < 1 || !dtype_ok(dtype)) return fail(MFC_EINVAL, "affine_silu_add: bad argument");
+  MFC_LAUNCH(mfc::launch_affine_silu_add(a, affine, r, out, B, chunks, pixels, dtype == MFC_BF16, (cudaStream_t)stream), "affine_silu_add");
+}
+
+// ---- fusion ------------------------------------------------------------------------------------
+int mfc_flow_warp(const MfcWarpArgs* a, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!a || a->B < 1 || a->H < 2 || a->W < 2 || a->K < 2 || a->K > MFC_MAX_SRC || !a->grid || a->seg_chunks < 0 || !dtype_ok(a->dtype))
+    return fail(MFC_EINVAL, "flow_warp: bad argument");
+  if (a->H > a->grid_h || a->W > a->grid_w) return fail(MFC_EINVAL, "flow_warp: %dx%d exceeds the stored %dx%d grid", a->H, a->W, a->grid_h, a->grid_w);
+  for (int f = 1; f < a->K; ++f) {
+    if (!a->flow[f - 1]) return fail(MFC_EINVAL, "flow_warp: flow %d is null", f - 1);
+    if (a->seg_chunks > 0 && (!a->seg[f] || !a->seg_out[f])) return fail(MFC_EINVAL, "flow_warp: seg/seg_out %d is null", f);
+  }
+  MFC_LAUNCH(mfc::launch_flow_warp(*a, (cudaStream_t)stream), "flow_warp");
+}
+
+int mfc_heatmap_head(const float* logits, int B, int N, long long pixels, float* logp, float* prob, uint8_t* argmax, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!logits || B < 1 || N < 1 || N > 255 || pixels < 1) return fail(MFC_EINVAL, "heatmap_head: bad argument");
+  MFC_LAUNCH(mfc::launch_heatmap_head(logits, B, N, pixels, logp, prob, argmax, (cudaStream_t)stream), "heatmap_head");
+}
+
+int mfc_argmax_u8(const float* x, int B, int N, long long pixels, uint8_t* out, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!x || !out || B < 1 || N < 1 || N > 255 || pixels < 1) return fail(MFC_EINVAL, "argmax_u8: bad argument");
+  MFC_LAUNCH(mfc::launch_argmax_u8(x, B, N, pixels, out, (cudaStream_t)stream), "argmax_u8");
+}
+
+// ---- correlation -------------------------------------------------------------------------------
+int mfc_correlation_fwd(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp, int stride2,
+                        int exact_order, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!first || !second || !out || B < 1 || C < 1 || H < 1 || W < 1) return fail(MFC_EINVAL, "correlation: bad argument");
+  if (stride2 != 1 && stride2 != 2) return fail(MFC_EINVAL, "correlation: stride2 %d unsupported (1 or 2)", stride2);
+  if (max_disp < 0 || max_disp > 32 || max_disp % stride2) return fail(MFC_EINVAL, "correlation: max_disp %d unsupported", max_disp);
+  MFC_LAUNCH(mfc::launch_correlation(first, second, out, B, C, H, W, max_disp, stride2, exact_order, (cudaStream_t)stream), "correlation");
+}
+
+// ---- key points --------------------------------------------------------------------------------
+int mfc_gaussian_blur(const float* heat, float* tmp, float* out, int B, int H, int W, const double* weights_dev, int radius, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!heat || !tmp || !out || !weights_dev || B < 1 || H < 1 || W < 1 || radius < 0 || radius > 64) return fail(MFC_EINVAL, "gaussian_blur: bad argument");
+  MFC_LAUNCH(mfc::launch_gaussian_blur(heat, tmp, out, B, H, W, weights_dev, radius, (cudaStream_t)stream), "gaussian_blur");
+}
+
+int mfc_localmax_mask(const float* sm, const uint8_t* cls, int cls_id, const uint8_t* footprint, int fh, int fw, uint8_t* mask, int B,
+                      int H, int W, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!sm || !cls || !footprint || !mask || fh < 1 || fw < 1 || fh > 31 || fw > 31 || B < 1 || H < 1 || W < 1)
+    return fail(MFC_EINVAL, "localmax_mask: bad argument");
+  MFC_LAUNCH(mfc::launch_localmax_mask(sm, cls, cls_id, footprint, fh, fw, mask, B, H, W, (cudaStream_t)stream), "localmax_mask");
+}
+
+int mfc_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, long long n, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!cls || !mask || n < 1) return fail(MFC_EINVAL, "class_mask: bad argument");
+  MFC_LAUNCH(mfc::launch_class_mask(cls, cls_id, mask, n, (cudaStream_t)stream), "class_mask");
+}
+
+int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours, int* n_out, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!mask || !labels || !out || !n_out || H < 1 || W < 1 || max_contours < 1) return fail(MFC_EINVAL, "trace_contours: bad argument");
+  MFC_LAUNCH(mfc::launch_trace_contours(mask, H, W, labels, out, max_contours, n_out, (cudaStream_t)stream), "trace_contours");
+}
+
+// ---- command list ------------------------------------------------------------------------------
+int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
+  if (!cmds || n < 0) return fail(MFC_EINVAL, "run_list: bad argument");
+  for (int i = 0; i < n; ++i) {
+    const MfcCmd& c = cmds[i];
+    int rc = MFC_OK;
+    switch (c.op) {
+      case MFC_OP_CONV:
+        rc = mfc_conv2d_fwd((const MfcConvDesc*)c.a, (const MfcConvIO*)c.b, stream);
+        break;
+      case MFC_OP_GN_FINALIZE: {
+        const MfcGnArgs* g = (const MfcGnArgs*)c.a;
+        rc = mfc_gn_finalize(g->stats, g->B, g->tiles_per_image, g->cpad, g->C, g->groups, g->pixels, g->gamma, g->beta, g->eps, g->affine, stream);
+        break;
+      }
+      case MFC_OP_AFFINE_SILU_ADD: {
+        const MfcAddArgs* g = (const MfcAddArgs*)c.a;
+        rc = mfc_affine_silu_add(g->a, g->affine, g->r, g->out, g->B, g->chunks, g->pixels, g->dtype, stream);
+        break;
+      }
+      case MFC_OP_GATHER: {
+        const MfcGatherArgs* g = (const MfcGatherArgs*)c.a;
+        rc = mfc_gather_nchw_to_c8(&g->g, g->dst, g->dst_bstride_bytes, g->B, g->H, g->W, g->dtype, stream);
+        break;
+      }
+      case MFC_OP_WARP:
+        rc = mfc_flow_warp((const MfcWarpArgs*)c.a, stream);
+        break;
+      default:
+        rc = fail(MFC_EINVAL, "run_list: unknown op %d at %d", c.op, i);
+    }
+    if (rc != MFC_OK) {
+      char tmp[400];
+      strncpy(tmp, g_err, sizeof(tmp) - 1);
+      tmp[sizeof(tmp) - 1] = 0;
+      return fail(rc, "run_list[%d] op %d: %s", i, c.op, tmp);
+    }
+  }
+  return MFC_OK;
+}
+
+}  // extern "C"

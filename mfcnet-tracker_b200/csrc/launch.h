@@ -1,0 +1,47 @@
+// launch.h -- internal launcher prototypes shared between the kernel translation units and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mfcnet_b200.h"
+#include "conv_tc.cuh"
+
+namespace mfc {
+
+// conv_tc.cu
+cudaError_t launch_conv(const ConvParams& p, bool bf16, cudaStream_t st);
+cudaError_t launch_pack_weights(const float* w, int Cout, int Cin_w, int taps, const int* chan_map, int cin_chunks,
+                                int ksteps, int NB, int nblk, void* out, bool bf16, cudaStream_t st);
+
+// pointwise.cu
+cudaError_t launch_gather(const MfcGather& g, void* dst, long long dst_bs, int B, int H, int W, bool bf16, cudaStream_t st);
+cudaError_t launch_c8_to_nchw(const void* src, long long src_bs, float* dst, int B, int C, int H, int W, bool bf16, cudaStream_t st);
+cudaError_t launch_weight_standardize(const float* w, float* out, int Cout, int fan_in, float eps, cudaStream_t st);
+cudaError_t launch_bn_fold(const float* g, const float* b, const float* m, const float* v, const float* cb, float eps,
+                           float* scale, float* shift, int C, cudaStream_t st);
+cudaError_t launch_gn_finalize(const float* stats, int B, int tiles, int cpad, int C, int groups, long long pixels,
+                               const float* gamma, const float* beta, float eps, float* affine, cudaStream_t st);
+cudaError_t launch_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks,
+                                   long long pixels, bool bf16, cudaStream_t st);
+
+// fusion_ops.cu
+cudaError_t launch_flow_warp(const MfcWarpArgs& a, cudaStream_t st);
+cudaError_t launch_heatmap_head(const float* logits, int B, int N, long long pixels, float* logp, float* prob, uint8_t* amax,
+                                cudaStream_t st);
+
+cudaError_t launch_argmax_u8(const float* x, int B, int N, long long pixels, uint8_t* out, cudaStream_t st);
+
+// correlation.cu
+cudaError_t launch_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp,
+                               int stride2, int exact_order, cudaStream_t st);
+
+// localize.cu
+cudaError_t launch_gaussian_blur(const float* heat, float* tmp, float* out, int B, int H, int W, const double* w, int radius,
+                                 cudaStream_t st);
+cudaError_t launch_localmax_mask(const float* sm, const uint8_t* cls, int cls_id, const uint8_t* fp, int fh, int fw,
+                                 uint8_t* mask, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, long long n, cudaStream_t st);
+cudaError_t launch_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours, int* n_out,
+                                  cudaStream_t st);
+
+}  // namespace mfc

@@ -1,0 +1,192 @@
+// localize.cu -- heat-map -> key-point kernels (reference: utils/localization_utils_v2.py:5-40).
+//
+//   gaussian blur   scipy.ndimage.gaussian_filter semantics (fp64 accumulate in scipy's order, fp32
+//                   store per axis, reflect boundary)
+//   local maxima    scipy.ndimage.maximum_filter(footprint) == smoothed, AND class blob
+//   contours        8-connected component labelling (union-find, root = raster-first pixel) +
+//                   4-connected background labelling to decide which components are external,
+//                   then one thread per component follows its outer border (localize_core.h)
+// All of it keeps the 6 MB probability maps on the device: the reference copies them to the host
+// twice per frame and runs single-threaded scipy/OpenCV.
+#include "common.cuh"
+#include "launch.h"
+#include "localize_core.h"
+
+namespace mfc {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  // scipy 'reflect' (d c b a | a b c d | d c b a), valid for any offset
+  const int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - 1 - i;
+}
+
+// One pass of scipy's symmetric correlate1d along `axis` (0: rows, 1: columns):
+//   tmp = x[l]*w[r];  for ii = -r..-1: tmp += (x[l+ii] + x[l-ii]) * w[ii+r]      (all in fp64, no FMA)
+__global__ void gauss1d_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int H, int W,
+                               const double* __restrict__ w, int radius, int axis) {
+  const long long total = (long long)B * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const float* img = src + (i / ((long long)H * W)) * H * W;
+    const int n = axis == 0 ? H : W;
+    const int l = axis == 0 ? y : x;
+    const long long stride = axis == 0 ? W : 1;
+    const float* line = img + (axis == 0 ? x : (long long)y * W);
+    double tmp = __dmul_rn((double)line[(long long)l * stride], w[radius]);
+    for (int ii = -radius; ii < 0; ++ii) {
+      const double a = (double)line[(long long)reflect_idx(l + ii, n) * stride];
+      const double b = (double)line[(long long)reflect_idx(l - ii, n) * stride];
+      tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(a, b), w[ii + radius]));
+    }
+    dst[i] = (float)tmp;
+  }
+}
+
+__global__ void localmax_kernel(const float* __restrict__ sm, const uint8_t* __restrict__ cls, int cls_id,
+                                const uint8_t* __restrict__ fp, int fh, int fw, uint8_t* __restrict__ mask, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  const int cy = fh / 2, cx = fw / 2;  // scipy origin 0: centre = size // 2
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const float* img = sm + (i / ((long long)H * W)) * H * W;
+    uint8_t out = 0;
+    if (cls[i] == cls_id) {
+      const float v = img[(long long)y * W + x];
+      float m = -INFINITY;
+      for (int j = 0; j < fh; ++j) {
+        const int yy = reflect_idx(y + j - cy, H);
+        for (int k = 0; k < fw; ++k) {
+          if (fp[j * fw + k]) m = fmaxf(m, img[(long long)yy * W + reflect_idx(x + k - cx, W)]);
+        }
+      }
+      out = (m == v) ? 255 : 0;
+    }
+    mask[i] = out;
+  }
+}
+
+__global__ void class_mask_kernel(const uint8_t* __restrict__ cls, int cls_id, uint8_t* __restrict__ mask, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mask[i] = cls[i] == cls_id ? 255 : 0;
+}
+
+// ---- connected components (union-find; the root of a set is its smallest linear index) ----------
+__device__ __forceinline__ int uf_find(int* lab, int a) {
+  int r = a;
+  while (true) {
+    const int p = reinterpret_cast<volatile int*>(lab)[r];
+    if (p == r) break;
+    r = p;
+  }
+  return r;
+}
+__device__ __forceinline__ void uf_union(int* lab, int a, int b) {
+  while (true) {
+    a = uf_find(lab, a);
+    b = uf_find(lab, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(&lab[a], b);  // a > b: hang a under b
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void ccl_init_kernel(int* __restrict__ lab, int* __restrict__ flag, int n, int* __restrict__ n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    lab[i] = i;
+    flag[i] = 0;
+  }
+  if (i == 0) *n_out = 0;
+}
+
+// foreground: 8-connectivity; background: 4-connectivity (the complement convention of findContours)
+__global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lab, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int x = i % W, y = i / W;
+  const bool fg = mask[i] != 0;
+  if (x > 0 && (mask[i - 1] != 0) == fg) uf_union(lab, i, i - 1);
+  if (y > 0 && (mask[i - W] != 0) == fg) uf_union(lab, i, i - W);
+  if (fg && y > 0) {
+    if (x > 0 && mask[i - W - 1] != 0) uf_union(lab, i, i - W - 1);
+    if (x + 1 < W && mask[i - W + 1] != 0) uf_union(lab, i, i - W + 1);
+  }
+}
+
+__global__ void ccl_flatten_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lab, int* __restrict__ flag, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int r = uf_find(lab, i);
+  lab[i] = r;
+  const int x = i % W, y = i / W;
+  // background regions that touch the image frame are connected to the outside
+  if (mask[i] == 0 && (x == 0 || y == 0 || x == W - 1 || y == H - 1)) flag[r] = 1;
+}
+
+// One thread per component root.  A component is external (RETR_EXTERNAL) iff the background
+// pixel left of its raster-first pixel belongs to a background region that reaches the frame.
+__global__ void trace_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ lab, const int* __restrict__ flag, int H, int W,
+                             double* __restrict__ out, int max_contours, int* __restrict__ n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  if (mask[i] == 0 || lab[i] != i) return;
+  const int x = i % W, y = i / W;
+  if (x > 0 && flag[lab[i - 1]] == 0) return;  // sits in a hole of another component
+  const ContourSums s = trace_outer_border(mask, H, W, x, y, 4LL * H * W + 8);
+  const int slot = atomicAdd(n_out, 1);
+  if (slot < max_contours) {
+    double* o = out + (size_t)slot * 6;
+    o[0] = (double)s.a00;
+    o[1] = (double)s.a10;
+    o[2] = (double)s.a01;
+    o[3] = (double)x;
+    o[4] = (double)y;
+    o[5] = (double)s.npoints;
+  }
+}
+
+static inline int grid_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = (long long)kSmCount * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+cudaError_t launch_gaussian_blur(const float* heat, float* tmp, float* out, int B, int H, int W, const double* w, int radius,
+                                 cudaStream_t st) {
+  const int grid = grid_for((long long)B * H * W, 256);
+  gauss1d_kernel<<<grid, 256, 0, st>>>(heat, tmp, B, H, W, w, radius, 0);
+  gauss1d_kernel<<<grid, 256, 0, st>>>(tmp, out, B, H, W, w, radius, 1);
+  return cudaGetLastError();
+}
+cudaError_t launch_localmax_mask(const float* sm, const uint8_t* cls, int cls_id, const uint8_t* fp, int fh, int fw, uint8_t* mask,
+                                 int B, int H, int W, cudaStream_t st) {
+  localmax_kernel<<<grid_for((long long)B * H * W, 256), 256, 0, st>>>(sm, cls, cls_id, fp, fh, fw, mask, B, H, W);
+  return cudaGetLastError();
+}
+cudaError_t launch_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, long long n, cudaStream_t st) {
+  class_mask_kernel<<<grid_for(n, 256), 256, 0, st>>>(cls, cls_id, mask, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours, int* n_out,
+                                  cudaStream_t st) {
+  const int n = H * W;
+  const int blocks = (n + 255) / 256;
+  int* flag = labels + n;
+  ccl_init_kernel<<<blocks, 256, 0, st>>>(labels, flag, n, n_out);
+  ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, labels, H, W);
+  ccl_flatten_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W);
+  trace_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W, out, max_contours, n_out);
+  return cudaGetLastError();
+}
+
+}  // namespace mfc

@@ -1,0 +1,412 @@
+"""Host-side plan builder: turns a module's layers into a command list for libmfcnet_b200.so.
+
+PyTorch is used for device memory and the current stream only; every arithmetic step of the
+forward is a kernel of the native library, issued by ONE ``mfc_run_list`` call per program.
+
+Activations use the "C8" layout of include/mfcnet_b200.h: ``[B][ceil(C/8)][H][W][8]`` fp16/bf16.
+A channel concat is a list of sources (zero-copy); GroupNorm+SiLU is a pending per-(sample,
+channel) affine that the consuming conv applies while staging its input tile.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import abi
+
+_DTYPES = {"fp16": (torch.float16, abi.MFC_F16), "bf16": (torch.bfloat16, abi.MFC_BF16)}
+
+
+def default_dtype():
+    """Activation / weight storage type of the conv path (accumulation is always fp32).
+    bf16 is the default; MFC_B200_DTYPE=fp16 selects fp16 storage."""
+    return os.environ.get("MFC_B200_DTYPE", "bf16")
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("%s: mfcnet_tracker_b200 runs on a B200 only; got a %s tensor (there is no CPU fallback)"
+                           % (what, t.device.type))
+
+
+class Ext:
+    """An external fp32 NCHW input of a plan: a binding key + the placeholder tensor used at build time."""
+    __slots__ = ("key", "t")
+
+    def __init__(self, key, t):
+        self.key, self.t = key, t
+
+    @property
+    def channels(self):
+        return self.t.shape[1]
+
+
+class Act:
+    """A C8 activation: tensor [B, chunks, H, W, 8] + real channel count + optional pending affine."""
+    __slots__ = ("t", "C", "affine")
+
+    def __init__(self, t, C_, affine=None):
+        self.t, self.C, self.affine = t, C_, affine
+
+    @property
+    def B(self):
+        return self.t.shape[0]
+
+    @property
+    def chunks(self):
+        return self.t.shape[1]
+
+    @property
+    def H(self):
+        return self.t.shape[2]
+
+    @property
+    def W(self):
+        return self.t.shape[3]
+
+    @property
+    def bstride(self):  # bytes between samples
+        return self.t.stride(0) * self.t.element_size()
+
+    def with_affine(self, aff):
+        return Act(self.t, self.C, aff)
+
+    def batch_slice(self, lo, hi):
+        return Act(self.t[lo:hi], self.C, None if self.affine is None else self.affine[lo:hi])
+
+
+class Arena:
+    """Replay allocator: the first program built after construction allocates device tensors;
+    after `reset()` the same sequence of requests returns the SAME tensors, so programs built
+    with an identical allocation sequence (the sub-batches of one forward, which run one after
+    another on one stream) share their intermediate buffers."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.slots = []
+        self.pos = 0
+
+    def reset(self):
+        self.pos = 0
+
+    def alloc(self, shape, dtype, zero=False):
+        shape = tuple(int(s) for s in shape)
+        if self.pos < len(self.slots):
+            t = self.slots[self.pos]
+            if tuple(t.shape) != shape or t.dtype != dtype:
+                raise RuntimeError("arena replay mismatch: %s/%s vs %s/%s" % (tuple(t.shape), t.dtype, shape, dtype))
+        else:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self.slots.append(t)
+        self.pos += 1
+        return t
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.slots)
+
+
+class Program:
+    """A recorded list of native commands plus everything that must stay alive for them."""
+
+    def __init__(self, device, dtype_name):
+        self.lib = abi.load()
+        self.device = torch.device(device)
+        self.dtype_name = dtype_name
+        self.tdtype, self.cdtype = _DTYPES[dtype_name]
+        self.cmds = []       # (op, struct_a, struct_b)
+        self.keep = []       # tensors referenced by raw pointer
+        self._array = None
+        self.n_kernels = 0   # kernel launches one run() issues
+        self.bindings = {}   # external input key -> [setter(tensor)]
+
+    # ---- low-level recording -----------------------------------------------------------------
+    def _push(self, op, a, b=None, launches=1):
+        self.cmds.append((op, a, b))
+        self._array = None
+        self.n_kernels += launches
+
+    def finalize(self):
+        arr = (abi.MfcCmd * len(self.cmds))()
+        for i, (op, a, b) in enumerate(self.cmds):
+            arr[i].op = op
+            arr[i].a = C.cast(C.pointer(a), C.c_void_p)
+            arr[i].b = C.cast(C.pointer(b), C.c_void_p) if b is not None else None
+        self._array = arr
+        return self
+
+    def run(self, stream=None):
+        if self._array is None:
+            self.finalize()
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        abi.check(self.lib.mfc_run_list(self._array, len(self.cmds), stream))
+
+    def extend(self, other):
+        self.cmds += other.cmds
+        self.keep += other.keep
+        self.n_kernels += other.n_kernels
+        self._array = None
+
+    # ---- ops ---------------------------------------------------------------------------------
+    def bind(self, key, setter):
+        """Register `setter(tensor)` to re-point a raw pointer at the caller's tensor `key`."""
+        self.bindings.setdefault(key, []).append(setter)
+
+    def rebind(self, tensors):
+        """tensors: {key: fp32 tensor with contiguous (C,H,W) inner dims}.  Must cover every key."""
+        for key, setters in self.bindings.items():
+            t = tensors[key]
+            if t.dtype != torch.float32 or t.device != self.device:
+                raise ValueError("input %r must be a float32 tensor on %s" % (key, self.device))
+            if t.dim() != 4 or t.stride(3) != 1 or t.stride(2) != t.shape[3] or t.stride(1) != t.shape[2] * t.shape[3]:
+                raise ValueError("input %r must have contiguous (C,H,W) dims" % (key,))
+            for fn in setters:
+                fn(t)
+
+    def gather(self, planes, dst_chunk_tensor, B, H, W):
+        """planes: up to 8 entries of Ext-channel (ext, channel) or None -> one C8 chunk, where
+        ext = Ext(key, placeholder fp32 [B,Cx,H,W] tensor).  The pointers are re-pointed per call
+        through `rebind`."""
+        a = abi.MfcGatherArgs()
+        for j in range(8):
+            p = planes[j] if j < len(planes) else None
+            if p is None:
+                a.g.plane[j] = None
+                a.g.plane_bstride[j] = 0
+            else:
+                ext, ch = p
+                if tuple(ext.t.shape[0:1] + ext.t.shape[2:]) != (B, H, W):
+                    raise ValueError("input %r has shape %s, expected batch %d and %dx%d" % (ext.key, tuple(ext.t.shape), B, H, W))
+
+                def setter(t, a=a, j=j, ch=ch, HW=H * W):
+                    a.g.plane[j] = t.data_ptr() + ch * HW * 4
+                    a.g.plane_bstride[j] = t.stride(0)
+                setter(ext.t)
+                self.bind(ext.key, setter)
+        a.dst = dst_chunk_tensor.data_ptr()
+        a.dst_bstride_bytes = dst_chunk_tensor.stride(0) * dst_chunk_tensor.element_size()
+        a.B, a.H, a.W, a.dtype = B, H, W, self.cdtype
+        self.keep.append(dst_chunk_tensor)
+        self._push(abi.OP_GATHER, a)
+        return a
+
+    def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act):
+        d = abi.MfcConvDesc()
+        s0 = srcs[0]
+        d.B, d.Hin, d.Win = s0.B, s0.H, s0.W
+        Hup, Wup = s0.H * upsample, s0.W * upsample
+        d.Hout = (Hup + 2 * pad - k) // stride + 1
+        d.Wout = (Wup + 2 * pad - k) // stride + 1
+        d.Cout, d.kh, d.kw, d.stride, d.pad, d.upsample, d.act = Cout, k, k, stride, pad, upsample, act
+        d.dtype = self.cdtype
+        if len(srcs) > abi.MFC_MAX_SRC:
+            raise ValueError("too many concat sources")
+        d.nsrc = len(srcs)
+        for i, s in enumerate(srcs):
+            if (s.B, s.H, s.W) != (s0.B, s0.H, s0.W):
+                raise ValueError("concat sources disagree in shape")
+            d.src[i].ptr = s.t.data_ptr()
+            d.src[i].affine = abi.ptr(s.affine)
+            d.src[i].batch_stride = s.bstride
+            d.src[i].nchunks = s.chunks
+        return d
+
+    def query(self, d):
+        info = abi.MfcConvInfo()
+        abi.check(self.lib.mfc_conv2d_query(C.byref(d), C.byref(info)))
+        return info
+
+    def conv(self, d, info, srcs, packed, residual=None, want_stats=False, out_c8=True, out_nchw=None, arena=None,
+             y_c8=None):
+        """Record one fused conv for descriptor `d` (from conv_desc) / `info` (from query).
+        `packed` = PackedConv (weights + scale/shift).  Returns (Act or None, stats or None, io)."""
+        io = abi.MfcConvIO()
+        io.w_packed = packed.w.data_ptr()
+        io.scale = abi.ptr(packed.scale)
+        io.shift = abi.ptr(packed.shift)
+        self.keep += [packed.w, packed.scale, packed.shift]
+        if residual is not None:
+            io.residual = residual.t.data_ptr()
+            io.res_affine = abi.ptr(residual.affine)
+            io.res_batch_stride = residual.bstride
+            self.keep += [residual.t, residual.affine]
+        out = None
+        B, Cout = d.B, d.Cout
+        if out_c8:
+            if y_c8 is None:
+                y_c8 = arena.alloc((B, (Cout + 7) // 8, d.Hout, d.Wout, 8), self.tdtype)
+            out = Act(y_c8, Cout)
+            io.y_c8 = y_c8.data_ptr()
+            io.y_batch_stride = out.bstride
+            self.keep.append(y_c8)
+        if out_nchw is not None:
+            io.y_nchw = out_nchw.data_ptr()
+            self.keep.append(out_nchw)
+        stats = None
+        if want_stats:
+            stats = arena.alloc((B, info.tiles_per_image, info.nb * info.nblk, 2), torch.float32)
+            io.stats = stats.data_ptr()
+            self.keep.append(stats)
+        for s in srcs:
+            self.keep += [s.t, s.affine]
+        self._push(abi.OP_CONV, d, io)
+        return out, stats, io
+
+    def gn_finalize(self, stats, info, gamma, beta, C_, groups, pixels, eps, affine):
+        a = abi.MfcGnArgs()
+        a.stats, a.gamma, a.beta, a.affine = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), affine.data_ptr()
+        a.pixels, a.B, a.tiles_per_image = pixels, stats.shape[0], info.tiles_per_image
+        a.cpad, a.C, a.groups, a.eps = info.nb * info.nblk, C_, groups, eps
+        self.keep += [stats, gamma, beta, affine]
+        self._push(abi.OP_GN_FINALIZE, a)
+        return affine
+
+    def affine_silu_add(self, a_act, r_act, out_t):
+        a = abi.MfcAddArgs()
+        a.a, a.affine, a.r, a.out = a_act.t.data_ptr(), a_act.affine.data_ptr(), r_act.t.data_ptr(), out_t.data_ptr()
+        a.pixels, a.B, a.chunks, a.dtype = a_act.H * a_act.W, a_act.B, a_act.chunks, self.cdtype
+        for t in (a_act.t, r_act.t, out_t):
+            if not t.is_contiguous():
+                raise ValueError("affine_silu_add needs dense C8 tensors")
+        self.keep += [a_act.t, a_act.affine, r_act.t, out_t]
+        self._push(abi.OP_AFFINE_SILU_ADD, a)
+        return Act(out_t, a_act.C)
+
+    def warp(self, args):
+        self._push(abi.OP_WARP, args)
+
+
+class PackedConv:
+    __slots__ = ("w", "scale", "shift")
+
+    def __init__(self, w, scale, shift):
+        self.w, self.scale, self.shift = w, scale, shift
+
+
+def chan_map_for(srcs_channels):
+    """Padded-concat channel -> weight Cin index.  srcs_channels: list of (real_channels, chunks,
+    first_weight_channel)."""
+    m = []
+    for real, chunks, first in srcs_channels:
+        for j in range(chunks * 8):
+            m.append(first + j if j < real else -1)
+    return m
+
+
+class WeightPacker:
+    """Derives the packed / folded device tensors a plan needs from a module's raw parameters.
+    Everything here runs native kernels (weight standardisation, BN fold, bf16/fp16 packing) on
+    the current stream; results are cached per (layer, geometry) until the weights change."""
+
+    def __init__(self, device, dtype_name):
+        self.lib = abi.load()
+        self.device = torch.device(device)
+        self.tdtype, self.cdtype = _DTYPES[dtype_name]
+        self.cache = {}
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def standardized(self, key, w, eps=1e-5):
+        k = ("ws", key)
+        if k not in self.cache:
+            w = w.detach().contiguous().float()
+            out = torch.empty_like(w)
+            abi.check(self.lib.mfc_weight_standardize(w.data_ptr(), out.data_ptr(), w.shape[0], w[0].numel(), eps, self._stream()))
+            self.cache[k] = out
+        return self.cache[k]
+
+    def bn_affine(self, key, bn_w, bn_b, mean, var, eps, conv_bias=None):
+        k = ("bn", key)
+        if k not in self.cache:
+            Cc = bn_w.numel()
+            scale = torch.empty(Cc, dtype=torch.float32, device=self.device)
+            shift = torch.empty(Cc, dtype=torch.float32, device=self.device)
+            f = lambda t: t.detach().contiguous().float()
+            args = [f(bn_w), f(bn_b), f(mean), f(var)]
+            cb = f(conv_bias) if conv_bias is not None else None
+            abi.check(self.lib.mfc_bn_fold(args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(), args[3].data_ptr(),
+                                           abi.ptr(cb), eps, scale.data_ptr(), shift.data_ptr(), Cc, self._stream()))
+            self.cache[k] = (scale, shift, args, cb)
+        return self.cache[k][0], self.cache[k][1]
+
+    def pack(self, key, prog, desc, info, w_oihw, cmap, scale=None, shift=None):
+        """w_oihw fp32 [Cout][Cin_w][kh][kw] device tensor -> PackedConv for this geometry."""
+        k = ("pk", key, info.nb, info.nblk, info.ksteps, tuple(cmap) if cmap is not None else None)
+        if k not in self.cache:
+            w = w_oihw.detach().contiguous().float()
+            packed = torch.empty(int(info.packed_weight_bytes), dtype=torch.uint8, device=self.device)
+            cm = None
+            if cmap is not None:
+                cm = torch.tensor(cmap, dtype=torch.int32, device=self.device)
+            abi.check(self.lib.mfc_conv2d_pack_weights(C.byref(desc), w.data_ptr(), w.shape[1], abi.ptr(cm), packed.data_ptr(),
+                                                       self._stream()))
+            cpad = info.nb * info.nblk
+            sc = sh = None
+            if scale is not None:
+                sc = torch.zeros(cpad, dtype=torch.float32, device=self.device)
+                sc[: scale.numel()] = scale.detach().float()
+            if shift is not None:
+                sh = torch.zeros(cpad, dtype=torch.float32, device=self.device)
+                sh[: shift.numel()] = shift.detach().float()
+            self.cache[k] = (PackedConv(packed, sc, sh), w, cm)
+        return self.cache[k][0]
+
+
+def params_fingerprint(module):
+    """Cheap change detector for a module's parameters and buffers (in-place updates bump
+    `_version`; `.to()` / `load_state_dict(assign=True)` change `data_ptr`)."""
+    h = 0
+    for t in list(module.parameters()) + list(module.buffers()):
+        h = (h * 1000003 + t.data_ptr() * 31 + t._version) & 0xFFFFFFFFFFFFFFF
+    return h
+
+
+class Builder:
+    """Program + weight packer + arena: the object module plans are written against."""
+
+    def __init__(self, device, dtype_name, packer, arena):
+        self.prog = Program(device, dtype_name)
+        self.packer = packer
+        self.arena = arena
+        self.device = self.prog.device
+        self.tdtype = self.prog.tdtype
+
+    def conv(self, key, srcs, w_oihw, k, *, bias=None, scale=None, shift=None, stride=1, pad=0, upsample=1, act=0,
+             residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None):
+        """srcs: list of Act (channel concat in order).  w_oihw: fp32 device weight whose Cin axis
+        is the concat of the sources' REAL channels (or, with first_weight_channel=[...], starts
+        at the given offsets).  Returns (Act|None, stats|None, info, io)."""
+        Cout = w_oihw.shape[0]
+        d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act)
+        info = self.prog.query(d)
+        layout = []
+        off = 0
+        for i, s in enumerate(srcs):
+            first = off if first_weight_channel is None else first_weight_channel[i]
+            layout.append((s.C, s.chunks, first))
+            off = first + s.C
+        identity = len(srcs) == 1 and srcs[0].C == w_oihw.shape[1] and layout[0][2] == 0
+        cmap = None if identity else chan_map_for(layout)
+        if shift is None and bias is not None:
+            shift = bias
+        packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift)
+        out, stats, io = self.prog.conv(d, info, srcs, packed, residual=residual, want_stats=want_stats, out_c8=out_c8,
+                                        out_nchw=out_nchw, arena=self.arena, y_c8=y_c8)
+        return out, stats, info, io
+
+    def group_norm_affine(self, stats, info, gamma, beta, C_, groups, pixels, eps=1e-5):
+        """Finalise GroupNorm statistics into the pending affine of the producing conv's output."""
+        B = stats.shape[0]
+        affine = self.arena.alloc((B, ((C_ + 7) // 8) * 8, 2), torch.float32, zero=True)
+        return self.prog.gn_finalize(stats, info, gamma.detach(), beta.detach(), C_, groups, pixels, eps, affine)
+
+    def gather_channels(self, exts, B, H, W):
+        """Ext inputs (all their channels, in order) -> one tightly packed C8 Act."""
+        planes = [(e, c) for e in exts for c in range(e.channels)]
+        chunks = (len(planes) + 7) // 8
+        dst = self.arena.alloc((B, chunks, H, W, 8), self.tdtype)
+        for q in range(chunks):
+            self.prog.gather(planes[q * 8:(q + 1) * 8], dst[:, q], B, H, W)
+        return Act(dst, len(planes))
