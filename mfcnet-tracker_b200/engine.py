@@ -24,9 +24,20 @@ def default_dtype():
 
 
 def require_cuda(t, what):
-    if not t.is_cuda:
+    if not t.is_cuda and not abi.plan_only():
         raise RuntimeError("%s: mfcnet_tracker_b200 runs on a B200 only; got a %s tensor (there is no CPU fallback)"
                            % (what, t.device.type))
+
+
+def device_guard(device):
+    import contextlib
+    return torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()
+
+
+def record_stream(t):
+    """Inputs are referenced by raw pointer until the kernels run: tie them to the launch stream."""
+    if t.is_cuda:
+        t.record_stream(torch.cuda.current_stream(t.device))
 
 
 class Ext:
@@ -139,7 +150,7 @@ class Program:
         if self._array is None:
             self.finalize()
         if stream is None:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
         abi.check(self.lib.mfc_run_list(self._array, len(self.cmds), stream))
 
     def extend(self, other):
@@ -306,7 +317,7 @@ class WeightPacker:
         self.cache = {}
 
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
 
     def standardized(self, key, w, eps=1e-5):
         k = ("ws", key)

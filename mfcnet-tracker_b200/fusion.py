@@ -124,9 +124,9 @@ class MultiFrameNetBase(nn.Module):
         out = torch.empty((B, self.num_classes, H, W), dtype=torch.float32, device=x.device)
         prog.rebind(self._split(x))
         io.y_nchw = out.data_ptr()
-        with torch.cuda.device(x.device):
+        with engine.device_guard(x.device):
             prog.run()
-        x.record_stream(torch.cuda.current_stream(x.device))
+        engine.record_stream(x)
         return out
 
 

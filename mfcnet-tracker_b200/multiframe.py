@@ -121,11 +121,10 @@ class _MultiFrame(nn.Module):
         plan["prog"].rebind(tensors)
         out = torch.empty((B, self.num_classes, H, W), dtype=torch.float32, device=dev)
         plan["io"].y_nchw = out.data_ptr()
-        with torch.cuda.device(dev):
+        with engine.device_guard(dev):
             plan["prog"].run()
-        st = torch.cuda.current_stream(dev)
         for t in tensors.values():
-            t.record_stream(st)
+            engine.record_stream(t)
         return out
 
 

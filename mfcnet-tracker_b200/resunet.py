@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import engine
-from .engine import Act
+from .engine import Act, Ext
 
 
 class _WSConv(nn.Conv2d):
@@ -158,33 +158,29 @@ class ResUnet_VB(nn.Module):
             x_c8 = arena.alloc((B, (self.channels + 7) // 8, H, W, 8), bld.tdtype)
             dummy_in = torch.zeros((B, self.channels, H, W), dtype=torch.float32, device=device)
             dummy_out = torch.empty((B, self.out_dim, H, W), dtype=torch.float32, device=device)
-            gathers = []
+            ext = Ext("x", dummy_in)
             for c0 in range(0, self.channels, 8):
-                planes = [(dummy_in, c) for c in range(c0, min(c0 + 8, self.channels))]
-                gathers.append((c0, bld.prog.gather(planes, x_c8[:, c0 // 8], B, H, W)))
+                bld.prog.gather([(ext, c) for c in range(c0, min(c0 + 8, self.channels))], x_c8[:, c0 // 8], B, H, W)
             _, io = self.record(bld, Act(x_c8, self.channels), logits_nchw=dummy_out)
             bld.prog.finalize()
-            self._plans[key] = (bld.prog, gathers, io, arena)
+            self._plans[key] = (bld.prog, io, arena)
         return self._plans[key]
 
     def forward(self, captimgs, *args, **kwargs):
         engine.require_cuda(captimgs, "ResUnet_VB.forward")
-        if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and captimgs.requires_grad:
+        if self.training:
             raise RuntimeError("ResUnet_VB (B200 engine) implements inference only: call .eval() and run under torch.no_grad()")
         x = captimgs.contiguous().float()
         B, Cc, H, W = x.shape
         if Cc != self.channels:
             raise ValueError("expected %d input channels, got %d" % (self.channels, Cc))
         dt = self._check_weights(x.device)
-        prog, gathers, io, _ = self._plan(B, H, W, x.device, dt)
+        prog, io, _ = self._plan(B, H, W, x.device, dt)
         out = torch.empty((B, self.out_dim, H, W), dtype=torch.float32, device=x.device)
-        for c0, g in gathers:
-            for j in range(min(8, self.channels - c0)):
-                g.g.plane[j] = x.data_ptr() + (c0 + j) * H * W * 4
-                g.g.plane_bstride[j] = x.stride(0)
+        prog.rebind({"x": x})
         io.y_nchw = out.data_ptr()
-        with torch.cuda.device(x.device):
+        with engine.device_guard(x.device):
             prog.run()
         # x and out are referenced by raw pointer until the kernels run: keep them alive on this stream
-        x.record_stream(torch.cuda.current_stream(x.device))
+        engine.record_stream(x)
         return out

@@ -1,0 +1,134 @@
+"""GPU parity tests of the memory-bound kernels through the C ABI: correlation cost volume, heat-map
+head, key-point extraction.  Integer / index results must be bit-exact; floating-point tolerances are
+written next to each comparison."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import corr, localize_cases, localize_oracle as LO, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mfcnet_tracker_b200 as m
+    assert torch.cuda.is_available()
+    m.abi.load()
+    return m
+
+
+# ---------------------------------------------------------------- correlation
+CORR_CASES = [  # (B, C, H, W, max_disp, stride2)
+    (1, 7, 9, 11, 4, 1), (2, 40, 9, 11, 4, 2), (1, 64, 13, 70, 20, 2), (2, 32, 30, 40, 4, 1),
+    (1, 256, 12, 40, 20, 2), (1, 16, 8, 8, 0, 1), (1, 33, 10, 67, 6, 2), (1, 8, 6, 9, 24, 2)]
+
+
+@pytest.mark.parametrize("case", CORR_CASES)
+def test_correlation_matches_oracle(M, case):
+    B, Cc, H, W, md, s2 = case
+    a = synth.normal("gcorr/a", (B, Cc, H, W), 3)
+    b = synth.normal("gcorr/b", (B, Cc, H, W), 4)
+    want_exact = corr.correlation_c(a, b, md, s2)
+    want64 = corr.correlation_f64(a, b, md, s2)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    fast = M.correlation(ta, tb, md, s2).cpu().numpy()
+    exact = M.correlation(ta, tb, md, s2, exact_order=True).cpu().numpy()
+    # exact_order reproduces the reference kernel's fp32 summation order: bit-exact vs the C oracle
+    assert np.array_equal(exact, want_exact)
+    # the fast kernel sums channels in ascending order: fp32 rounding only (|out| <~ 1, C <= 256)
+    assert np.abs(fast - want64).max() <= 2e-6
+
+
+def test_correlation_reference_operating_point_properties(M):
+    """C=256 at 48x160 (1/8 of 384x1280), max_disp 20 stride 2 (models/unflow_model.py:157-163):
+    too slow for the CPU oracle at full size, so check size-independent properties."""
+    B, Cc, H, W = 2, 256, 48, 160
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+    b = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+    out = M.correlation(a, b)
+    assert out.shape == (B, 441, H, W)
+    # centre displacement = per-pixel mean of a*b
+    assert torch.allclose(out[:, 220], (a * b).mean(1), atol=2e-6)
+    # linearity in the first argument
+    out2 = M.correlation(2.0 * a, b)
+    assert torch.equal(out2, 2.0 * out)
+    # a displacement that looks outside the image is exactly zero there
+    assert torch.count_nonzero(out[:, 0, :20, :]) == 0 and torch.count_nonzero(out[:, 0, :, :20]) == 0
+    # swapping the arguments mirrors the displacement grid: out(a,b)[d](p) == out(b,a)[-d](p+d)
+    o_ba = M.correlation(b, a)
+    d_idx = (10 + 3) * 21 + (10 - 2)      # dy=+6, dx=-4
+    m_idx = (10 - 3) * 21 + (10 + 2)
+    lhs = out[:, d_idx, : H - 6, 4:]
+    rhs = o_ba[:, m_idx, 6:, : W - 4]
+    assert torch.allclose(lhs, rhs, atol=2e-6)
+    # a random crop against the exact-order kernel
+    ex = M.correlation(a, b, exact_order=True)
+    assert (out - ex).abs().max().item() <= 2e-6
+
+
+def test_correlation_rejects_cpu(M):
+    with pytest.raises(NotImplementedError):
+        M.correlation(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8))
+
+
+# ---------------------------------------------------------------- heat-map head
+def test_heatmap_head_matches_torch(M):
+    x = torch.from_numpy(synth.normal("hm", (2, 5, 120, 160), 3, std=3.0)).cuda()
+    x[0, :, 5, 7] = 1.25          # an exact tie: the first class must win
+    logp, prob, amax = M.heatmap_head(x)
+    ref_lp = torch.log_softmax(x, 1)
+    assert (logp - ref_lp).abs().max().item() <= 2e-6      # fp32 log-softmax, different exp/log ulps
+    assert (prob - ref_lp.exp()).abs().max().item() <= 2e-6
+    assert np.array_equal(amax.cpu().numpy(), prob.cpu().numpy().argmax(1))     # first-max, bit-exact on our own probs
+    assert amax[0, 5, 7].item() == 0
+    agree = (amax.cpu().numpy() == ref_lp.exp().cpu().numpy().argmax(1)).mean()
+    assert agree >= 0.9999
+
+
+# ---------------------------------------------------------------- key-point extraction
+def test_gaussian_blur_bit_exact_with_scipy(M):
+    for shape in [(40, 56), (17, 23), (480, 640)]:
+        img = synth.uniform("ggauss", shape, 9)
+        got = M.gaussian_blur(torch.from_numpy(img).cuda(), 4).cpu().numpy()
+        assert np.array_equal(got, LO.smoothed(img)), shape
+
+
+def test_contours_match_cv2(M):
+    from mfcnet_tracker_b200 import heatmap as HM
+    rng = np.random.RandomState(0)
+    masks = [255 * (rng.rand(37, 53) < p).astype(np.uint8) for p in (0.05, 0.3, 0.5, 0.6, 0.8)]
+    masks += [255 * (rng.rand(480, 640) < p).astype(np.uint8) for p in (0.02, 0.45)]
+    ring = np.zeros((20, 20), np.uint8)
+    ring[2:18, 2:18] = 255
+    ring[4:16, 4:16] = 0
+    ring[8:12, 8:12] = 255
+    masks += [ring, np.full((9, 9), 255, np.uint8), np.zeros((9, 9), np.uint8)]
+    for mi, mask in enumerate(masks):
+        want = [tuple(r) for r in LO.contour_records(mask)]
+        got = HM.trace_contours(torch.from_numpy(mask).cuda())
+        assert got == want, mi
+        assert HM.calc_centroids(torch.from_numpy(mask).cuda()) == LO.calc_centroids(mask), mi
+
+
+def test_keypoints_bit_exact_on_identical_heatmaps(M):
+    """North-star criterion: tool-tip coordinates bit-exact given identical heat maps -- against the
+    reference's own outputs (tests/golden/localize_centroids.json) and the scipy/cv2 oracle."""
+    with open(os.path.join(ROOT, "tests", "golden", "localize_centroids.json")) as f:
+        gold = json.load(f)
+    for name, prob in localize_cases.cases().items():
+        got = M.predicted_keypoints(torch.from_numpy(prob).cuda())
+        norm = [[None if (isinstance(v, float) and np.isnan(v)) else int(v) for v in lst] for lst in got]
+        assert norm == gold[name], name
+    # noisy random maps: thousands of contours, ties and border effects
+    for seed in range(3):
+        p = synth.uniform("kp/%d" % seed, (1, 5, 120, 160), seed)
+        p = (p / p.sum(1, keepdims=True)).astype(np.float32)
+        got = M.predicted_keypoints(torch.from_numpy(p).cuda())
+        want = LO.predicted_keypoints(p)
+        assert str(got) == str(want), seed

@@ -1,0 +1,137 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/*.h declares
+(no compute calls without a GPU), the drop-in modules expose the reference's state_dict keys, and
+plans are constructible (MFC_B200_PLAN_ONLY: real descriptor validation / tiling queries, no launches)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from tests import golden_util as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def M(monkeypatch):
+    monkeypatch.setenv("MFC_B200_PLAN_ONLY", "1")
+    import mfcnet_tracker_b200 as m
+    monkeypatch.setattr(m.abi, "_lib", None)
+    yield m
+    m.abi._lib = None
+
+
+def _declared():
+    with open(os.path.join(ROOT, "include", "mfcnet_b200.h")) as f:
+        src = f.read()
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(mfc_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mfcnet_tracker_b200 as m
+    lib = C.CDLL(m.abi.library_path())
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(m.abi.EXPORTS) == names          # the ctypes binding covers the whole header
+    lib.mfc_abi_version.restype = C.c_int
+    assert lib.mfc_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    """sizeof() of every ctypes mirror equals the C compiler's (checked through a tiny gcc probe)."""
+    import shutil
+    import subprocess
+    import tempfile
+    import mfcnet_tracker_b200 as m
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    names = ["MfcGather", "MfcConvInfo", "MfcSrc", "MfcConvDesc", "MfcConvIO", "MfcWarpArgs", "MfcGnArgs", "MfcAddArgs",
+             "MfcGatherArgs", "MfcCmd"]
+    prog = '#include <stdio.h>\n#include "mfcnet_b200.h"\nint main(){' + "".join(
+        'printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in names) + "return 0;}"
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "p.c")
+        with open(src, "w") as f:
+            f.write(prog)
+        exe = os.path.join(td, "p")
+        subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    for n in names:
+        assert C.sizeof(getattr(m.abi, n)) == int(sizes[n]), n
+
+
+def test_invalid_descriptor_is_rejected_with_message():
+    import mfcnet_tracker_b200 as m
+    lib = m.abi.load()
+    d = m.abi.MfcConvDesc()
+    info = m.abi.MfcConvInfo()
+    rc = lib.mfc_conv2d_query(C.byref(d), C.byref(info))
+    assert rc == -1 and b"conv" in lib.mfc_last_error()
+
+
+@pytest.mark.parametrize("tag", ["resunet16_64x96", "resunet8_32x48"])
+def test_resunet_state_dict_keys(M, tag):
+    meta, man, _ = G.load(tag)
+    net = M.ResUnet_VB(channels=3, dim=meta["dim"], out_dim=meta["classes"])
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    net.load_state_dict(G.state_dict(man, meta["seed"]), strict=True)
+
+
+@pytest.mark.parametrize("variant", ["large", "basic"])
+@pytest.mark.parametrize("K", [3, 5])
+def test_fusion_state_dict_keys_and_plan(M, variant, K):
+    meta, man, _ = G.load(f"fusion_{variant}_k{K}_48x64")
+    cls = M.MultiFrameNetLarge if variant == "large" else M.MultiFrameNetBasic
+    net = cls(meta["N"], K, False, with_optflow=True, with_depth=True).eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    net.load_state_dict(G.state_dict(man, meta["seed"]), strict=True)
+    y = net(torch.zeros(2, net.expected_input_channels(), 48, 64))
+    assert y.shape == (2, meta["N"], 48, 64)
+    with pytest.raises(ValueError):
+        net(torch.zeros(2, net.expected_input_channels() + 1, 48, 64))
+
+
+@pytest.mark.parametrize("variant", ["large", "basic"])
+def test_mfcnet_wrapper_keys_and_plan(M, variant):
+    meta, man, _ = G.load(f"mfcnet_resunet16_{variant}_k3_64x96")
+    cls = M.ResUNetMultiLarge if variant == "large" else M.ResUNetMultiBasic
+    net = cls(num_classes=5, num_frames=3, pretrained=False, loadpath=None, optflow_inputs=True, depth_inputs=True).eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    assert [n for n, _ in net.named_children()] == ["base_model", "multiframe_net"]
+    xs = [torch.zeros(2, 3, 64, 96)] * 3
+    y = net(xs, optflow=[torch.zeros(2, 2, 64, 96)] * 2, depth=[torch.zeros(2, 1, 64, 96)] * 3)
+    assert y.shape == (2, 5, 64, 96)
+    plan = net._plans[(2, 64, 96)]
+    # 3 frame gathers + SFC passes of 60 launches + aux gather (large) or warp (basic) + 4 fusion convs
+    n_sfc = (3 * 2) // plan["sub_batch"]
+    assert plan["prog"].n_kernels == 3 + 60 * n_sfc + 1 + 4
+    with pytest.raises(ValueError):
+        net(xs)                                    # flow / depth missing
+    with pytest.raises(RuntimeError):
+        net.train()(xs, optflow=[torch.zeros(2, 2, 64, 96)] * 2, depth=[torch.zeros(2, 1, 64, 96)] * 3)
+
+
+def test_factories(M):
+    class A:
+        model_type = "ResUNetMulti-Large"
+        num_classes, num_input_frames, pretrained, load_wts_base_model = 5, 3, False, None
+        add_optflow_inputs, add_depth_inputs = True, True
+    net = M.get_multiframe_segmentation_model(A)
+    assert type(net).__name__ == "ResUNetMultiLarge" and net.multiframe_net.in_channels == 22
+    A.model_type = "nope"
+    with pytest.raises(ValueError):
+        M.get_multiframe_segmentation_model(A)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mfcnet-tracker_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            with open(os.path.join(pkg, fn)) as f:
+                src = f.read()
+            assert "oracle" not in src.replace("torch_oracle", "oracle") or fn == "" , fn
