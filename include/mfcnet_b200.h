@@ -299,6 +299,11 @@ typedef struct MfcCmd {
 
 int mfc_run_list(const MfcCmd* cmds, int n, void* stream);
 
+/* Measurement variant (bench.py's live roofline): the same list with a CUDA event recorded on
+ * `stream` around every command; synchronises the stream and writes each command's device time
+ * in milliseconds to ms_out[n].  This is the one entry point that creates events and blocks. */
+int mfc_run_list_timed(const MfcCmd* cmds, int n, void* stream, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "mfc_class_mask": ([c_void_p, c_int, c_void_p, c_ll, c_void_p], c_int),
     "mfc_trace_contours": ([c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "mfc_run_list": ([C.POINTER(MfcCmd), c_int, c_void_p], c_int),
+    "mfc_run_list_timed": ([C.POINTER(MfcCmd), c_int, c_void_p, C.POINTER(c_float)], c_int),
 }
 EXPORTS = tuple(_SIGNATURES)
 

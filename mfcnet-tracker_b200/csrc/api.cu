@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "launch.h"
 
@@ -343,6 +344,26 @@ int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
     }
   }
   return MFC_OK;
+}
+
+int mfc_run_list_timed(const MfcCmd* cmds, int n, void* stream, float* ms_out) {
+  if (!cmds || n < 1 || !ms_out) return fail(MFC_EINVAL, "run_list_timed: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev((size_t)n + 1);
+  for (auto& e : ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return fail(MFC_ECUDA, "run_list_timed: cudaEventCreate failed");
+  int rc = MFC_OK;
+  cudaEventRecord(ev[0], st);
+  for (int i = 0; i < n && rc == MFC_OK; ++i) {
+    rc = mfc_run_list(cmds + i, 1, stream);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaError_t e = cudaEventSynchronize(ev[n]);
+  if (rc == MFC_OK && e != cudaSuccess) rc = cuda_fail(e, "run_list_timed: sync");
+  if (rc == MFC_OK)
+    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (auto& x : ev) cudaEventDestroy(x);
+  return rc;
 }
 
 }  // extern "C"

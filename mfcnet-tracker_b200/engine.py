@@ -18,9 +18,12 @@ _DTYPES = {"fp16": (torch.float16, abi.MFC_F16), "bf16": (torch.bfloat16, abi.MF
 
 
 def default_dtype():
-    """Activation / weight storage type of the conv path (accumulation is always fp32).
-    bf16 is the default; MFC_B200_DTYPE=fp16 selects fp16 storage."""
-    return os.environ.get("MFC_B200_DTYPE", "bf16")
+    """Activation / weight STORAGE type of the conv path; accumulation is always fp32 in TMEM.
+    fp16 is the default: same width and tensor-core rate as bf16, but its 11-bit significand is what
+    keeps the end-to-end logit error inside the 2e-2 bound of BASELINE.json (measured on B200:
+    fp16 5.2e-3 / 99.93 % argmax agreement, bf16 4.2e-2 / 99.45 % on the 480x640 K=3 MFCNet; see
+    DESIGN.md).  MFC_B200_DTYPE=bf16 selects bf16 storage."""
+    return os.environ.get("MFC_B200_DTYPE", "fp16")
 
 
 def require_cuda(t, what):
@@ -152,6 +155,17 @@ class Program:
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
         abi.check(self.lib.mfc_run_list(self._array, len(self.cmds), stream))
+
+    def run_timed(self, stream=None):
+        """Measurement only: runs the list with CUDA events around every command and returns
+        [(op, struct_a, struct_b, milliseconds)].  Synchronises."""
+        if self._array is None:
+            self.finalize()
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        ms = (C.c_float * len(self.cmds))()
+        abi.check(self.lib.mfc_run_list_timed(self._array, len(self.cmds), stream, ms))
+        return [(op, a, b, float(ms[i])) for i, (op, a, b) in enumerate(self.cmds)]
 
     def extend(self, other):
         self.cmds += other.cmds
