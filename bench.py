@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the MFCNet multi-frame inference hot path on B200.
+
+Workload (BASELINE.json configs[1]): 3-frame MFCNet (ResUNet-16 SFC base, MultiFrameNetLarge fusion,
+RGB + depth + optical-flow inputs, 5 classes) at 480x640, batch 8 windows per step per GPU.  One step =
+one `model(frames, optflow=, depth=)` call: 24 SFC passes + 8 fusion passes, exactly what the reference
+module computes for that call (no cross-window feature reuse inside the timed region).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N ...            # the reference's fp32 CPU path (oracle port), rank 0 only
+
+Prints ONE JSON line on rank 0 (see README / DESIGN.md for the fields).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec @480x640 3-frame MFCNet (RGB+depth+flow)"
+N_CLASSES, K_FRAMES, H, W = 5, 3, 480, 640
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="windows per step per GPU")
+    ap.add_argument("--variant", default="large", choices=["large", "basic"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-kernel-timing", action="store_true", help="skip the per-launch event timing pass (profiling runs)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+def make_state_dict(variant, seed=0):
+    """Random-init weights of the architecture (no checkpoints offline), identical for both arms.
+    The key/shape manifest is the reference module's own state_dict layout, as recorded in
+    tests/golden by oracle/make_golden.py."""
+    import torch
+    from oracle import synth
+    with open(os.path.join(ROOT, "tests", "golden", "mfcnet_resunet16_%s_k3_64x96.json" % variant)) as f:
+        man = [(k, tuple(s), d) for k, s, d in json.load(f)["manifest"]]
+    return {k: torch.from_numpy(v) for k, v in synth.fill_state_dict(man, seed).items()}
+
+
+def make_model(variant, sd):
+    import mfcnet_tracker_b200 as M
+    cls = M.ResUNetMultiLarge if variant == "large" else M.ResUNetMultiBasic
+    net = cls(N_CLASSES, K_FRAMES, optflow_inputs=True, depth_inputs=True)
+    net.load_state_dict(sd, strict=True)
+    return net
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, smax = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use every sample we have
+            for ts, line in self.rows:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_fps(sd, variant, budget_s):
+    """The reference's fp32 CPU path (oracle port of the reference modules, torch CPU ops, all host
+    threads) on a bounded sample: B=1 windows of the same workload."""
+    import torch
+    from oracle import synth, torch_oracle as TO
+    torch.set_num_threads(os.cpu_count() or 1)
+    xs = [torch.from_numpy(synth.frames(f"bench/{i}", 1, H, W, 0)) for i in range(K_FRAMES)]
+    fl = [torch.from_numpy(synth.flow(f"bench/{i}", 1, H, W, 0)) for i in range(K_FRAMES - 1)]
+    dp = [torch.from_numpy(synth.depth(f"bench/{i}", 1, H, W, 0)) for i in range(K_FRAMES)]
+    times = []
+    with torch.no_grad():
+        TO.mfcnet_forward(sd, xs, fl, dp, base=TO.resunet_forward, variant=variant, N=N_CLASSES)  # warm-up
+        t_start = time.time()
+        while True:
+            t0 = time.time()
+            TO.mfcnet_forward(sd, xs, fl, dp, base=TO.resunet_forward, variant=variant, N=N_CLASSES)
+            times.append(time.time() - t0)
+            if len(times) >= 3 and time.time() - t_start > budget_s or len(times) >= 50:
+                break
+    best = min(times)
+    return 1.0 / best, len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sd = make_state_dict(args.variant)
+    # each "step" = one B=1 window (bounded sample of the B=8 workload); W warm-up + K timed steps
+    import torch
+    from oracle import synth, torch_oracle as TO
+    torch.set_num_threads(os.cpu_count() or 1)
+    xs = [torch.from_numpy(synth.frames(f"bench/{i}", 1, H, W, 0)) for i in range(K_FRAMES)]
+    fl = [torch.from_numpy(synth.flow(f"bench/{i}", 1, H, W, 0)) for i in range(K_FRAMES - 1)]
+    dp = [torch.from_numpy(synth.depth(f"bench/{i}", 1, H, W, 0)) for i in range(K_FRAMES)]
+    steps = min(args.steps, 40)
+    warm = min(args.warmup, 3)
+    with torch.no_grad():
+        for _ in range(max(1, warm)):
+            TO.mfcnet_forward(sd, xs, fl, dp, base=TO.resunet_forward, variant=args.variant, N=N_CLASSES)
+        t0 = time.time()
+        for _ in range(steps):
+            TO.mfcnet_forward(sd, xs, fl, dp, base=TO.resunet_forward, variant=args.variant, N=N_CLASSES)
+        dt = time.time() - t0
+    fps = steps / dt
+    cores = torch.get_num_threads()
+    sample = "B=1 window per step (1/%d of the batch-%d step), fp32 torch CPU ops, %d threads" % (args.batch, args.batch, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(1, warm), "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, note="reference CPU path; one B=1 window per step"),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, note=None):
+    c = {"workload": "MFCNet num_input_frames=3 (ResUNet-16 SFC + MultiFrameNet%s, add_depth_inputs + add_optflow_inputs), "
+                     "480x640, 5 classes, batch %d windows/GPU (BASELINE configs[1])" % (args.variant.capitalize(), args.batch),
+         "frames_per_window": K_FRAMES, "batch_per_gpu": args.batch, "height": H, "width": W, "classes": N_CLASSES,
+         "l2": "step inputs (%.0f MB fp32) and per-layer working sets exceed the 126 MB L2; no explicit flush"
+               % (args.batch * (K_FRAMES * 3 + 2 * (K_FRAMES - 1) + K_FRAMES) * H * W * 4 / 1e6)}
+    if note:
+        c["note"] = note
+    return c
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mfcnet_tracker_b200 as M
+    M.abi.load()
+    sd = make_state_dict(args.variant)
+    net = make_model(args.variant, sd).to(dev).eval()
+    dt_name = M.engine.default_dtype()
+    B = args.batch
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)      # every rank (clip shard) gets its own frames
+    frames = [torch.randn(B, 3, H, W, device=dev, generator=g) for _ in range(K_FRAMES)]
+    flows = [4.0 * torch.randn(B, 2, H, W, device=dev, generator=g) for _ in range(K_FRAMES - 1)]
+    depths = [torch.rand(B, 1, H, W, device=dev, generator=g) for _ in range(K_FRAMES)]
+
+    def step():
+        return net(frames, optflow=flows, depth=depths)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    W_ = max(3, args.warmup)
+    with torch.no_grad():
+        for _ in range(W_):
+            out = step()
+        torch.cuda.synchronize()
+        prog = net._plans[(B, H, W)]["prog"]
+        # ---- resident-input throughput ("value")
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop(t0, t1) if sampler else None
+        # ---- end to end through the public API with HOST buffers
+        pin = lambda t: t.cpu().pin_memory()
+        h_frames, h_flows, h_depths = [pin(t) for t in frames], [pin(t) for t in flows], [pin(t) for t in depths]
+        d_frames = [torch.empty_like(t) for t in frames]
+        d_flows = [torch.empty_like(t) for t in flows]
+        d_depths = [torch.empty_like(t) for t in depths]
+        h_amax = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+        h2d = sum(t.numel() * 4 for t in h_frames + h_flows + h_depths)
+        d2h = h_amax.numel()
+
+        def e2e_step():
+            for d, h in zip(d_frames + d_flows + d_depths, h_frames + h_flows + h_depths):
+                d.copy_(h, non_blocking=True)
+            y = net(d_frames, optflow=d_flows, depth=d_depths)
+            _, _, amax = M.heatmap_head(y, want_logp=False, want_prob=False)
+            h_amax.copy_(amax, non_blocking=True)
+
+        ms_e2e = float("nan")
+        if not args.no_e2e:
+            for _ in range(3):
+                e2e_step()
+            torch.cuda.synchronize()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                e2e_step()
+            f1.record()
+            torch.cuda.synchronize()
+            barrier()
+            ms_e2e = f0.elapsed_time(f1)
+        # ---- live per-kernel timing of one step (events around every launch) for the roofline
+        per_cmd = None
+        if rank == 0 and not args.no_kernel_timing:
+            for _ in range(2):
+                per_cmd = prog.run_timed()
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    frames_total = world * B * args.steps
+    value = frames_total / (ms / 1000.0)
+    e2e_val = frames_total / (ms_e2e / 1000.0)
+    hbm_peak, tf_peak, peak_src = peaks()
+    if per_cmd is None:
+        print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                          "ms_per_step": ms / args.steps, "note": "profiling run (no roofline / e2e legs)"}), flush=True)
+        return 0
+    kinds = {}
+    for c in per_cmd:
+        k = kinds.setdefault(c["kind"], {"n": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+        k["n"] += 1
+        k["ms"] += c["ms"]
+        k["bytes"] += c["bytes"]
+        k["flops"] += c["flops"]
+    tot_ms = sum(k["ms"] for k in kinds.values())
+    conv = kinds["conv"]
+    achieved = conv["bytes"] / 1e9 / (conv["ms"] / 1e3)
+    roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % conv["n"], "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": conv["bytes"] / conv["n"],
+                "avg_launch_ms": conv["ms"] / conv["n"], "share_of_step": conv["ms"] / tot_ms,
+                "tensor_tflops": conv["flops"] / 1e12 / (conv["ms"] / 1e3), "tensor_frac": conv["flops"] / 1e12 / (conv["ms"] / 1e3) / tf_peak,
+                "step_shares": {k: round(v["ms"] / tot_ms, 4) for k, v in kinds.items()}}
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "%s storage, fp32 accumulate (tcgen05 kind::f16)" % dt_name, "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "path": "pinned host fp32 frames/flow/depth -> H2D -> model() -> heatmap_head argmax -> D2H uint8 class map"},
+            "gpu_launches": (prog.n_kernels * args.steps) + (prog.n_kernels + 1) * args.steps,
+            "gpu_launches_per_step": prog.n_kernels, "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        fps, n, cores = cpu_reference_fps(sd, args.variant, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "%d B=1 windows (3 SFC + fusion each) of the same workload, best time, fp32 torch CPU ops" % n}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

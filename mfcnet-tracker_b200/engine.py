@@ -133,10 +133,12 @@ class Program:
         self._array = None
         self.n_kernels = 0   # kernel launches one run() issues
         self.bindings = {}   # external input key -> [setter(tensor)]
+        self.meta = []       # per command: {'kind', 'name', 'bytes', 'flops'} (algorithmic, for the roofline)
 
     # ---- low-level recording -----------------------------------------------------------------
-    def _push(self, op, a, b=None, launches=1):
+    def _push(self, op, a, b=None, launches=1, meta=None):
         self.cmds.append((op, a, b))
+        self.meta.append(meta or {"kind": "op%d" % op, "name": "", "bytes": 0, "flops": 0})
         self._array = None
         self.n_kernels += launches
 
@@ -158,17 +160,18 @@ class Program:
 
     def run_timed(self, stream=None):
         """Measurement only: runs the list with CUDA events around every command and returns
-        [(op, struct_a, struct_b, milliseconds)].  Synchronises."""
+        the per-command meta dicts with an added 'ms' (device milliseconds).  Synchronises."""
         if self._array is None:
             self.finalize()
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         ms = (C.c_float * len(self.cmds))()
         abi.check(self.lib.mfc_run_list_timed(self._array, len(self.cmds), stream, ms))
-        return [(op, a, b, float(ms[i])) for i, (op, a, b) in enumerate(self.cmds)]
+        return [dict(self.meta[i], ms=float(ms[i])) for i in range(len(self.cmds))]
 
     def extend(self, other):
         self.cmds += other.cmds
+        self.meta += other.meta
         self.keep += other.keep
         self.n_kernels += other.n_kernels
         self._array = None
@@ -213,7 +216,9 @@ class Program:
         a.dst_bstride_bytes = dst_chunk_tensor.stride(0) * dst_chunk_tensor.element_size()
         a.B, a.H, a.W, a.dtype = B, H, W, self.cdtype
         self.keep.append(dst_chunk_tensor)
-        self._push(abi.OP_GATHER, a)
+        nreal = sum(1 for p in planes if p is not None)
+        self._push(abi.OP_GATHER, a, meta={"kind": "gather", "name": "", "flops": 0,
+                                           "bytes": B * H * W * (4 * nreal + 16)})
         return a
 
     def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act):
@@ -243,7 +248,7 @@ class Program:
         return info
 
     def conv(self, d, info, srcs, packed, residual=None, want_stats=False, out_c8=True, out_nchw=None, arena=None,
-             y_c8=None):
+             y_c8=None, name=""):
         """Record one fused conv for descriptor `d` (from conv_desc) / `info` (from query).
         `packed` = PackedConv (weights + scale/shift).  Returns (Act or None, stats or None, io)."""
         io = abi.MfcConvIO()
@@ -275,7 +280,21 @@ class Program:
             self.keep.append(stats)
         for s in srcs:
             self.keep += [s.t, s.affine]
-        self._push(abi.OP_CONV, d, io)
+        # algorithmic work of this layer as the reference conv sees it (DESIGN.md "roofline"): the
+        # input tensor read once (at the resolution the conv consumes), the output written once, the
+        # weights once; 2 bytes per activation element (fp32 NCHW outputs count 4).
+        cin = sum(s.C for s in srcs)
+        hin, win = d.Hin * d.upsample, d.Win * d.upsample
+        nbytes = B * cin * hin * win * 2 + Cout * cin * d.kh * d.kw * 2
+        if out_c8:
+            nbytes += B * Cout * d.Hout * d.Wout * 2
+        if out_nchw is not None:
+            nbytes += B * Cout * d.Hout * d.Wout * 4
+        if residual is not None:
+            nbytes += B * Cout * d.Hout * d.Wout * 2
+        flops = 2 * B * Cout * d.Hout * d.Wout * cin * d.kh * d.kw
+        self._push(abi.OP_CONV, d, io, meta={"kind": "conv", "name": name, "bytes": nbytes, "flops": flops,
+                                             "shape": "B%d %dx%d %d->%d k%d s%d u%d" % (B, d.Hout, d.Wout, cin, Cout, d.kh, d.stride, d.upsample)})
         return out, stats, io
 
     def gn_finalize(self, stats, info, gamma, beta, C_, groups, pixels, eps, affine):
@@ -284,7 +303,7 @@ class Program:
         a.pixels, a.B, a.tiles_per_image = pixels, stats.shape[0], info.tiles_per_image
         a.cpad, a.C, a.groups, a.eps = info.nb * info.nblk, C_, groups, eps
         self.keep += [stats, gamma, beta, affine]
-        self._push(abi.OP_GN_FINALIZE, a)
+        self._push(abi.OP_GN_FINALIZE, a, meta={"kind": "gn_finalize", "name": "", "flops": 0, "bytes": stats.numel() * 4})
         return affine
 
     def affine_silu_add(self, a_act, r_act, out_t):
@@ -295,11 +314,12 @@ class Program:
             if not t.is_contiguous():
                 raise ValueError("affine_silu_add needs dense C8 tensors")
         self.keep += [a_act.t, a_act.affine, r_act.t, out_t]
-        self._push(abi.OP_AFFINE_SILU_ADD, a)
+        self._push(abi.OP_AFFINE_SILU_ADD, a, meta={"kind": "affine_silu_add", "name": "", "flops": 0,
+                                                    "bytes": 3 * a_act.B * a_act.C * a_act.H * a_act.W * 2})
         return Act(out_t, a_act.C)
 
-    def warp(self, args):
-        self._push(abi.OP_WARP, args)
+    def warp(self, args, nbytes=0):
+        self._push(abi.OP_WARP, args, meta={"kind": "flow_warp", "name": "", "flops": 0, "bytes": nbytes})
 
 
 class PackedConv:
@@ -418,7 +438,7 @@ class Builder:
             shift = bias
         packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift)
         out, stats, io = self.prog.conv(d, info, srcs, packed, residual=residual, want_stats=want_stats, out_c8=out_c8,
-                                        out_nchw=out_nchw, arena=self.arena, y_c8=y_c8)
+                                        out_nchw=out_nchw, arena=self.arena, y_c8=y_c8, name=key)
         return out, stats, info, io
 
     def group_norm_affine(self, stats, info, gamma, beta, C_, groups, pixels, eps=1e-5):

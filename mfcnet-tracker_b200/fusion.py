@@ -222,5 +222,6 @@ class MultiFrameNetBasic(MultiFrameNetBase):
             prog.keep.append(dplane)
             srcs = srcs + [Act(dplane, K)]
             fwc.append(N * K)
-        prog.warp(a)
+        nb = B * H * W * ((K - 1) * (2 * maps[0].chunks * 16 + 8) + (16 + 4 * K if depths else 0))
+        prog.warp(a, nb)
         return record_stack(bld, "multiframe_net", self.multiframe_net, srcs, fwc, out_nchw)
