@@ -299,6 +299,24 @@ def run_b200(args):
         k["bytes"] += c["bytes"]
         k["flops"] += c["flops"]
     tot_ms = sum(k["ms"] for k in kinds.values())
+    # per-layer-shape table (device time, achieved GB/s and TFLOP/s) for the optimisation log
+    shapes = {}
+    for c in per_cmd:
+        key = c["kind"] + " " + c.get("shape", "")
+        s_ = shapes.setdefault(key, {"n": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+        s_["n"] += 1
+        s_["ms"] += c["ms"]
+        s_["bytes"] += c["bytes"]
+        s_["flops"] += c["flops"]
+    table = [dict(layer=k, n=v["n"], ms_total=round(v["ms"], 4), us_each=round(1e3 * v["ms"] / v["n"], 2),
+                  gbs=round(v["bytes"] / 1e6 / max(v["ms"], 1e-9), 1), tflops=round(v["flops"] / 1e9 / max(v["ms"], 1e-9), 2),
+                  share=round(v["ms"] / tot_ms, 4)) for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])]
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "bench_layers.json"), "w") as f:
+            json.dump({"ms_per_step_events": tot_ms, "layers": table}, f, indent=1)
+    except OSError:
+        pass
     conv = kinds["conv"]
     achieved = conv["bytes"] / 1e9 / (conv["ms"] / 1e3)
     roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % conv["n"], "bound": "hbm",

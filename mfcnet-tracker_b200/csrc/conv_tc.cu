@@ -158,20 +158,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     mbar_init(&mma_done[1], 1);
     fence_mbar_init();
   }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, p.t.tmem_cols);
-    tmem_relinquish();
-  }
   for (int i = tid; i < NB; i += kConvThreads) {
     s_scale[i] = p.scale ? __ldg(p.scale + nbk * NB + i) : 1.0f;
     s_shift[i] = p.shift ? __ldg(p.shift + nbk * NB + i) : 0.0f;
   }
   if (p.stats)
     for (int i = tid; i < 8 * NB * 2; i += kConvThreads) s_stats[i] = 0.0f;
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  uint32_t tmem_base = 0;
 
   // ---- K loop over channel stages
   const int iy_base = oy0 * p.stride - p.pad, ix_base = ox0 * p.stride - p.pad;
@@ -211,24 +205,61 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         stage_plane<BF16, false>(p, plane, src, nullptr, iy_base, ix_base);
       }
     }
+    if (ks == 0) {
+      // TMEM is claimed only now, after the first tile has been staged: a CTA that has to wait for
+      // columns held by a co-resident CTA overlaps that wait with its own global loads.
+      if (warp == 0) {
+        tmem_alloc(tmem_slot, p.t.tmem_cols);
+        tmem_relinquish();
+      }
+      tc_fence_before();
+    }
     cp_async_wait_all();
     fence_async_smem();
     __syncthreads();
+    if (ks == 0) {
+      tc_fence_after();
+      tmem_base = *tmem_slot;
+    }
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t a_base = smem_u32(abuf), b_base = smem_u32(bbuf);
-      const int s = p.stride, P = p.t.P;
-      for (int r = 0; r < p.t.R; ++r) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(r * NB);
-        for (int t = 0; t < taps; ++t) {
-          const int ky = t / p.kw, kx = t - ky * p.kw;
-          const int py = ky % s, px = kx % s;
-          const uint32_t a_off = (uint32_t)(((py * s + px) * p.t.slots_sub + r * 128 + (ky / s) * P + (kx / s)) * 16);
+      // Descriptors differ only in their 14-bit start-address field (16-byte units), so the whole
+      // issue loop is integer adds on the low word: no divisions, ~10 instructions per MMA.
+      const uint64_t da0 = make_smem_desc(smem_u32(abuf), p.t.plane_bytes, 128);
+      const uint64_t db0 = make_smem_desc(smem_u32(bbuf), (uint32_t)(NB * 16), 128);
+      const uint32_t da_hi = (uint32_t)(da0 >> 32), db_hi = (uint32_t)(db0 >> 32);
+      const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
+      const uint32_t a_kstep = (2u * p.t.plane_bytes) >> 4;  // two 8-channel planes per K step
+      const uint32_t b_tap = (uint32_t)(2 * NB);             // (2*NB*16) >> 4
+      const uint32_t b_kstep = (uint32_t)taps * b_tap;
+      const bool s2 = p.stride == 2;
+      const uint32_t P = (uint32_t)p.t.P, sub = (uint32_t)p.t.slots_sub;
+      const uint32_t idesc = p.idesc;
+      // Loop order: taps outermost, the tile's R independent 128-pixel runs innermost, so that
+      // back-to-back MMAs never accumulate into the same TMEM columns (a dependent accumulate
+      // chain serialises on the tensor pipe's latency, which dwarfs an N=16 MMA's 8 busy cycles).
+      uint32_t b_t = db_lo0;
+      const uint32_t first = (ks == 0) ? 0u : 1u;
+      for (int ky = 0; ky < p.kh; ++ky) {
+        const uint32_t a_row = da_lo0 + (s2 ? (uint32_t)(ky & 1) * 2u * sub + (uint32_t)(ky >> 1) * P : (uint32_t)ky * P);
+        for (int kx = 0; kx < p.kw; ++kx) {
+          const uint32_t a_tap = a_row + (s2 ? (uint32_t)(kx & 1) * sub + (uint32_t)(kx >> 1) : (uint32_t)kx);
+          const uint32_t acc_tap = (ky | kx) ? 1u : first;
+          uint32_t b_lo = b_t;
+          uint32_t a_sk = a_tap;
           for (int sk = 0; sk < nks; ++sk) {
-            const uint64_t da = make_smem_desc(a_base + (uint32_t)(sk * 2) * p.t.plane_bytes + a_off, p.t.plane_bytes, 128);
-            const uint64_t db = make_smem_desc(b_base + (uint32_t)((sk * taps + t) * (2 * NB * 16)), (uint32_t)(NB * 16), 128);
-            umma_f16_ss(d_tmem, da, db, p.idesc, (ks > 0 || t > 0 || sk > 0) ? 1u : 0u);
+            const uint32_t acc = sk ? 1u : acc_tap;
+            uint32_t a_lo = a_sk;
+            uint32_t d_tmem = tmem_base;
+            for (int r = 0; r < p.t.R; ++r) {
+              umma_f16_ss(d_tmem, ((uint64_t)da_hi << 32) | a_lo, ((uint64_t)db_hi << 32) | b_lo, idesc, acc);
+              a_lo += 128u;
+              d_tmem += (uint32_t)NB;
+            }
+            a_sk += a_kstep;
+            b_lo += b_kstep;
           }
+          b_t += b_tap;
         }
       }
       umma_commit(&mma_done[buf]);

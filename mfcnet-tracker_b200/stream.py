@@ -1,0 +1,117 @@
+"""Sliding-window (streaming) MFCNet inference with a zero-copy feature ring buffer, and clip sharding.
+
+The reference video loop (scripts/test_multiframe_segmentation_on_videos_v3.py:233-280) re-runs the
+SFC network on all K frames of the window for every output frame, although K-1 of them were already
+processed for the previous outputs (models/multiframe_model.py:426-428).  The SFC network is
+per-frame and deterministic in eval mode, so here every frame is encoded ONCE: its class maps are
+written into slot ``t % K`` of a ring of C8 planes, and the fusion head of step t reads the slots in
+window order (current frame first) simply as a different list of source pointers -- the frame-window
+channel concat is a rotation of pointers, not a copy.
+
+``shard_frames`` splits a video of F frames into contiguous clips, one per GPU, each preceded by a
+K-1-frame halo that only fills the ring (no collective on the inference path).
+"""
+import torch
+
+from . import engine
+from .engine import Act, Ext
+
+
+def shard_frames(n_frames, world, rank, num_input_frames):
+    """Contiguous clip of output frames [lo, hi) for `rank`, and the first frame it must encode
+    (`enc_lo` = lo - (K-1), clamped at 0).  Outputs exist for t >= K-1 only, as in the reference loop."""
+    K = num_input_frames
+    first_out = K - 1
+    n_out = max(0, n_frames - first_out)
+    per = (n_out + world - 1) // world
+    lo = first_out + min(n_out, rank * per)
+    hi = first_out + min(n_out, (rank + 1) * per)
+    return {"lo": lo, "hi": hi, "enc_lo": max(0, lo - (K - 1)), "n_out": hi - lo}
+
+
+class StreamingMFCNet:
+    """Feeds frames one at a time through a `ResUNetMulti*`-style wrapper with SFC feature reuse.
+
+    step(frame, flows, depths) takes the newest frame (1,3,H,W), the K-1 flows of the current window
+    (flows[i-1]: current frame -> frame i earlier, as in the reference loop :264-271) and the K depth
+    maps in window order; returns fp32 logits (1,N,H,W) once K frames have been seen, else None.
+    """
+
+    def __init__(self, model, H, W, device="cuda", dtype_name=None):
+        self.model = model
+        self.K, self.N = model.num_frames, model.num_classes
+        self.H, self.W = H, W
+        self.device = torch.device(device)
+        self.dt = dtype_name or model.dtype_name or engine.default_dtype()
+        self.t = 0
+        self._build()
+
+    def _build(self):
+        m, K, N, H, W, dev = self.model, self.K, self.N, self.H, self.W, self.device
+        packer = engine.WeightPacker(dev, self.dt)
+        self._fingerprint = engine.params_fingerprint(m)
+        tdtype = engine._DTYPES[self.dt][0]
+        cin = m.base_model.channels
+        self.ring = torch.zeros((K, (N + 7) // 8, H, W, 8), dtype=tdtype, device=dev)   # slot s holds frame t with t % K == s
+        self.x_c8 = torch.empty((1, (cin + 7) // 8, H, W, 8), dtype=tdtype, device=dev)
+        self.out = torch.empty((1, N, H, W), dtype=torch.float32, device=dev)
+        ph = torch.zeros((1, cin, H, W), dtype=torch.float32, device=dev)
+        arena_sfc, arena_fus = engine.Arena(dev), engine.Arena(dev)
+        self.sfc, self.fus = [], []
+        for s in range(K):
+            arena_sfc.reset()
+            b = engine.Builder(dev, self.dt, packer, arena_sfc)
+            ext = Ext("frame", ph)
+            for c0 in range(0, cin, 8):
+                b.prog.gather([(ext, c) for c in range(c0, min(c0 + 8, cin))], self.x_c8[:, c0 // 8], 1, H, W)
+            m.base_model.record(b, Act(self.x_c8, cin), maps_c8=self.ring[s:s + 1])
+            b.prog.finalize()
+            self.sfc.append(b.prog)
+        phf = torch.zeros((1, 2, H, W), dtype=torch.float32, device=dev)
+        phd = torch.zeros((1, 1, H, W), dtype=torch.float32, device=dev)
+        for s in range(K):  # s = slot of the current frame; frame i earlier lives in slot (s - i) % K
+            arena_fus.reset()
+            b = engine.Builder(dev, self.dt, packer, arena_fus)
+            maps = [Act(self.ring[(s - i) % K:(s - i) % K + 1], N) for i in range(K)]
+            flows = [Ext(("flow", i), phf) for i in range(K - 1)] if m.optflow_inputs else None
+            depths = [Ext(("depth", i), phd) for i in range(K)] if m.depth_inputs else None
+            io = m.multiframe_net.record(b, maps, flows, depths, self.out)
+            b.prog.finalize()
+            self.fus.append((b.prog, io))
+        self.launches_per_frame = self.sfc[0].n_kernels + self.fus[0][0].n_kernels
+        self._keep = (packer, arena_sfc, arena_fus)
+
+    def reset(self):
+        self.t = 0
+
+    def encode(self, frame):
+        """Run the SFC network on one frame into its ring slot (used alone for the shard halo)."""
+        if engine.params_fingerprint(self.model) != self._fingerprint:
+            self._build()
+        s = self.t % self.K
+        f = frame.contiguous().float()
+        self.sfc[s].rebind({"frame": f})
+        with engine.device_guard(self.device):
+            self.sfc[s].run()
+        engine.record_stream(f)
+        self.t += 1
+        return s
+
+    def step(self, frame, flows=None, depths=None, out=None):
+        s = self.encode(frame)
+        if self.t < self.K:
+            return None
+        prog, io = self.fus[s]
+        tensors = {}
+        if self.model.optflow_inputs:
+            tensors.update({("flow", i): flows[i].contiguous().float() for i in range(self.K - 1)})
+        if self.model.depth_inputs:
+            tensors.update({("depth", i): depths[i].contiguous().float() for i in range(self.K)})
+        prog.rebind(tensors)
+        y = out if out is not None else torch.empty_like(self.out)
+        io.y_nchw = y.data_ptr()
+        with engine.device_guard(self.device):
+            prog.run()
+        for t in tensors.values():
+            engine.record_stream(t)
+        return y
