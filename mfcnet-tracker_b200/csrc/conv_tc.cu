@@ -25,9 +25,9 @@ namespace mfc {
 
 constexpr int kConvThreads = 256;
 
-template <bool BF16, bool AFF>
+template <bool BF16, bool AFF, int NT>
 __device__ __forceinline__ void stage_plane(const ConvParams& p, uint8_t* plane, const uint8_t* __restrict__ src,
-                                            const float* __restrict__ aff, int iy_base, int ix_base) {
+                                            const float* __restrict__ aff, int iy_base, int ix_base, int tid) {
   const int s = p.stride;
   const int P = p.t.P;
   const int items = p.t.rows_sub * P;
@@ -45,12 +45,12 @@ __device__ __forceinline__ void stage_plane(const ConvParams& p, uint8_t* plane,
   for (int sub = 0; sub < s * s; ++sub) {
     const int py = sub / s, px = sub - py * s;
     uint8_t* sp = plane + (size_t)sub * p.t.slots_sub * 16;
-    for (int base = threadIdx.x; base < items; base += kConvThreads * 4) {
+    for (int base = tid; base < items; base += NT * 4) {
       uint4 v[4];
       bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * kConvThreads;
+        const int idx = base + u * NT;
         v[u] = make_uint4(0, 0, 0, 0);
         ok[u] = false;
         if (idx < items) {
@@ -66,7 +66,7 @@ __device__ __forceinline__ void stage_plane(const ConvParams& p, uint8_t* plane,
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * kConvThreads;
+        const int idx = base + u * NT;
         if (idx < items) {
           if constexpr (AFF) {
             if (ok[u]) {
@@ -84,9 +84,35 @@ __device__ __forceinline__ void stage_plane(const ConvParams& p, uint8_t* plane,
   }
 }
 
-__device__ __forceinline__ void zero_plane(const ConvParams& p, uint8_t* plane) {
+template <int NT>
+__device__ __forceinline__ void zero_plane(const ConvParams& p, uint8_t* plane, int tid) {
   const int n16 = p.t.plane_bytes / 16;
-  for (int i = threadIdx.x; i < n16; i += kConvThreads) sts16(plane + (size_t)i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < n16; i += NT) sts16(plane + (size_t)i * 16, make_uint4(0, 0, 0, 0));
+}
+
+// stage the A planes [k0, k0 + 2*nks) of the K loop (channel chunks of the concat) for one tile
+template <bool BF16, int NT>
+__device__ __forceinline__ void stage_a(const ConvParams& p, uint8_t* abuf, int b, int k0, int nplanes, int iy_base, int ix_base,
+                                        int tid) {
+  for (int q = 0; q < nplanes; ++q) {
+    const int k = k0 + q;
+    uint8_t* plane = abuf + (size_t)q * p.t.plane_bytes;
+    if (k >= p.t.cin_chunks) {
+      zero_plane<NT>(p, plane, tid);
+      continue;
+    }
+    int si = 0;
+    while (k >= p.src_end[si]) ++si;
+    const int kin = k - (si ? p.src_end[si - 1] : 0);
+    const int nch = p.src_end[si] - (si ? p.src_end[si - 1] : 0);
+    const uint8_t* src = p.src_ptr[si] + (size_t)b * p.src_bs[si] + (size_t)kin * p.Hin * p.Win * 16;
+    if (p.src_aff[si]) {
+      const float* aff = p.src_aff[si] + ((size_t)b * nch + kin) * 16;
+      stage_plane<BF16, true, NT>(p, plane, src, aff, iy_base, ix_base, tid);
+    } else {
+      stage_plane<BF16, false, NT>(p, plane, src, nullptr, iy_base, ix_base, tid);
+    }
+  }
 }
 
 // warp-wide sum of 16 per-lane values, result for channel ch(lane) left in a[0];
@@ -127,6 +153,121 @@ __device__ __forceinline__ float reduce_scatter16(float (&a)[16], int lane) {
   }
   a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
   return a[0];
+}
+
+// Epilogue of one tile: TMEM accumulators -> scale/shift -> residual -> ReLU -> GroupNorm partial sums ->
+// C8 / NCHW stores.  Called by 8 warps: `lq` = TMEM lane quarter of the warp (hardware: warp id % 4),
+// `half` = which of the two interleaved run sets (r = half, half+2, ...) the warp owns.
+template <bool BF16>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem_acc, const float* s_scale, const float* s_shift,
+                                              float* my_stats, int b, int oy0, int ox0, int nbk, int lq, int half, int lane) {
+  const int NB = p.t.NB;
+  const int cc_out = (p.Cout + 7) >> 3;
+  // With a single 16-channel column group the per-channel sums stay in registers for the whole tile
+  // and are reduced across lanes ONCE (30 shuffles per tile instead of per 128-pixel run).
+  const bool defer = p.stats != nullptr && NB == 16;
+  float d1[16], d2[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d1[i] = d2[i] = 0.0f;
+  for (int r = half; r < p.t.R; r += 2) {
+    const int sl = r * 128 + lq * 32 + lane;
+    const int row = (int)fdiv((uint32_t)sl, p.divP);
+    const int col = sl - row * p.t.P;
+    const int oy = oy0 + row, ox = ox0 + col;
+    const bool valid = row < p.t.TH && col < p.t.TW && oy < p.Hout && ox < p.Wout;
+    const size_t pix = (size_t)oy * p.Wout + ox;
+    for (int j = 0; j < NB; j += 16) {
+      uint32_t acc[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(lq * 32) << 16) + (uint32_t)(r * NB + j), acc);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(acc[i]), s_scale[j + i], s_shift[j + i]);
+      const int co0 = nbk * NB + j;
+      if (p.res && valid) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = (co0 >> 3) + h;
+          if (ch < cc_out) {
+            uint4 rv = ldg_nc16(p.res + (size_t)b * p.res_bs + ((size_t)ch * p.Hout * p.Wout + pix) * 16);
+            float rf[8];
+            unpack8<BF16>(rv, rf);
+            if (p.res_aff) {
+              const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float2 a = __ldg(ra + i);
+                rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[h * 8 + i] += rf[i];
+          }
+        }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+      }
+      if (p.stats) {
+        if (defer) {
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              d1[i] += f[i];
+              d2[i] = fmaf(f[i], f[i], d2[i]);
+            }
+          }
+        } else {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float m = valid ? f[i] : 0.0f;
+            s1[i] = m;
+            s2[i] = m * m;
+          }
+          const float t1 = reduce_scatter16(s1, lane);
+          const float t2 = reduce_scatter16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            my_stats[(j + c) * 2 + 0] += t1;
+            my_stats[(j + c) * 2 + 1] += t2;
+          }
+        }
+      }
+      if (valid) {
+        if (p.y) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = (co0 >> 3) + h;
+            if (ch < cc_out) {
+              float g[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] = f[h * 8 + i];
+              uint4 ov = pack8<BF16>(g);
+              *reinterpret_cast<uint4*>(p.y + (size_t)b * p.y_bs + ((size_t)ch * p.Hout * p.Wout + pix) * 16) = ov;
+            }
+          }
+        }
+        if (p.y_nchw) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int co = co0 + i;
+            if (co < p.Cout) p.y_nchw[((size_t)b * p.Cout + co) * p.Hout * p.Wout + pix] = f[i];
+          }
+        }
+      }
+    }
+  }
+  if (defer) {
+    const float t1 = reduce_scatter16(d1, lane);
+    const float t2 = reduce_scatter16(d2, lane);
+    if ((lane & 1) == 0) {
+      const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      my_stats[c * 2 + 0] += t1;
+      my_stats[c * 2 + 1] += t2;
+    }
+  }
 }
 
 template <bool BF16>
@@ -186,25 +327,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       cp_async_commit();
     }
     // activations: 2*nks planes
-    for (int q = 0; q < 2 * nks; ++q) {
-      const int k = ks * p.t.CBc + q;
-      uint8_t* plane = abuf + (size_t)q * p.t.plane_bytes;
-      if (k >= p.t.cin_chunks) {
-        zero_plane(p, plane);
-        continue;
-      }
-      int si = 0;
-      while (k >= p.src_end[si]) ++si;
-      const int kin = k - (si ? p.src_end[si - 1] : 0);
-      const int nch = p.src_end[si] - (si ? p.src_end[si - 1] : 0);
-      const uint8_t* src = p.src_ptr[si] + (size_t)b * p.src_bs[si] + (size_t)kin * p.Hin * p.Win * 16;
-      if (p.src_aff[si]) {
-        const float* aff = p.src_aff[si] + ((size_t)b * nch + kin) * 16;
-        stage_plane<BF16, true>(p, plane, src, aff, iy_base, ix_base);
-      } else {
-        stage_plane<BF16, false>(p, plane, src, nullptr, iy_base, ix_base);
-      }
-    }
+    stage_a<BF16, kConvThreads>(p, abuf, b, ks * p.t.CBc, 2 * nks, iy_base, ix_base, tid);
     if (ks == 0) {
       // TMEM is claimed only now, after the first tile has been staged: a CTA that has to wait for
       // columns held by a co-resident CTA overlaps that wait with its own global loads.
@@ -272,89 +395,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   tc_fence_after();
 
   // ---- epilogue
-  const int lq = warp & 3, half = warp >> 2;
-  const int cc_out = (p.Cout + 7) >> 3;
-  float* my_stats = s_stats + (size_t)warp * NB * 2;
-  for (int r = half; r < p.t.R; r += 2) {
-    const int sl = r * 128 + lq * 32 + lane;
-    const int row = (int)fdiv((uint32_t)sl, p.divP);
-    const int col = sl - row * p.t.P;
-    const int oy = oy0 + row, ox = ox0 + col;
-    const bool valid = row < p.t.TH && col < p.t.TW && oy < p.Hout && ox < p.Wout;
-    const size_t pix = (size_t)oy * p.Wout + ox;
-    for (int j = 0; j < NB; j += 16) {
-      uint32_t acc[16];
-      tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(r * NB + j), acc);
-      tmem_ld_wait();
-      float f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(acc[i]), s_scale[j + i], s_shift[j + i]);
-      const int co0 = nbk * NB + j;
-      if (p.res && valid) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int ch = (co0 >> 3) + h;
-          if (ch < cc_out) {
-            uint4 rv = ldg_nc16(p.res + (size_t)b * p.res_bs + ((size_t)ch * p.Hout * p.Wout + pix) * 16);
-            float rf[8];
-            unpack8<BF16>(rv, rf);
-            if (p.res_aff) {
-              const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float2 a = __ldg(ra + i);
-                rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[h * 8 + i] += rf[i];
-          }
-        }
-      }
-      if (p.act == 1) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
-      }
-      if (p.stats) {
-        float s1[16], s2[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float m = valid ? f[i] : 0.0f;
-          s1[i] = m;
-          s2[i] = m * m;
-        }
-        const float t1 = reduce_scatter16(s1, lane);
-        const float t2 = reduce_scatter16(s2, lane);
-        if ((lane & 1) == 0) {
-          const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          my_stats[(j + c) * 2 + 0] += t1;
-          my_stats[(j + c) * 2 + 1] += t2;
-        }
-      }
-      if (valid) {
-        if (p.y) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ch = (co0 >> 3) + h;
-            if (ch < cc_out) {
-              float g[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) g[i] = f[h * 8 + i];
-              uint4 ov = pack8<BF16>(g);
-              *reinterpret_cast<uint4*>(p.y + (size_t)b * p.y_bs + ((size_t)ch * p.Hout * p.Wout + pix) * 16) = ov;
-            }
-          }
-        }
-        if (p.y_nchw) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int co = co0 + i;
-            if (co < p.Cout) p.y_nchw[((size_t)b * p.Cout + co) * p.Hout * p.Wout + pix] = f[i];
-          }
-        }
-      }
-    }
-  }
+  epilogue_tile<BF16>(p, tmem_base, s_scale, s_shift, s_stats + (size_t)warp * NB * 2, b, oy0, ox0, nbk, warp & 3, warp >> 2, lane);
 
   // ---- teardown
   tc_fence_before();
