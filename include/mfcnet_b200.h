@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MFC_ABI_VERSION 1
+#define MFC_ABI_VERSION 2
 
 /* error codes */
 #define MFC_OK 0
@@ -94,9 +94,13 @@ typedef struct MfcConvInfo {
   int cin_chunks;      /* total 8-channel input planes (sum of src[].nchunks)         */
   int ksteps;          /* ceil(cin_chunks/2): 16-channel MMA K-steps per tap          */
   int tile_h, tile_w;  /* output tile                                                 */
-  int tiles_per_image; /* tiles in one sample: stats partials are [B*tiles][nb*nblk][2] */
+  int tiles_per_image; /* output tiles in one sample                                  */
+  int stats_per_image; /* GroupNorm partial records per sample (tiles x epilogue warps):
+                          the stats buffer is [B][stats_per_image][nb*nblk][2]         */
   int runs;            /* 128-row MMA runs per tile                                   */
   int kstages;         /* channel stages of the K loop                                */
+  int nstages;         /* depth of the shared-memory stage ring                       */
+  int grid;            /* persistent CTAs launched                                    */
   int smem_bytes;      /* dynamic shared memory per CTA                               */
   int tmem_cols;       /* TMEM columns allocated per CTA                              */
   long long packed_weight_bytes;
@@ -151,14 +155,14 @@ typedef struct MfcConvIO {
   void* y_c8;                /* C8 output or NULL                            */
   long long y_batch_stride;  /* bytes                                        */
   float* y_nchw;             /* fp32 [B][Cout][Hout][Wout] or NULL           */
-  float* stats;              /* [B][tiles_per_image][nb*nblk][2] or NULL     */
+  float* stats;              /* [B][stats_per_image][nb*nblk][2] or NULL     */
 } MfcConvIO;
 int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream);
 
 /* GroupNorm statistics -> per-(sample,channel) affine.  Replaces nn.GroupNorm
  * (models/resunet.py:72,77) split in two: partial sums come from the producing conv's
  * epilogue, this finalises them (fp64) into scale = g*rstd, shift = b - mean*g*rstd. */
-int mfc_gn_finalize(const float* stats, int B, int tiles_per_image, int cpad, int C, int groups,
+int mfc_gn_finalize(const float* stats, int B, int stats_per_image, int cpad, int C, int groups,
                     long long pixels, const float* gamma, const float* beta, float eps,
                     float* affine /*[B][ceil(C/8)*8][2]*/, void* stream);
 
@@ -269,7 +273,7 @@ typedef struct MfcGnArgs {
   const float* beta;
   float* affine;
   long long pixels;
-  int B, tiles_per_image, cpad, C, groups;
+  int B, stats_per_image, cpad, C, groups;
   float eps;
 } MfcGnArgs;
 

@@ -23,8 +23,8 @@ class MfcGather(C.Structure):
 
 class MfcConvInfo(C.Structure):
     _fields_ = [("nb", c_int), ("nblk", c_int), ("cin_chunks", c_int), ("ksteps", c_int), ("tile_h", c_int),
-                ("tile_w", c_int), ("tiles_per_image", c_int), ("runs", c_int), ("kstages", c_int),
-                ("smem_bytes", c_int), ("tmem_cols", c_int), ("packed_weight_bytes", c_ll)]
+                ("tile_w", c_int), ("tiles_per_image", c_int), ("stats_per_image", c_int), ("runs", c_int),
+                ("kstages", c_int), ("nstages", c_int), ("grid", c_int), ("smem_bytes", c_int), ("tmem_cols", c_int), ("packed_weight_bytes", c_ll)]
 
 
 class MfcSrc(C.Structure):
@@ -54,7 +54,7 @@ class MfcWarpArgs(C.Structure):
 
 class MfcGnArgs(C.Structure):
     _fields_ = [("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("affine", c_void_p), ("pixels", c_ll),
-                ("B", c_int), ("tiles_per_image", c_int), ("cpad", c_int), ("C", c_int), ("groups", c_int), ("eps", c_float)]
+                ("B", c_int), ("stats_per_image", c_int), ("cpad", c_int), ("C", c_int), ("groups", c_int), ("eps", c_float)]
 
 
 class MfcAddArgs(C.Structure):
@@ -133,7 +133,7 @@ def load(build_if_missing=True):
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.argtypes = args
             fn.restype = res
-        if lib.mfc_abi_version() != 1:
+        if lib.mfc_abi_version() != 2:
             raise RuntimeError("libmfcnet_b200.so ABI version mismatch")
         _lib = _PlanOnly(lib) if plan_only() else lib
     return _lib

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libmfcnet_b200.so (include/mfcnet_b200.h): argument validation, the conv
 // planner cache, and dispatch into the kernel launchers.  No allocation, no synchronisation.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -60,7 +61,7 @@ int arch_ok() {
 inline bool dtype_ok(int dt) { return dt == MFC_F16 || dt == MFC_BF16; }
 
 // ---- conv planner cache ---------------------------------------------------------------------
-using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int, int, int, int>;
+using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int>;
 std::mutex g_plan_mu;
 std::map<PlanKey, mfc::ConvTiling> g_plans;
 
@@ -85,9 +86,12 @@ int validate_desc(const MfcConvDesc* d) {
 }
 
 int get_tiling(const MfcConvDesc* d, mfc::ConvTiling* out) {
-  int chunks = 0;
-  for (int i = 0; i < d->nsrc; ++i) chunks += d->src[i].nchunks;
-  PlanKey key{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks};
+  int chunks = 0, aff = 0;
+  for (int i = 0; i < d->nsrc; ++i) {
+    chunks += d->src[i].nchunks;
+    aff |= d->src[i].affine != nullptr;
+  }
+  PlanKey key{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks, aff};
   {
     std::lock_guard<std::mutex> g(g_plan_mu);
     auto it = g_plans.find(key);
@@ -164,8 +168,11 @@ int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info) {
   info->tile_h = t.TH;
   info->tile_w = t.TW;
   info->tiles_per_image = t.tiles_x * t.tiles_y;
+  info->stats_per_image = t.grid * mfc::kEpiWarps;
   info->runs = t.R;
   info->kstages = t.kstages;
+  info->nstages = t.nstages;
+  info->grid = t.grid;
   info->smem_bytes = (int)t.smem_bytes;
   info->tmem_cols = (int)t.tmem_cols;
   info->packed_weight_bytes = (long long)t.nblk * t.ksteps * d->kh * d->kw * 2 * t.NB * 16;
@@ -211,6 +218,9 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
     p.src_end[i] = end;
   }
   p.divP = mfc::make_fastdiv((uint32_t)p.t.P);
+  p.div_nblk = mfc::make_fastdiv((uint32_t)p.t.nblk);
+  p.div_tx = mfc::make_fastdiv((uint32_t)p.t.tiles_x);
+  p.div_ty = mfc::make_fastdiv((uint32_t)p.t.tiles_y);
   p.idesc = mfc::make_idesc_f16(p.t.NB, d->dtype == MFC_BF16);
   p.w = (const uint8_t*)io->w_packed;
   p.scale = io->scale;
@@ -222,17 +232,22 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
   p.y_bs = io->y_batch_stride;
   p.y_nchw = io->y_nchw;
   p.stats = io->stats;
+  {
+    static const int dbg = getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0;
+    p.debug = dbg;
+  }
+  if (p.stats && p.t.NB * p.t.nblk > 256) return fail(MFC_EINVAL, "conv: GroupNorm statistics need Cout <= 256");
   if (((uintptr_t)p.w & 15) || ((uintptr_t)p.y & 15) || ((uintptr_t)p.res & 15) || (p.y_bs & 15) || (p.res_bs & 15))
     return fail(MFC_EINVAL, "conv: weights / output / residual not 16-byte aligned");
   MFC_LAUNCH(mfc::launch_conv(p, d->dtype == MFC_BF16, (cudaStream_t)stream), "conv2d_fwd");
 }
 
-int mfc_gn_finalize(const float* stats, int B, int tiles_per_image, int cpad, int C, int groups, long long pixels, const float* gamma,
+int mfc_gn_finalize(const float* stats, int B, int stats_per_image, int cpad, int C, int groups, long long pixels, const float* gamma,
                     const float* beta, float eps, float* affine, void* stream) {
   MFC_REQUIRE_ARCH();
-  if (!stats || !gamma || !beta || !affine || B < 1 || tiles_per_image < 1 || C < 1 || groups < 1 || C % groups || cpad < C || pixels < 1)
+  if (!stats || !gamma || !beta || !affine || B < 1 || stats_per_image < 1 || C < 1 || groups < 1 || C % groups || cpad < C || pixels < 1)
     return fail(MFC_EINVAL, "gn_finalize: bad argument");
-  MFC_LAUNCH(mfc::launch_gn_finalize(stats, B, tiles_per_image, cpad, C, groups, pixels, gamma, beta, eps, affine, (cudaStream_t)stream),
+  MFC_LAUNCH(mfc::launch_gn_finalize(stats, B, stats_per_image, cpad, C, groups, pixels, gamma, beta, eps, affine, (cudaStream_t)stream),
              "gn_finalize");
 }
 
@@ -317,7 +332,7 @@ int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
         break;
       case MFC_OP_GN_FINALIZE: {
         const MfcGnArgs* g = (const MfcGnArgs*)c.a;
-        rc = mfc_gn_finalize(g->stats, g->B, g->tiles_per_image, g->cpad, g->C, g->groups, g->pixels, g->gamma, g->beta, g->eps, g->affine, stream);
+        rc = mfc_gn_finalize(g->stats, g->B, g->stats_per_image, g->cpad, g->C, g->groups, g->pixels, g->gamma, g->beta, g->eps, g->affine, stream);
         break;
       }
       case MFC_OP_AFFINE_SILU_ADD: {

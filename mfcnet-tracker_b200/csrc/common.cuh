@@ -30,16 +30,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Bounded wait (~2 s of SM clocks): a protocol bug must fault the launch, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 0x3FFu) != 0) continue;  // try_wait suspends in hardware; look at the clock rarely
+    if (t0 == 0) t0 = clock64();
     if (clock64() - t0 > 4000000000LL) {
       printf("mfc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
   }
+}
+
+// True in exactly one lane of a fully converged warp.  ptxas knows that code guarded by elect.sync runs
+// in a single thread, so values computed there stay in uniform registers (no per-value waterfall loops
+// in front of every tcgen05.mma, which a `lane == 0` test produces).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -111,6 +130,19 @@ __host__ __device__ inline uint32_t make_idesc_f16(int n, bool bf16) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+// 16-byte async copy that writes zeros when `valid` is false (src-size 0): the conv zero padding.
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(const void* p) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)) : "memory");
+  return r;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -161,6 +193,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
+__device__ __forceinline__ float tanh_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
 // silu(y) = y * sigmoid(y) = 0.5*y*(1 + tanh(y/2)): one MUFU op per element.
 __device__ __forceinline__ float silu_fast(float y) {
   float t;

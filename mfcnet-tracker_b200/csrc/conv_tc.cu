@@ -1,6 +1,11 @@
 // conv_tc.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM).
 //
-// One CTA computes a TH x TW output tile for one N-block of output channels.
+// Persistent, warp-specialised kernel: one CTA per SM walks a list of work items
+// (item = output tile x N-block of output channels) through three pipelines that overlap
+//   8 producer warps : global -> (concat / nearest x2 / GroupNorm-affine + SiLU / zero pad) -> smem stage ring
+//   1 MMA warp       : tcgen05.mma over the staged tile, accumulators in one of two TMEM buffers
+//   8 epilogue warps : tcgen05.ld -> scale/shift -> residual -> ReLU -> GroupNorm partial sums -> stores
+// synchronised by mbarriers only (full/empty per smem stage, full/empty per TMEM buffer).
 //
 //   A operand (activations): the input halo tile is staged ONCE in shared memory as 8-channel planes
 //     plane[q][slot] = 16 bytes = 8 channels of one pixel,   slot = row*P + col,  P = TW + halo
@@ -11,74 +16,74 @@
 //   An MMA "run" is 128 consecutive slots of the flattened tile (M = 128); slots that fall on halo
 //   columns produce garbage rows that the epilogue drops.  Stride-2 convs (3x3 s2, and the
 //   pixel-unshuffle 2x2 s2) de-interleave the tile into 4 parity sub-planes while staging.
-//   The staging loop is where the fusions live: channel concat (a list of plane pointers),
-//   nearest x2 upsample (index shift), GroupNorm-apply + SiLU (per-(sample,channel) affine), zero pad.
 //   B operand (weights): pre-packed on the host side of the ABI into the smem image
-//     [kstep][tap][khalf(2)][NB][8]  -> cp.async'd verbatim.
-//   D: TMEM, R runs x NB fp32 columns.
-//   Epilogue: tcgen05.ld 32 lanes x 16 columns -> scale/shift (bias / folded BN) -> residual
-//   (optionally silu(affine)) -> ReLU -> per-channel GroupNorm partial sums -> C8 fp16/bf16
-//   and/or NCHW fp32 stores (coalesced: lane = pixel).
+//     [n-block][kstep][tap][khalf(2)][NB][8]; resident in smem for the whole kernel when the layer has a
+//   single K stage and N-block, otherwise streamed with each K stage (cp.async).
+//   D: TMEM, R runs x NB fp32 columns per accumulator buffer.
 #include "conv_tc.cuh"
 
 namespace mfc {
 
-constexpr int kConvThreads = 256;
-
-template <bool BF16, bool AFF, int NT>
-__device__ __forceinline__ void stage_plane(const ConvParams& p, uint8_t* plane, const uint8_t* __restrict__ src,
-                                            const float* __restrict__ aff, int iy_base, int ix_base, int tid) {
+// ---- producers: phase 1, asynchronous raw copy of one 8-channel plane of the halo tile --------------
+// Every thread enumerates the same (idx -> row, col) items in phase 1 and phase 2, so a thread only ever
+// touches smem slots it filled itself: cp.async.wait_group is the only synchronisation between the phases.
+template <int NT>
+__device__ __forceinline__ void issue_plane(const ConvParams& p, uint8_t* plane, const uint8_t* __restrict__ src, int iy_base,
+                                            int ix_base, int tid) {
   const int s = p.stride;
   const int P = p.t.P;
   const int items = p.t.rows_sub * P;
   const int Hup = p.Hin * p.upsample, Wup = p.Win * p.upsample;
   const int ush = p.upsample == 2 ? 1 : 0;
-  float sc[8], sh[8];
-  if constexpr (AFF) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float2 a = __ldg(reinterpret_cast<const float2*>(aff) + i);
-      sc[i] = a.x;
-      sh[i] = a.y;
+  for (int sub = 0; sub < s * s; ++sub) {
+    const int py = sub / s, px = sub - py * s;
+    uint8_t* sp = plane + (size_t)sub * p.t.slots_sub * 16;
+#pragma unroll 2
+    for (int idx = tid; idx < items; idx += NT) {
+      const int r2 = (int)fdiv((uint32_t)idx, p.divP);
+      const int c2 = idx - r2 * P;
+      const int iy = iy_base + r2 * s + py;
+      const int ix = ix_base + c2 * s + px;
+      const bool ok = iy >= 0 && iy < Hup && ix >= 0 && ix < Wup;
+      const size_t off = ok ? ((size_t)(iy >> ush) * p.Win + (ix >> ush)) * 16 : 0;
+      cp_async16_zfill(sp + (size_t)idx * 16, src + off, ok);  // out of image -> zeros (the conv padding)
     }
+  }
+}
+
+// ---- producers: phase 2, in-place GroupNorm-affine + SiLU of the thread's own slots ----------------
+template <bool BF16, int NT>
+__device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* plane, const float* __restrict__ aff, int iy_base,
+                                                int ix_base, int tid) {
+  const int s = p.stride;
+  const int P = p.t.P;
+  const int items = p.t.rows_sub * P;
+  const int Hup = p.Hin * p.upsample, Wup = p.Win * p.upsample;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 a = __ldg(reinterpret_cast<const float2*>(aff) + i);
+    sc[i] = 0.5f * a.x;  // silu(y) = h + h*tanh(h) with h = y/2: the halving is folded into the affine
+    sh[i] = 0.5f * a.y;
   }
   for (int sub = 0; sub < s * s; ++sub) {
     const int py = sub / s, px = sub - py * s;
     uint8_t* sp = plane + (size_t)sub * p.t.slots_sub * 16;
-    for (int base = tid; base < items; base += NT * 4) {
-      uint4 v[4];
-      bool ok[4];
+#pragma unroll 2
+    for (int idx = tid; idx < items; idx += NT) {
+      const int r2 = (int)fdiv((uint32_t)idx, p.divP);
+      const int c2 = idx - r2 * P;
+      const int iy = iy_base + r2 * s + py;
+      const int ix = ix_base + c2 * s + px;
+      if (iy >= 0 && iy < Hup && ix >= 0 && ix < Wup) {  // padding stays exactly zero
+        float f[8];
+        unpack8<BF16>(lds16(sp + (size_t)idx * 16), f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * NT;
-        v[u] = make_uint4(0, 0, 0, 0);
-        ok[u] = false;
-        if (idx < items) {
-          const int r2 = (int)fdiv((uint32_t)idx, p.divP);
-          const int c2 = idx - r2 * P;
-          const int iy = iy_base + r2 * s + py;
-          const int ix = ix_base + c2 * s + px;
-          if (iy >= 0 && iy < Hup && ix >= 0 && ix < Wup) {
-            ok[u] = true;
-            v[u] = ldg_nc16(src + ((size_t)(iy >> ush) * p.Win + (ix >> ush)) * 16);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float h = fmaf(f[i], sc[i], sh[i]);
+          f[i] = fmaf(h, tanh_fast(h), h);
         }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * NT;
-        if (idx < items) {
-          if constexpr (AFF) {
-            if (ok[u]) {
-              float f[8];
-              unpack8<BF16>(v[u], f);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = silu_fast(fmaf(f[i], sc[i], sh[i]));
-              v[u] = pack8<BF16>(f);
-            }
-          }
-          sts16(sp + (size_t)idx * 16, v[u]);
-        }
+        sts16(sp + (size_t)idx * 16, pack8<BF16>(f));
       }
     }
   }
@@ -90,28 +95,70 @@ __device__ __forceinline__ void zero_plane(const ConvParams& p, uint8_t* plane, 
   for (int i = tid; i < n16; i += NT) sts16(plane + (size_t)i * 16, make_uint4(0, 0, 0, 0));
 }
 
-// stage the A planes [k0, k0 + 2*nks) of the K loop (channel chunks of the concat) for one tile
-template <bool BF16, int NT>
-__device__ __forceinline__ void stage_a(const ConvParams& p, uint8_t* abuf, int b, int k0, int nplanes, int iy_base, int ix_base,
-                                        int tid) {
-  for (int q = 0; q < nplanes; ++q) {
-    const int k = k0 + q;
+struct SrcRef {
+  const uint8_t* src;
+  const float* aff;
+};
+// plane k of the channel concat of sample b: its source pointer and (optional) GroupNorm affine
+__device__ __forceinline__ SrcRef locate_plane(const ConvParams& p, int b, int k) {
+  int si = 0;
+  while (k >= p.src_end[si]) ++si;
+  const int kin = k - (si ? p.src_end[si - 1] : 0);
+  const int nch = p.src_end[si] - (si ? p.src_end[si - 1] : 0);
+  SrcRef r;
+  r.src = p.src_ptr[si] + (size_t)b * p.src_bs[si] + (size_t)kin * p.Hin * p.Win * 16;
+  r.aff = p.src_aff[si] ? p.src_aff[si] + ((size_t)b * nch + kin) * 16 : nullptr;
+  return r;
+}
+
+// phase 1 of one (item, K stage): weights (when streamed) + all A planes, asynchronously
+template <int NT>
+__device__ __forceinline__ void issue_stage(const ConvParams& p, uint8_t* abuf, int b, int nbk, int ks, int iy_base, int ix_base,
+                                            int tid) {
+  const int ksteps_per_stage = p.t.CBc / 2;
+  const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
+  if (!p.t.b_resident) {
+    const int taps = p.kh * p.kw;
+    uint8_t* bbuf = abuf + p.t.a_stage_bytes;
+    const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * taps * (size_t)(2 * p.t.NB * 16);
+    const int n16 = nks * taps * 2 * p.t.NB;
+#pragma unroll 4
+    for (int i = tid; i < n16; i += NT) cp_async16(bbuf + (size_t)i * 16, wsrc + (size_t)i * 16);
+  }
+  for (int q = 0; q < 2 * nks; ++q) {
+    const int k = ks * p.t.CBc + q;
     uint8_t* plane = abuf + (size_t)q * p.t.plane_bytes;
     if (k >= p.t.cin_chunks) {
       zero_plane<NT>(p, plane, tid);
       continue;
     }
-    int si = 0;
-    while (k >= p.src_end[si]) ++si;
-    const int kin = k - (si ? p.src_end[si - 1] : 0);
-    const int nch = p.src_end[si] - (si ? p.src_end[si - 1] : 0);
-    const uint8_t* src = p.src_ptr[si] + (size_t)b * p.src_bs[si] + (size_t)kin * p.Hin * p.Win * 16;
-    if (p.src_aff[si]) {
-      const float* aff = p.src_aff[si] + ((size_t)b * nch + kin) * 16;
-      stage_plane<BF16, true, NT>(p, plane, src, aff, iy_base, ix_base, tid);
-    } else {
-      stage_plane<BF16, false, NT>(p, plane, src, nullptr, iy_base, ix_base, tid);
-    }
+    issue_plane<NT>(p, plane, locate_plane(p, b, k).src, iy_base, ix_base, tid);
+  }
+}
+
+// phase 2 of one (item, K stage)
+template <bool BF16, int NT>
+__device__ __forceinline__ void transform_stage(const ConvParams& p, uint8_t* abuf, int b, int ks, int iy_base, int ix_base, int tid) {
+  const int ksteps_per_stage = p.t.CBc / 2;
+  const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
+  for (int q = 0; q < 2 * nks; ++q) {
+    const int k = ks * p.t.CBc + q;
+    if (k >= p.t.cin_chunks) break;
+    const SrcRef r = locate_plane(p, b, k);
+    if (r.aff) transform_plane<BF16, NT>(p, abuf + (size_t)q * p.t.plane_bytes, r.aff, iy_base, ix_base, tid);
+  }
+}
+
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait_group<0>(); break;
+    case 1: cp_async_wait_group<1>(); break;
+    case 2: cp_async_wait_group<2>(); break;
+    case 3: cp_async_wait_group<3>(); break;
+    case 4: cp_async_wait_group<4>(); break;
+    case 5: cp_async_wait_group<5>(); break;
+    case 6: cp_async_wait_group<6>(); break;
+    default: cp_async_wait_group<7>(); break;
   }
 }
 
@@ -155,261 +202,468 @@ __device__ __forceinline__ float reduce_scatter16(float (&a)[16], int lane) {
   return a[0];
 }
 
-// Epilogue of one tile: TMEM accumulators -> scale/shift -> residual -> ReLU -> GroupNorm partial sums ->
-// C8 / NCHW stores.  Called by 8 warps: `lq` = TMEM lane quarter of the warp (hardware: warp id % 4),
+// ---- epilogue -----------------------------------------------------------------------------------------
+struct PixRef {
+  size_t pix;
+  bool valid;
+};
+__device__ __forceinline__ PixRef run_pixel(const ConvParams& p, int r, int lq, int lane, int oy0, int ox0) {
+  const int sl = r * 128 + lq * 32 + lane;
+  const int row = (int)fdiv((uint32_t)sl, p.divP);
+  const int col = sl - row * p.t.P;
+  const int oy = oy0 + row, ox = ox0 + col;
+  PixRef q;
+  q.valid = row < p.t.TH && col < p.t.TW && oy < p.Hout && ox < p.Wout;
+  q.pix = (size_t)oy * p.Wout + ox;
+  return q;
+}
+
+__device__ __forceinline__ int stat_channel(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// Epilogue specialisations (template MODE): the combinations the networks use get their own lean code
+// path (fewer instructions, and a smaller hot loop for the instruction cache); anything else runs GENERIC.
+enum : int { EPI_PLAIN = 0, EPI_STATS = 1, EPI_RES = 2, EPI_NCHW = 3, EPI_GENERIC = 4 };
+
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// Epilogue of one work item: TMEM accumulators -> scale/shift -> residual -> ReLU -> GroupNorm partial
+// sums -> C8 / NCHW stores.  Called by 8 warps: `lq` = TMEM lane quarter of the warp (hardware: warp id % 4),
 // `half` = which of the two interleaved run sets (r = half, half+2, ...) the warp owns.
-template <bool BF16>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem_acc, const float* s_scale, const float* s_shift,
-                                              float* my_stats, int b, int oy0, int ox0, int nbk, int lq, int half, int lane) {
-  const int NB = p.t.NB;
+// The TMEM load of step s+1 is issued as soon as step s's accumulators have been converted, so its
+// latency hides behind the statistics / packing / stores of step s.
+// GroupNorm sums accumulate ACROSS items (registers d1/d2 when NB == 16, else the warp's smem scratch
+// `my_stats` [cpad][2]) and are flushed by flush_stats() when the sample index changes.
+// NB16: scale/shift live in registers (sc/sh) for the whole kernel; otherwise they are read from smem.
+template <bool BF16, int MODE, bool NB16>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem_acc, uint32_t s_scale_addr, float* my_stats,
+                                              float (&d1)[16], float (&d2)[16], const float (&sc)[16], const float (&sh)[16], int b,
+                                              int oy0, int ox0, int nbk, int lq, int half, int lane) {
+  constexpr bool kRes = MODE == EPI_RES || MODE == EPI_GENERIC;
+  constexpr bool kStats = MODE == EPI_STATS || MODE == EPI_GENERIC;
+  constexpr bool kNchw = MODE == EPI_NCHW || MODE == EPI_GENERIC;
+  const int NB = NB16 ? 16 : p.t.NB;
+  const int cpad = NB * p.t.nblk;
   const int cc_out = (p.Cout + 7) >> 3;
-  // With a single 16-channel column group the per-channel sums stay in registers for the whole tile
-  // and are reduced across lanes ONCE (30 shuffles per tile instead of per 128-pixel run).
-  const bool defer = p.stats != nullptr && NB == 16;
-  float d1[16], d2[16];
+  const size_t HWo = (size_t)p.Hout * p.Wout;
+  const bool has_res = kRes && p.res != nullptr;
+  const bool has_stats = kStats && p.stats != nullptr;
+  const bool has_nchw = kNchw && p.y_nchw != nullptr;
+  const bool has_c8 = (MODE != EPI_NCHW && MODE != EPI_GENERIC) || p.y != nullptr;
+  const uint8_t* res_b = has_res ? p.res + (size_t)b * p.res_bs : nullptr;
+  uint8_t* y_b = has_c8 ? p.y + (size_t)b * p.y_bs : nullptr;
+  const uint32_t tm_lane = tmem_acc + ((uint32_t)(lq * 32) << 16);
+  int r = half, j = 0;
+  if (r >= p.t.R) return;
+  uint32_t acc[16];
+  tmem_ld16(tm_lane + (uint32_t)(r * NB + j), acc);
+  uint4 rv_next[2];
+  rv_next[0] = rv_next[1] = make_uint4(0, 0, 0, 0);
+  auto fetch_res = [&](int rr, int jj) {
+    // residual of step (rr, jj): issued one step ahead so that its latency hides behind the current step
+    const PixRef q = run_pixel(p, rr, lq, lane, oy0, ox0);
+    const int co0 = nbk * NB + jj;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) d1[i] = d2[i] = 0.0f;
-  for (int r = half; r < p.t.R; r += 2) {
-    const int sl = r * 128 + lq * 32 + lane;
-    const int row = (int)fdiv((uint32_t)sl, p.divP);
-    const int col = sl - row * p.t.P;
-    const int oy = oy0 + row, ox = ox0 + col;
-    const bool valid = row < p.t.TH && col < p.t.TW && oy < p.Hout && ox < p.Wout;
-    const size_t pix = (size_t)oy * p.Wout + ox;
-    for (int j = 0; j < NB; j += 16) {
-      uint32_t acc[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(lq * 32) << 16) + (uint32_t)(r * NB + j), acc);
+    for (int h = 0; h < 2; ++h) {
+      const int ch = (co0 >> 3) + h;
+      rv_next[h] = (q.valid && ch < cc_out) ? ldg_nc16(res_b + ((size_t)ch * HWo + q.pix) * 16) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  if (has_res) fetch_res(r, j);
+  while (true) {
+    const PixRef q = run_pixel(p, r, lq, lane, oy0, ox0);
+    const bool valid = q.valid;
+    const size_t pix = q.pix;
+    const int co0 = nbk * NB + j;
+    int r2 = r, j2 = j + 16;
+    if (NB16 || j2 >= NB) {
+      j2 = 0;
+      r2 = r + 2;
+    }
+    const bool more = r2 < p.t.R;
+    uint4 rv[2];
+    if (kRes) {
+      rv[0] = rv_next[0];
+      rv[1] = rv_next[1];
+      if (has_res && more) fetch_res(r2, j2);
+    }
+    tmem_ld_wait();
+    for (int a = 1; a < p.t.kacc; ++a) {  // K-split accumulator sets: add the partial sums
+      uint32_t part[16];
+      tmem_ld16(tm_lane + (uint32_t)((a * p.t.R + r) * NB + j), part);
       tmem_ld_wait();
-      float f[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(acc[i]), s_scale[j + i], s_shift[j + i]);
-      const int co0 = nbk * NB + j;
-      if (p.res && valid) {
+      for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
+    }
+    float f[16];
+    if constexpr (NB16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(acc[i]), sc[i], sh[i]);
+    } else {
+      const uint32_t sa = s_scale_addr + (uint32_t)co0 * 4, sb = sa + (uint32_t)cpad * 4;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 a = lds_f4(sa + i * 4), c = lds_f4(sb + i * 4);
+        f[i + 0] = fmaf(__uint_as_float(acc[i + 0]), a.x, c.x);
+        f[i + 1] = fmaf(__uint_as_float(acc[i + 1]), a.y, c.y);
+        f[i + 2] = fmaf(__uint_as_float(acc[i + 2]), a.z, c.z);
+        f[i + 3] = fmaf(__uint_as_float(acc[i + 3]), a.w, c.w);
+      }
+    }
+    if (more) tmem_ld16(tm_lane + (uint32_t)(r2 * NB + j2), acc);  // in flight during the rest of this step
+    if (kRes && has_res && valid) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = (co0 >> 3) + h;
+        if (ch < cc_out) {
+          float rf[8];
+          unpack8<BF16>(rv[h], rf);
+          if (p.res_aff) {
+            const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float2 a = __ldg(ra + i);
+              rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[h * 8 + i] += rf[i];
+        }
+      }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+    }
+    if (kStats && has_stats) {
+      if (NB16) {
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            d1[i] += f[i];
+            d2[i] = fmaf(f[i], f[i], d2[i]);
+          }
+        }
+      } else {
+        float s1[16], s2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float m = valid ? f[i] : 0.0f;
+          s1[i] = m;
+          s2[i] = m * m;
+        }
+        const float t1 = reduce_scatter16(s1, lane);
+        const float t2 = reduce_scatter16(s2, lane);
+        if ((lane & 1) == 0) {
+          const int c = co0 + stat_channel(lane);
+          my_stats[c * 2 + 0] += t1;
+          my_stats[c * 2 + 1] += t2;
+        }
+      }
+    }
+    if (valid) {
+      if (has_c8) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int ch = (co0 >> 3) + h;
           if (ch < cc_out) {
-            uint4 rv = ldg_nc16(p.res + (size_t)b * p.res_bs + ((size_t)ch * p.Hout * p.Wout + pix) * 16);
-            float rf[8];
-            unpack8<BF16>(rv, rf);
-            if (p.res_aff) {
-              const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
+            float g[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float2 a = __ldg(ra + i);
-                rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[h * 8 + i] += rf[i];
+            for (int i = 0; i < 8; ++i) g[i] = f[h * 8 + i];
+            uint4 ov = pack8<BF16>(g);
+            *reinterpret_cast<uint4*>(y_b + ((size_t)ch * HWo + pix) * 16) = ov;
           }
         }
       }
-      if (p.act == 1) {
+      if (kNchw && has_nchw) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
-      }
-      if (p.stats) {
-        if (defer) {
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              d1[i] += f[i];
-              d2[i] = fmaf(f[i], f[i], d2[i]);
-            }
-          }
-        } else {
-          float s1[16], s2[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float m = valid ? f[i] : 0.0f;
-            s1[i] = m;
-            s2[i] = m * m;
-          }
-          const float t1 = reduce_scatter16(s1, lane);
-          const float t2 = reduce_scatter16(s2, lane);
-          if ((lane & 1) == 0) {
-            const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            my_stats[(j + c) * 2 + 0] += t1;
-            my_stats[(j + c) * 2 + 1] += t2;
-          }
-        }
-      }
-      if (valid) {
-        if (p.y) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ch = (co0 >> 3) + h;
-            if (ch < cc_out) {
-              float g[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) g[i] = f[h * 8 + i];
-              uint4 ov = pack8<BF16>(g);
-              *reinterpret_cast<uint4*>(p.y + (size_t)b * p.y_bs + ((size_t)ch * p.Hout * p.Wout + pix) * 16) = ov;
-            }
-          }
-        }
-        if (p.y_nchw) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int co = co0 + i;
-            if (co < p.Cout) p.y_nchw[((size_t)b * p.Cout + co) * p.Hout * p.Wout + pix] = f[i];
-          }
+        for (int i = 0; i < 16; ++i) {
+          const int co = co0 + i;
+          if (co < p.Cout) p.y_nchw[((size_t)b * p.Cout + co) * HWo + pix] = f[i];
         }
       }
     }
-  }
-  if (defer) {
-    const float t1 = reduce_scatter16(d1, lane);
-    const float t2 = reduce_scatter16(d2, lane);
-    if ((lane & 1) == 0) {
-      const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-      my_stats[c * 2 + 0] += t1;
-      my_stats[c * 2 + 1] += t2;
-    }
+    if (!more) break;
+    r = r2;
+    j = j2;
   }
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+// Writes this warp's GroupNorm partial record of one sample ([cpad][2] floats) and clears the accumulators.
+__device__ __forceinline__ void flush_stats(const ConvParams& p, float* my_stats, float (&d1)[16], float (&d2)[16], float* record,
+                                            int lane) {
+  if (p.t.NB == 16) {
+    const float t1 = reduce_scatter16(d1, lane);
+    const float t2 = reduce_scatter16(d2, lane);
+    if ((lane & 1) == 0) *reinterpret_cast<float2*>(record + stat_channel(lane) * 2) = make_float2(t1, t2);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d1[i] = d2[i] = 0.0f;
+  } else {
+    const int n = p.t.NB * p.t.nblk * 2;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      record[i] = my_stats[i];
+      my_stats[i] = 0.0f;
+    }
+    __syncwarp();
+  }
+}
+
+struct ItemCoord {
+  int b, oy0, ox0, nbk, tile_lin;
+};
+__device__ __forceinline__ ItemCoord decode_item(const ConvParams& p, int w) {
+  ItemCoord c;
+  uint32_t tile = fdiv((uint32_t)w, p.div_nblk);
+  c.nbk = w - (int)tile * p.t.nblk;
+  c.tile_lin = (int)tile;
+  uint32_t t2 = fdiv(tile, p.div_tx);
+  const int tx = (int)(tile - t2 * (uint32_t)p.t.tiles_x);
+  const uint32_t bb = fdiv(t2, p.div_ty);
+  const int ty = (int)(t2 - bb * (uint32_t)p.t.tiles_y);
+  c.b = (int)bb;
+  c.oy0 = ty * p.t.TH;
+  c.ox0 = tx * p.t.TW;
+  return c;
+}
+
+template <bool BF16, int MODE, bool NB16>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem);  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
-  float* s_scale = reinterpret_cast<float*>(smem + p.t.off_scale);
-  float* s_shift = s_scale + p.t.NB;
-  float* s_stats = reinterpret_cast<float*>(smem + p.t.off_stats);  // [8 warps][NB][2]
-  uint8_t* a_buf = smem + p.t.off_a;
-  uint8_t* b_buf = smem + p.t.off_b;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages] producers -> MMA
+  uint64_t* bar_empty = bar_full + kMaxStages;                        // [kMaxStages] MMA (commit) -> producers
+  uint64_t* bar_tfull = bar_empty + kMaxStages;                       // [2] MMA (commit) -> epilogue
+  uint64_t* bar_tempty = bar_tfull + 2;                               // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + p.t.off_scale);    // [NB*nblk]
+  float* s_shift = s_scale + p.t.NB * p.t.nblk;
+  float* s_stats = reinterpret_cast<float*>(smem + p.t.off_stats);    // [kEpiWarps][cpad][2] (cpad <= 256)
+  uint8_t* b_res = smem + p.t.off_bres;
+  uint8_t* stage0 = smem + p.t.off_stage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NB = p.t.NB;
-  const int nbk = blockIdx.y;
-  int tile = blockIdx.x;
-  const int tx = tile % p.t.tiles_x;
-  tile /= p.t.tiles_x;
-  const int ty = tile % p.t.tiles_y;
-  const int b = tile / p.t.tiles_y;
-  const int oy0 = ty * p.t.TH, ox0 = tx * p.t.TW;
   const int taps = p.kh * p.kw;
+  const int total_items = p.B * p.t.tiles_x * p.t.tiles_y * p.t.nblk;
+  const int ksteps_per_stage = p.t.CBc / 2;
 
-  // ---- one-time setup
+  // ---- one-time setup (independent of the previous kernel's output)
   if (tid == 0) {
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
+    for (int i = 0; i < p.t.nstages; ++i) {
+      mbar_init(&bar_full[i], kProdWarps);
+      mbar_init(&bar_empty[i], kMmaWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tfull[i], kMmaWarps);
+      mbar_init(&bar_tempty[i], kEpiWarps);
+    }
     fence_mbar_init();
   }
-  for (int i = tid; i < NB; i += kConvThreads) {
-    s_scale[i] = p.scale ? __ldg(p.scale + nbk * NB + i) : 1.0f;
-    s_shift[i] = p.shift ? __ldg(p.shift + nbk * NB + i) : 0.0f;
+  {
+    const int cpad = NB * p.t.nblk;
+    for (int i = tid; i < cpad; i += kConvThreads) {
+      s_scale[i] = p.scale ? __ldg(p.scale + i) : 1.0f;
+      s_shift[i] = p.shift ? __ldg(p.shift + i) : 0.0f;
+    }
+    if (p.stats)
+      for (int i = tid; i < kEpiWarps * cpad * 2; i += kConvThreads) s_stats[i] = 0.0f;
   }
-  if (p.stats)
-    for (int i = tid; i < 8 * NB * 2; i += kConvThreads) s_stats[i] = 0.0f;
-  __syncthreads();
-  uint32_t tmem_base = 0;
-
-  // ---- K loop over channel stages
-  const int iy_base = oy0 * p.stride - p.pad, ix_base = ox0 * p.stride - p.pad;
-  const int ksteps_per_stage = p.t.CBc / 2;
-  for (int ks = 0; ks < p.t.kstages; ++ks) {
-    const int buf = ks % p.t.nbuf;
-    uint8_t* abuf = a_buf + (size_t)buf * p.t.a_stage_bytes;
-    uint8_t* bbuf = b_buf + (size_t)buf * p.t.b_stage_bytes;
-    if (ks >= p.t.nbuf) {  // the MMAs that read this buffer must have drained
-      mbar_wait(&mma_done[buf], (uint32_t)((ks / p.t.nbuf) - 1) & 1u);
-    }
-    const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
-    // weights: contiguous blob of this (n-block, stage)
-    {
-      const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * taps * (size_t)(2 * NB * 16);
-      const int n16 = nks * taps * 2 * NB;
-      for (int i = tid; i < n16; i += kConvThreads) cp_async16(bbuf + (size_t)i * 16, wsrc + (size_t)i * 16);
-      cp_async_commit();
-    }
-    // activations: 2*nks planes
-    stage_a<BF16, kConvThreads>(p, abuf, b, ks * p.t.CBc, 2 * nks, iy_base, ix_base, tid);
-    if (ks == 0) {
-      // TMEM is claimed only now, after the first tile has been staged: a CTA that has to wait for
-      // columns held by a co-resident CTA overlaps that wait with its own global loads.
-      if (warp == 0) {
-        tmem_alloc(tmem_slot, p.t.tmem_cols);
-        tmem_relinquish();
-      }
-      tc_fence_before();
-    }
+  if (p.t.b_resident) {
+    const int n16 = p.t.ksteps * taps * 2 * NB;
+    for (int i = tid; i < n16; i += kConvThreads) cp_async16(b_res + (size_t)i * 16, p.w + (size_t)i * 16);
+    cp_async_commit();
     cp_async_wait_all();
     fence_async_smem();
-    __syncthreads();
-    if (ks == 0) {
-      tc_fence_after();
-      tmem_base = *tmem_slot;
-    }
-    if (tid == 0) {
-      tc_fence_after();
-      // Descriptors differ only in their 14-bit start-address field (16-byte units), so the whole
-      // issue loop is integer adds on the low word: no divisions, ~10 instructions per MMA.
-      const uint64_t da0 = make_smem_desc(smem_u32(abuf), p.t.plane_bytes, 128);
-      const uint64_t db0 = make_smem_desc(smem_u32(bbuf), (uint32_t)(NB * 16), 128);
-      const uint32_t da_hi = (uint32_t)(da0 >> 32), db_hi = (uint32_t)(db0 >> 32);
-      const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
-      const uint32_t a_kstep = (2u * p.t.plane_bytes) >> 4;  // two 8-channel planes per K step
-      const uint32_t b_tap = (uint32_t)(2 * NB);             // (2*NB*16) >> 4
-      const uint32_t b_kstep = (uint32_t)taps * b_tap;
-      const bool s2 = p.stride == 2;
-      const uint32_t P = (uint32_t)p.t.P, sub = (uint32_t)p.t.slots_sub;
-      const uint32_t idesc = p.idesc;
-      // Loop order: taps outermost, the tile's R independent 128-pixel runs innermost, so that
-      // back-to-back MMAs never accumulate into the same TMEM columns (a dependent accumulate
-      // chain serialises on the tensor pipe's latency, which dwarfs an N=16 MMA's 8 busy cycles).
-      uint32_t b_t = db_lo0;
-      const uint32_t first = (ks == 0) ? 0u : 1u;
-      for (int ky = 0; ky < p.kh; ++ky) {
-        const uint32_t a_row = da_lo0 + (s2 ? (uint32_t)(ky & 1) * 2u * sub + (uint32_t)(ky >> 1) * P : (uint32_t)ky * P);
-        for (int kx = 0; kx < p.kw; ++kx) {
-          const uint32_t a_tap = a_row + (s2 ? (uint32_t)(kx & 1) * sub + (uint32_t)(kx >> 1) : (uint32_t)kx);
-          const uint32_t acc_tap = (ky | kx) ? 1u : first;
-          uint32_t b_lo = b_t;
-          uint32_t a_sk = a_tap;
-          for (int sk = 0; sk < nks; ++sk) {
-            const uint32_t acc = sk ? 1u : acc_tap;
-            uint32_t a_lo = a_sk;
-            uint32_t d_tmem = tmem_base;
-            for (int r = 0; r < p.t.R; ++r) {
-              umma_f16_ss(d_tmem, ((uint64_t)da_hi << 32) | a_lo, ((uint64_t)db_hi << 32) | b_lo, idesc, acc);
-              a_lo += 128u;
-              d_tmem += (uint32_t)NB;
-            }
-            a_sk += a_kstep;
-            b_lo += b_kstep;
-          }
-          b_t += b_tap;
-        }
-      }
-      umma_commit(&mma_done[buf]);
-    }
   }
-  {
-    const int last = p.t.kstages - 1;
-    mbar_wait(&mma_done[last % p.t.nbuf], (uint32_t)(last / p.t.nbuf) & 1u);
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, p.t.tmem_cols);
+    tmem_relinquish();
   }
-  tc_fence_after();
-
-  // ---- epilogue
-  epilogue_tile<BF16>(p, tmem_base, s_scale, s_shift, s_stats + (size_t)warp * NB * 2, b, oy0, ox0, nbk, warp & 3, warp >> 2, lane);
-
-  // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (p.stats) {
-    const int tile_lin = blockIdx.x;  // = (b*tiles_y + ty)*tiles_x + tx
-    float* out = p.stats + ((size_t)tile_lin * (NB * p.t.nblk) + (size_t)nbk * NB) * 2;
-    for (int i = tid; i < NB * 2; i += kConvThreads) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) acc += s_stats[(size_t)w * NB * 2 + i];
-      out[i] = acc;
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long t_setup = clock64();
+
+  if (warp >= kProdWarp0) {
+    // =========================================================== producers
+    // Software pipeline: the raw copies of stage i+D are in flight (cp.async) while stage i is
+    // transformed in place and handed to the MMA warp; D = nstages-1 stages of loads hide HBM latency.
+    const int ptid = tid - kProdWarp0 * 32;
+    const int D = p.t.nstages - 1;
+    int wi = blockIdx.x, ksi = 0, slot_i = 0;  // issue cursor
+    uint32_t phase_i = 0;
+    int wt = blockIdx.x, kst = 0, slot_t = 0;  // transform / hand-off cursor
+    auto issue_next = [&]() {
+      if (wi < total_items) {
+        const ItemCoord c = decode_item(p, wi);
+        mbar_wait(&bar_empty[slot_i], phase_i ^ 1u);  // the MMAs that read this slot have drained
+        if (!(p.debug & 1))
+          issue_stage<kProdThreads>(p, stage0 + (size_t)slot_i * p.t.stage_bytes, c.b, c.nbk, ksi,
+                                    c.oy0 * p.stride - p.pad, c.ox0 * p.stride - p.pad, ptid);
+        if (++ksi == p.t.kstages) {
+          ksi = 0;
+          wi += gridDim.x;
+        }
+        if (++slot_i == p.t.nstages) {
+          slot_i = 0;
+          phase_i ^= 1u;
+        }
+      }
+      cp_async_commit();  // one group per pipeline step, empty or not: keeps wait_group(D) exact
+    };
+    // Order matters: stage i is handed to the MMA warp BEFORE the copies of stage i+D are issued, because
+    // that issue has to wait for the MMAs of stage i-1 to release their slot (D = nstages-1).
+    for (int j = 0; j < D; ++j) issue_next();
+    while (wt < total_items) {
+      if (D == 0) issue_next();
+      cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // this thread's copies of the hand-off stage have landed
+      const ItemCoord c = decode_item(p, wt);
+      if (!(p.debug & 1))
+        transform_stage<BF16, kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, c.b, kst, c.oy0 * p.stride - p.pad,
+                                            c.ox0 * p.stride - p.pad, ptid);
+      fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[slot_t]);
+      if (++kst == p.t.kstages) {
+        kst = 0;
+        wt += gridDim.x;
+      }
+      if (++slot_t == p.t.nstages) slot_t = 0;
+      if (D > 0) issue_next();
     }
+    cp_async_wait_group<0>();
+  } else if (warp >= kMmaWarp0) {
+    // =========================================================== MMA issue (warp i: runs r = i, i+kMmaWarps, ...)
+    const int mw = warp - kMmaWarp0;
+    int stage = 0;
+    uint32_t phase = 0;
+    int item = 0;
+    const bool s2 = p.stride == 2;
+    const uint32_t P = (uint32_t)p.t.P, sub = (uint32_t)p.t.slots_sub;
+    const uint32_t idesc = p.idesc;
+    const uint32_t a_kstep = (2u * p.t.plane_bytes) >> 4;  // two 8-channel planes per K step
+    const uint32_t b_tap = (uint32_t)(2 * NB);             // (2*NB*16) >> 4
+    const uint32_t b_kstep = (uint32_t)taps * b_tap;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+      const int acc_i = p.t.nacc == 2 ? (item & 1) : 0;
+      const uint32_t use = p.t.nacc == 2 ? (uint32_t)(item >> 1) : (uint32_t)item;
+      mbar_wait(&bar_tempty[acc_i], (use & 1u) ^ 1u);  // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)acc_i * p.t.acc_cols;
+      int ecount = 0, aset = 0;
+      for (int ks = 0; ks < p.t.kstages; ++ks) {
+        mbar_wait(&bar_full[stage], phase);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const int kh_eff = (p.debug & 4) ? 0 : p.kh;
+          const uint8_t* abuf = stage0 + (size_t)stage * p.t.stage_bytes;
+          const uint8_t* bbuf = p.t.b_resident ? b_res : abuf + p.t.a_stage_bytes;
+          const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
+          // Descriptors differ only in their 14-bit start-address field (16-byte units), so the whole
+          // issue loop is integer adds on the low word: no divisions, ~10 instructions per MMA.
+          const uint64_t da0 = make_smem_desc(smem_u32(abuf), p.t.plane_bytes, 128);
+          const uint64_t db0 = make_smem_desc(smem_u32(bbuf), (uint32_t)(NB * 16), 128);
+          const uint32_t da_hi = (uint32_t)(da0 >> 32), db_hi = (uint32_t)(db0 >> 32);
+          const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
+          // Loop order: taps outermost, the tile's R independent 128-pixel runs innermost, so that
+          // back-to-back MMAs never accumulate into the same TMEM columns (a dependent accumulate
+          // chain serialises on the tensor pipe's latency, which dwarfs an N=16 MMA's busy cycles).
+          uint32_t b_t = db_lo0;
+          for (int ky = 0; ky < kh_eff; ++ky) {
+            const uint32_t a_row = da_lo0 + (s2 ? (uint32_t)(ky & 1) * 2u * sub + (uint32_t)(ky >> 1) * P : (uint32_t)ky * P);
+            for (int kx = 0; kx < p.kw; ++kx) {
+              const uint32_t a_tap = a_row + (s2 ? (uint32_t)(kx & 1) * sub + (uint32_t)(kx >> 1) : (uint32_t)kx);
+              uint32_t b_lo = b_t;
+              uint32_t a_sk = a_tap;
+              for (int sk = 0; sk < nks; ++sk) {
+                // entry e = (K stage, tap, K step) of this item goes to accumulator set e % kacc; this warp issues the
+                // (set, run) pairs q = set*R + r with q % kMmaWarps == mw
+                const uint32_t acc = ecount >= p.t.kacc ? 1u : 0u;
+                const int q0 = aset * p.t.R;
+                const int r0 = (mw - q0) & (kMmaWarps - 1);
+                uint32_t a_lo = a_sk + 128u * (uint32_t)r0;
+                uint32_t d_tmem = tmem_acc + (uint32_t)((q0 + r0) * NB);
+                for (int r = r0; r < p.t.R; r += kMmaWarps) {
+                  umma_f16_ss(d_tmem, ((uint64_t)da_hi << 32) | a_lo, ((uint64_t)db_hi << 32) | b_lo, idesc, acc);
+                  a_lo += 128u * kMmaWarps;
+                  d_tmem += (uint32_t)(NB * kMmaWarps);
+                }
+                ++ecount;
+                if (++aset == p.t.kacc) aset = 0;
+                a_sk += a_kstep;
+                b_lo += b_kstep;
+              }
+              b_t += b_tap;
+            }
+          }
+          umma_commit(&bar_empty[stage]);                              // smem slot free once these MMAs retire
+          if (ks == p.t.kstages - 1) umma_commit(&bar_tfull[acc_i]);   // accumulators complete
+        }
+        __syncwarp();
+        if (++stage == p.t.nstages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // =========================================================== epilogue
+    constexpr bool kStats = MODE == EPI_STATS || MODE == EPI_GENERIC;
+    int item = 0;
+    const int lq = warp & 3, half = warp >> 2;
+    const int cpad = NB * p.t.nblk;
+    float* my_stats = s_stats + (size_t)warp * cpad * 2;
+    const bool has_stats = kStats && p.stats != nullptr;
+    float d1[16], d2[16], sc[16], sh[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      d1[i] = d2[i] = 0.0f;
+      sc[i] = NB16 ? s_scale[i] : 1.0f;
+      sh[i] = NB16 ? s_shift[i] : 0.0f;
+    }
+    // stats layout: [B][grid * kEpiWarps][cpad][2]; this warp owns record (blockIdx.x * kEpiWarps + warp) of every sample
+    const size_t rec_stride = (size_t)cpad * 2;
+    const size_t img_stride = (size_t)gridDim.x * kEpiWarps * rec_stride;
+    float* my_rec = has_stats ? p.stats + ((size_t)blockIdx.x * kEpiWarps + warp) * rec_stride : nullptr;
+    if (has_stats) {
+      for (int bb = 0; bb < p.B; ++bb)
+        for (int i = lane; i < cpad * 2; i += 32) my_rec[(size_t)bb * img_stride + i] = 0.0f;
+      __syncwarp();
+    }
+    int cur_b = -1;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+      const ItemCoord c = decode_item(p, w);
+      if (has_stats && c.b != cur_b) {
+        if (cur_b >= 0) flush_stats(p, my_stats, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
+        cur_b = c.b;
+      }
+      const int acc_i = p.t.nacc == 2 ? (item & 1) : 0;
+      const uint32_t use = p.t.nacc == 2 ? (uint32_t)(item >> 1) : (uint32_t)item;
+      mbar_wait(&bar_tfull[acc_i], use & 1u);
+      tc_fence_after();
+      if (!(p.debug & 2))
+        epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
+                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc_i]);
+    }
+    if (has_stats && cur_b >= 0) flush_stats(p, my_stats, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
   }
+
+  // ---- teardown
+  if ((p.debug & 8) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kMmaWarp0 || warp == kProdWarp0))
+    printf("mfc conv timing: warp %d role loop %lld cycles (items/cta %d)\n", warp, clock64() - t_setup,
+           (total_items + (int)gridDim.x - 1) / (int)gridDim.x);
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.t.tmem_cols);
@@ -470,13 +724,22 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
   const int hy = (d.kh - 1) / s, hx = (d.kw - 1) / s;
   const int taps = d.kh * d.kw;
   int cin_chunks = 0;
-  for (int i = 0; i < d.nsrc; ++i) cin_chunks += d.src[i].nchunks;
+  bool any_aff = false;
+  for (int i = 0; i < d.nsrc; ++i) {
+    cin_chunks += d.src[i].nchunks;
+    any_aff = any_aff || d.src[i].affine != nullptr;
+  }
   const int ksteps = ceil_div(cin_chunks, 2);
   int nblk;
   const int NB = conv_nb(d.Cout, &nblk);
+  const uint32_t cpad = (uint32_t)(NB * nblk);
+  const uint32_t off_scale = 256;
+  const uint32_t off_stats = off_scale + cpad * 8;
+  const uint32_t off_bres = (off_stats + (cpad <= 256 ? (uint32_t)kEpiWarps * cpad * 8 : 0u) + 127) & ~127u;
+  const uint64_t w_bytes_nblk = (uint64_t)ksteps * taps * 2 * NB * 16;  // one N-block's packed weights
   double best_cost = 1e300;
   bool found = false;
-  for (int nx = 1; nx <= 32; ++nx) {
+  for (int nx = 1; nx <= 40; ++nx) {
     const int TW = ceil_div(d.Wout, nx);
     if (nx > 1 && TW < 8) break;
     if (nx > 1 && ceil_div(d.Wout, nx - 1) == TW) continue;
@@ -484,52 +747,67 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
     for (int TH = 1; TH <= d.Hout && TH <= 64; ++TH) {
       const int R = ceil_div((TH - 1) * P + TW, 128);
       if ((uint32_t)(R * NB) > 512) break;
-      const uint32_t tmem = pow2_at_least((uint32_t)(R * NB), 32);
+      // a dependent accumulate costs ~167 cycles, an independent N<=32 MMA ~39: every issuing warp wants
+      // >= 4 accumulators to rotate over.  Tiles with few runs split K over kacc accumulator sets.
+      int kacc = 1;
+      while (kacc < 4 && ceil_div(R * kacc, kMmaWarps) < 4 && R * NB * kacc * 2 <= 512 && kacc * 2 <= taps * ksteps) kacc *= 2;
+      const int nacc = (2 * R * NB * kacc <= 512) ? 2 : 1;
+      const uint32_t tmem = pow2_at_least((uint32_t)(nacc * R * NB * kacc), 32);
       const int rows_sub = TH + hy;
       const int slots_sub = std::max(R * 128 + hy * P + hx, rows_sub * P);
       const uint32_t plane_bytes = (uint32_t)(s * s) * slots_sub * 16;
       if (plane_bytes > 200000u) break;
       const int tiles_x = nx, tiles_y = ceil_div(d.Hout, TH);
-      // K staging options: everything resident (1 buffer), or 16/32/64-channel stages double-buffered
-      // (single-buffered stages are the fallback when two stages of 11x11 weights do not fit)
-      const int opts[7] = {2 * ksteps, 8, 4, 2, 8, 4, 2};
-      for (int oi = 0; oi < 7; ++oi) {
+      const long long items = (long long)d.B * tiles_x * tiles_y * nblk;
+      // K staging options: all channels in one stage, or 16/32/64/128-channel stages
+      const int opts[5] = {2 * ksteps, 16, 8, 4, 2};
+      for (int oi = 0; oi < 5; ++oi) {
         const int CBc = opts[oi];
         if (oi > 0 && CBc >= 2 * ksteps) continue;
         const int kstages = ceil_div(2 * ksteps, CBc);
-        const int nbuf = (kstages > 1 && oi < 4) ? 2 : 1;
+        const bool resident = kstages == 1 && nblk == 1;
         const uint32_t a_stage = (uint32_t)CBc * plane_bytes;
-        const uint32_t b_stage = (uint32_t)(CBc / 2) * taps * 2 * NB * 16;
-        const uint32_t off_scale = 128;
-        const uint32_t off_stats = off_scale + (uint32_t)NB * 8;
-        const uint32_t off_a = (off_stats + (uint32_t)NB * 64 + 127) & ~127u;
-        const uint64_t off_b64 = (uint64_t)off_a + (uint64_t)nbuf * a_stage;
-        const uint64_t smem64 = off_b64 + (uint64_t)nbuf * b_stage + 128;
-        if (smem64 > (uint64_t)kSmemPerCtaMax) continue;
-        const uint32_t smem = (uint32_t)smem64;
-        int ctas = std::min(std::min((int)(kSmemPerSm / (smem + 1024)), (int)(512 / tmem)), 2048 / kConvThreads);
-        if (ctas < 1) continue;
-        // ---- cost model (SM cycles per tile, then waves)
-        const double load_items = (double)std::min(2 * ksteps, cin_chunks + 1) * s * s * rows_sub * P;
-        const double L = load_items * 0.55 + (double)kstages * (b_stage / 16) * 0.12;  // staging
-        const double per_mma = std::max(NB / 2.0, 34.0 + NB / 4.0);
-        const double M = (double)R * taps * ksteps * per_mma;                            // tensor pipe
-        const double E = (double)R * (NB / 16) * 60.0;                                    // epilogue
-        const long long total_tiles = (long long)d.B * tiles_x * tiles_y * nblk;
-        const double tiles_per_sm = std::ceil((double)total_tiles / kSmCount);
-        double per_tile = (ctas >= 2 || (kstages > 1 && nbuf > 1)) ? std::max(L + E, M) + 0.15 * std::min(L + E, M) : (L + M + E);
-        const double fixed = 2500.0;
-        double cost = tiles_per_sm * per_tile + fixed * std::ceil(tiles_per_sm / ctas);
+        const uint64_t b_stage = (uint64_t)(CBc / 2) * taps * 2 * NB * 16;
+        const uint64_t stage_bytes = ((uint64_t)a_stage + (resident ? 0 : b_stage) + 127) & ~(uint64_t)127;
+        const uint64_t off_stage = ((uint64_t)off_bres + (resident ? w_bytes_nblk : 0) + 127) & ~(uint64_t)127;
+        if (off_stage + stage_bytes + 128 > (uint64_t)kSmemPerCtaMax) continue;
+        int nstages = (int)(((uint64_t)kSmemPerCtaMax - 128 - off_stage) / stage_bytes);
+        nstages = std::min(nstages, kstages > 1 ? 6 : 4);
+        nstages = std::min(nstages, kMaxStages);
+        if (nstages < 1) continue;
+        const uint32_t smem = (uint32_t)(off_stage + (uint64_t)nstages * stage_bytes + 128);
+        // ---- cost model (SM cycles per work item; the three roles overlap when there are >= 2 stages)
+        const double load_items = (double)cin_chunks * s * s * rows_sub * P;
+        // producers: cp.async issue (~0.3 cyc per 16-byte item) or the HBM share of one SM (~0.7), plus the
+        // in-place affine+SiLU pass; streamed weights come from L2
+        const double L = load_items * (any_aff ? 1.0 : 0.7) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.3) + 60.0 * kstages;
+        const double indep = std::max(1, (R * kacc) / kMmaWarps);  // accumulators each issuing warp rotates over
+        const double per_mma = std::max(std::max(NB / 2.0, 32.0 + NB / 4.0) + 3.0, 167.0 / indep / kMmaWarps);
+        const double M = (double)R * taps * ksteps * per_mma;
+        const double e_run = 120.0 + (d.nsrc > 0 ? 0.0 : 0.0);
+        const double E = (double)((R + 1) / 2) * (NB / 16) * (e_run + 40.0 * (kacc - 1)) + 200.0;
+        const int G = (int)std::min<long long>(items, kSmCount);
+        const double rounds = std::ceil((double)items / G);
+        double per_item;
+        if (nstages >= 2) {
+          const double mx = std::max(L, std::max(M, nacc == 2 ? E : 0.0));
+          per_item = mx + 0.15 * (L + M + E - mx) + (nacc == 2 ? 0.0 : E) + 150.0;
+        } else {
+          per_item = L + std::max(M, E) + (nacc == 2 ? 0.0 : std::min(M, E)) + 300.0;
+        }
+        const double cost = rounds * per_item + (L + M + E) * 0.5 + (resident ? (double)(w_bytes_nblk / 16) * 0.05 : 0.0);
         if (cost < best_cost) {
           best_cost = cost;
           found = true;
           best.TH = TH; best.TW = TW; best.P = P; best.R = R; best.rows_sub = rows_sub; best.slots_sub = slots_sub;
-          best.CBc = CBc; best.kstages = kstages; best.nbuf = nbuf; best.tiles_x = tiles_x; best.tiles_y = tiles_y;
+          best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.b_resident = resident ? 1 : 0;
+          best.tiles_x = tiles_x; best.tiles_y = tiles_y;
           best.NB = NB; best.nblk = nblk; best.ksteps = ksteps; best.cin_chunks = cin_chunks;
-          best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = b_stage;
-          best.smem_bytes = smem; best.tmem_cols = tmem;
-          best.off_scale = off_scale; best.off_stats = off_stats; best.off_a = off_a; best.off_b = (uint32_t)off_b64;
-          best.ctas_per_sm = ctas;
+          best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;
+          best.stage_bytes = (uint32_t)stage_bytes;
+          best.smem_bytes = smem; best.tmem_cols = tmem; best.acc_cols = (uint32_t)(R * NB * kacc);
+          best.off_scale = off_scale; best.off_stats = off_stats; best.off_bres = off_bres; best.off_stage = (uint32_t)off_stage;
+          best.grid = G;
         }
       }
     }
@@ -537,19 +815,33 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
   return found;
 }
 
-template <bool BF16>
-static cudaError_t launch_conv_t(const ConvParams& p, cudaStream_t st) {
+template <bool BF16, int MODE, bool NB16>
+static cudaError_t launch_conv_inst(const ConvParams& p, cudaStream_t st) {
   static int configured_for = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_for != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerCtaMax);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BF16, MODE, NB16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerCtaMax);
     if (e != cudaSuccess) return e;
     configured_for = dev;
   }
-  dim3 grid((unsigned)(p.B * p.t.tiles_x * p.t.tiles_y), (unsigned)p.t.nblk);
-  conv_tc_kernel<BF16><<<grid, kConvThreads, p.t.smem_bytes, st>>>(p);
+  conv_tc_kernel<BF16, MODE, NB16><<<(unsigned)p.t.grid, kConvThreads, p.t.smem_bytes, st>>>(p);
   return cudaGetLastError();
+}
+
+template <bool BF16, int MODE>
+static cudaError_t launch_conv_mode(const ConvParams& p, cudaStream_t st) {
+  return p.t.NB == 16 ? launch_conv_inst<BF16, MODE, true>(p, st) : launch_conv_inst<BF16, MODE, false>(p, st);
+}
+
+template <bool BF16>
+static cudaError_t launch_conv_t(const ConvParams& p, cudaStream_t st) {
+  const bool res = p.res != nullptr, stats = p.stats != nullptr, nchw = p.y_nchw != nullptr;
+  if (!res && !stats && !nchw) return launch_conv_mode<BF16, EPI_PLAIN>(p, st);
+  if (stats && !res && !nchw) return launch_conv_mode<BF16, EPI_STATS>(p, st);
+  if (res && !stats && !nchw) return launch_conv_mode<BF16, EPI_RES>(p, st);
+  if (nchw && !res && !stats) return launch_conv_mode<BF16, EPI_NCHW>(p, st);
+  return launch_conv_mode<BF16, EPI_GENERIC>(p, st);
 }
 
 cudaError_t launch_conv(const ConvParams& p, bool bf16, cudaStream_t st) {

@@ -5,6 +5,17 @@
 
 namespace mfc {
 
+// warp roles of conv_tc_kernel (one persistent CTA per SM)
+constexpr int kEpiWarps = 8;                       // warps 0..7 : TMEM -> registers -> global (lane quarter = warp % 4)
+constexpr int kMmaWarp0 = kEpiWarps;               // warps 8..9  : tcgen05.mma issue (one elected lane each; warp i
+constexpr int kMmaWarps = 2;                       //               issues the runs r = i, i+2, ...: a single thread
+                                                   //               cannot issue N=16 MMAs at the tensor pipe's rate)
+constexpr int kProdWarp0 = kMmaWarp0 + kMmaWarps;  // warps 10..15: tile staging (global -> transform -> smem)
+constexpr int kProdWarps = 6;                      // 16 warps = 512 threads: 128 registers each
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kConvThreads = (kEpiWarps + kMmaWarps + kProdWarps) * 32;
+constexpr int kMaxStages = 8;
+
 struct ConvTiling {
   int TH, TW;        // output tile
   int P;             // smem row pitch in pixels = TW + (kw-1)/stride
@@ -12,8 +23,12 @@ struct ConvTiling {
   int rows_sub;      // rows loaded per parity sub-plane = TH + (kh-1)/stride
   int slots_sub;     // 16-byte pixel slots per parity sub-plane
   int CBc;           // 8-channel planes per K stage (even)
-  int kstages;
-  int nbuf;          // A/B stage buffers (1 or 2)
+  int kstages;       // K stages per work item
+  int nstages;       // depth of the shared-memory stage ring
+  int nacc;          // TMEM accumulator buffers (2 = the epilogue of item i overlaps the MMAs of item i+1)
+  int kacc;          // K-split accumulator sets per buffer (1, 2 or 4): consecutive taps rotate over them so that
+                     // back-to-back MMAs are independent even when the tile has a single run; the epilogue sums them
+  int b_resident;    // 1: the whole packed weight blob is loaded once per CTA; 0: streamed with each stage
   int tiles_x, tiles_y;
   int NB, nblk;
   int ksteps;        // total 16-channel K steps = ceil(cin_chunks/2)
@@ -21,10 +36,12 @@ struct ConvTiling {
   uint32_t plane_bytes;    // bytes of one 8-channel plane (all parity sub-planes)
   uint32_t a_stage_bytes;  // CBc * plane_bytes
   uint32_t b_stage_bytes;  // (CBc/2) * taps * 2*NB*16
+  uint32_t stage_bytes;    // a_stage_bytes (+ b_stage_bytes when streamed), 128-byte aligned
   uint32_t smem_bytes;
-  uint32_t tmem_cols;
-  uint32_t off_scale, off_stats, off_a, off_b;  // smem carve-up (bytes from the 128B-aligned base)
-  int ctas_per_sm;
+  uint32_t tmem_cols;      // allocated (power of two >= 32)
+  uint32_t acc_cols;       // kacc * R * NB, columns of one accumulator buffer
+  uint32_t off_scale, off_stats, off_bres, off_stage;  // smem carve-up (bytes from the 128B-aligned base)
+  int grid;                // persistent CTAs
 };
 
 struct ConvParams {
@@ -36,7 +53,7 @@ struct ConvParams {
   long long src_bs[MFC_MAX_SRC];
   int src_end[MFC_MAX_SRC];  // exclusive prefix end (in chunks) of each source
   ConvTiling t;
-  FastDiv divP;
+  FastDiv divP, div_nblk, div_tx, div_ty;
   uint32_t idesc;
   const uint8_t* w;
   const float* scale;
@@ -48,9 +65,10 @@ struct ConvParams {
   long long y_bs;
   float* y_nchw;
   float* stats;
+  int debug;  // measurement only (MFC_CONV_DEBUG): bit0 skip producer copies, bit1 skip epilogue body, bit2 skip MMAs
 };
 
-// host planner (conv_plan.cpp part of api.cu)
+// host planner
 int conv_nb(int cout, int* nblk);
 bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& out);
 

@@ -39,10 +39,6 @@ struct CorrParams {
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // stage `nch` channels starting at c0 into `buf`
 __device__ __forceinline__ void corr_stage(const CorrParams& p, float* buf, int b, int c0, int nch, int y0, int x0, int dy0) {

@@ -101,11 +101,12 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, int tiles, i
   const int c0 = g * cpg;
   double s = 0.0, q = 0.0;
   const int n = tiles * cpg;
+#pragma unroll 4
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int t = i / cpg, c = c0 + i % cpg;
-    const float* p = stats + (((size_t)b * tiles + t) * cpad + c) * 2;
-    s += p[0];
-    q += p[1];
+    const float2 v = __ldg(reinterpret_cast<const float2*>(stats + (((size_t)b * tiles + t) * cpad + c) * 2));
+    s += v.x;
+    q += v.y;
   }
   for (int o = 16; o; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -194,7 +195,7 @@ cudaError_t launch_bn_fold(const float* g, const float* b, const float* m, const
 }
 cudaError_t launch_gn_finalize(const float* stats, int B, int tiles, int cpad, int C, int groups, long long pixels, const float* gamma,
                                const float* beta, float eps, float* affine, cudaStream_t st) {
-  gn_finalize_kernel<<<B * groups, 256, 0, st>>>(stats, tiles, cpad, C, groups, pixels, gamma, beta, eps, affine);
+  gn_finalize_kernel<<<B * groups, 1024, 0, st>>>(stats, tiles, cpad, C, groups, pixels, gamma, beta, eps, affine);
   return cudaGetLastError();
 }
 cudaError_t launch_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks, long long pixels,

@@ -275,7 +275,7 @@ class Program:
             self.keep.append(out_nchw)
         stats = None
         if want_stats:
-            stats = arena.alloc((B, info.tiles_per_image, info.nb * info.nblk, 2), torch.float32)
+            stats = arena.alloc((B, info.stats_per_image, info.nb * info.nblk, 2), torch.float32)
             io.stats = stats.data_ptr()
             self.keep.append(stats)
         for s in srcs:
@@ -300,7 +300,7 @@ class Program:
     def gn_finalize(self, stats, info, gamma, beta, C_, groups, pixels, eps, affine):
         a = abi.MfcGnArgs()
         a.stats, a.gamma, a.beta, a.affine = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), affine.data_ptr()
-        a.pixels, a.B, a.tiles_per_image = pixels, stats.shape[0], info.tiles_per_image
+        a.pixels, a.B, a.stats_per_image = pixels, stats.shape[0], info.stats_per_image
         a.cpad, a.C, a.groups, a.eps = info.nb * info.nblk, C_, groups, eps
         self.keep += [stats, gamma, beta, affine]
         self._push(abi.OP_GN_FINALIZE, a, meta={"kind": "gn_finalize", "name": "", "flops": 0, "bytes": stats.numel() * 4})

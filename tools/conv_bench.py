@@ -1,0 +1,96 @@
+"""GPU micro-benchmark of single fused-conv layers through libmfcnet_b200.so (CUDA-event timing).
+Usage: python tools/conv_bench.py [case-index ...] [--iters N]   (no index = all cases)
+Prints one JSON line per case: device microseconds per launch, algorithmic GB/s and TFLOP/s."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mfcnet_tracker_b200 as M  # noqa: E402,F401
+from mfcnet_tracker_b200 import engine  # noqa: E402
+from mfcnet_tracker_b200.engine import Act  # noqa: E402
+
+CASES = [
+    dict(name="16->16 k3 plain", B=4, H=480, W=640, cins=[16], Cout=16, k=3),
+    dict(name="16->16 k3 stats", B=4, H=480, W=640, cins=[16], Cout=16, k=3, stats=True),
+    dict(name="16->16 k3 aff+stats", B=4, H=480, W=640, cins=[16], Cout=16, k=3, stats=True, aff=True),
+    dict(name="32->16 k3 stats", B=4, H=480, W=640, cins=[16, 16], Cout=16, k=3, stats=True),
+    dict(name="32->16 k1 res", B=4, H=480, W=640, cins=[16, 16], Cout=16, k=1, res=True),
+    dict(name="3->16 k7", B=4, H=480, W=640, cins=[3], Cout=16, k=7),
+    dict(name="128->128 k3 stats", B=4, H=60, W=80, cins=[128], Cout=128, k=3, stats=True),
+    dict(name="64->64 k3", B=4, H=120, W=160, cins=[64], Cout=64, k=3),
+    dict(name="32->16 k3 up2", B=4, H=240, W=320, cins=[32], Cout=16, k=3, ups=2),
+    dict(name="fusion 11x11", B=8, H=480, W=640, cins=[5, 5, 5, 7], Cout=15, k=11, act=1),
+    dict(name="16->5 k1 nchw", B=4, H=480, W=640, cins=[16], Cout=5, k=1, nchw=True),
+]
+
+
+def run(case, iters):
+    dev = torch.device("cuda")
+    dt = "fp16"
+    tdtype = engine._DTYPES[dt][0]
+    c = dict(case)
+    name = c.pop("name")
+    B, H, W, cins, Cout, k = c["B"], c["H"], c["W"], c["cins"], c["Cout"], c["k"]
+    ups, act = c.get("ups", 1), c.get("act", 0)
+    packer = engine.WeightPacker(dev, dt)
+    arena = engine.Arena(dev)
+    bld = engine.Builder(dev, dt, packer, arena)
+    acts = []
+    for ci in cins:
+        t = torch.randn(B, (ci + 7) // 8, H, W, 8, device=dev).to(tdtype)
+        a = Act(t, ci)
+        if c.get("aff"):
+            aff = torch.zeros(B, ((ci + 7) // 8) * 8, 2, device=dev)
+            aff[..., 0] = 1.0
+            a = a.with_affine(aff)
+        acts.append(a)
+    cin = sum(cins)
+    w = torch.randn(Cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
+    Ho, Wo = H * ups, W * ups
+    res = None
+    if c.get("res"):
+        res = Act(torch.randn(B, (Cout + 7) // 8, Ho, Wo, 8, device=dev).to(tdtype), Cout)
+        aff = torch.zeros(B, ((Cout + 7) // 8) * 8, 2, device=dev)
+        aff[..., 0] = 1.0
+        res = res.with_affine(aff)
+    out_nchw = torch.empty(B, Cout, Ho, Wo, device=dev) if c.get("nchw") else None
+    out, st, info, io = bld.conv("c", acts, w, k, bias=torch.zeros(Cout, device=dev), pad=k // 2, upsample=ups, act=act,
+                                 residual=res, want_stats=bool(c.get("stats")), out_nchw=out_nchw, out_c8=out_nchw is None)
+    prog = bld.prog
+    for _ in range(3):
+        prog.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        prog.run()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1000.0 / iters
+    m = prog.meta[0]
+    r = {"case": name, "us": round(us, 2), "gbs": round(m["bytes"] / us * 1e-3, 1), "tflops": round(m["flops"] / us * 1e-6, 2),
+         "tile": [info.tile_h, info.tile_w], "R": info.runs, "kst": info.kstages, "nst": info.nstages, "grid": info.grid,
+         "smem": info.smem_bytes}
+    print(json.dumps(r), flush=True)
+    return r
+
+
+def main():
+    args = sys.argv[1:]
+    iters = 20
+    if "--iters" in args:
+        i = args.index("--iters")
+        iters = int(args[i + 1])
+        del args[i:i + 2]
+    idx = [int(a) for a in args] or range(len(CASES))
+    out = [run(CASES[i], iters) for i in idx]
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/conv_bench.json", "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
