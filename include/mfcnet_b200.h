@@ -95,7 +95,7 @@ typedef struct MfcConvInfo {
   int ksteps;          /* ceil(cin_chunks/2): 16-channel MMA K-steps per tap          */
   int tile_h, tile_w;  /* output tile                                                 */
   int tiles_per_image; /* output tiles in one sample                                  */
-  int stats_per_image; /* GroupNorm partial records per sample (tiles x epilogue warps):
+  int stats_per_image; /* GroupNorm partial records per sample (one per persistent CTA):
                           the stats buffer is [B][stats_per_image][nb*nblk][2]         */
   int runs;            /* 128-row MMA runs per tile                                   */
   int kstages;         /* channel stages of the K loop                                */

@@ -168,7 +168,7 @@ int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info) {
   info->tile_h = t.TH;
   info->tile_w = t.TW;
   info->tiles_per_image = t.tiles_x * t.tiles_y;
-  info->stats_per_image = t.grid * mfc::kEpiWarps;
+  info->stats_per_image = t.grid;
   info->runs = t.R;
   info->kstages = t.kstages;
   info->nstages = t.nstages;

@@ -394,24 +394,34 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   }
 }
 
-// Writes this warp's GroupNorm partial record of one sample ([cpad][2] floats) and clears the accumulators.
-__device__ __forceinline__ void flush_stats(const ConvParams& p, float* my_stats, float (&d1)[16], float (&d2)[16], float* record,
-                                            int lane) {
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+// Writes this CTA's GroupNorm partial record of one sample ([cpad][2] floats) and clears the accumulators.
+// All 8 epilogue warps call it together (they walk the same items, so they see the same sample change):
+// every warp parks its partial sums in its smem slot, then the 8 slots are added in a FIXED order, which
+// keeps the statistics bit-reproducible from run to run.
+__device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_stats, int warp, float (&d1)[16], float (&d2)[16],
+                                            float* record, int lane) {
+  const int n = p.t.NB * p.t.nblk * 2;
+  float* mine = s_stats + (size_t)warp * n;
   if (p.t.NB == 16) {
     const float t1 = reduce_scatter16(d1, lane);
     const float t2 = reduce_scatter16(d2, lane);
-    if ((lane & 1) == 0) *reinterpret_cast<float2*>(record + stat_channel(lane) * 2) = make_float2(t1, t2);
+    if ((lane & 1) == 0) *reinterpret_cast<float2*>(mine + stat_channel(lane) * 2) = make_float2(t1, t2);
 #pragma unroll
     for (int i = 0; i < 16; ++i) d1[i] = d2[i] = 0.0f;
-  } else {
-    const int n = p.t.NB * p.t.nblk * 2;
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      record[i] = my_stats[i];
-      my_stats[i] = 0.0f;
-    }
-    __syncwarp();
   }
+  epi_barrier();
+  for (int i = warp * 32 + lane; i < n; i += kEpiWarps * 32) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kEpiWarps; ++w) {
+      acc += s_stats[(size_t)w * n + i];
+      s_stats[(size_t)w * n + i] = 0.0f;
+    }
+    record[i] = acc;
+  }
+  epi_barrier();
 }
 
 struct ItemCoord {
@@ -628,20 +638,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       sc[i] = NB16 ? s_scale[i] : 1.0f;
       sh[i] = NB16 ? s_shift[i] : 0.0f;
     }
-    // stats layout: [B][grid * kEpiWarps][cpad][2]; this warp owns record (blockIdx.x * kEpiWarps + warp) of every sample
+    // stats layout: [B][grid][cpad][2]; this CTA owns record blockIdx.x of every sample
     const size_t rec_stride = (size_t)cpad * 2;
-    const size_t img_stride = (size_t)gridDim.x * kEpiWarps * rec_stride;
-    float* my_rec = has_stats ? p.stats + ((size_t)blockIdx.x * kEpiWarps + warp) * rec_stride : nullptr;
+    const size_t img_stride = (size_t)gridDim.x * rec_stride;
+    float* my_rec = has_stats ? p.stats + (size_t)blockIdx.x * rec_stride : nullptr;
     if (has_stats) {
       for (int bb = 0; bb < p.B; ++bb)
-        for (int i = lane; i < cpad * 2; i += 32) my_rec[(size_t)bb * img_stride + i] = 0.0f;
-      __syncwarp();
+        for (int i = warp * 32 + lane; i < cpad * 2; i += kEpiWarps * 32) my_rec[(size_t)bb * img_stride + i] = 0.0f;
     }
     int cur_b = -1;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
       const ItemCoord c = decode_item(p, w);
       if (has_stats && c.b != cur_b) {
-        if (cur_b >= 0) flush_stats(p, my_stats, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
+        if (cur_b >= 0) flush_stats(p, s_stats, warp, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
         cur_b = c.b;
       }
       const int acc_i = p.t.nacc == 2 ? (item & 1) : 0;
@@ -655,7 +664,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc_i]);
     }
-    if (has_stats && cur_b >= 0) flush_stats(p, my_stats, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
+    if (has_stats && cur_b >= 0) flush_stats(p, s_stats, warp, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
   }
 
   // ---- teardown

@@ -195,7 +195,7 @@ cudaError_t launch_bn_fold(const float* g, const float* b, const float* m, const
 }
 cudaError_t launch_gn_finalize(const float* stats, int B, int tiles, int cpad, int C, int groups, long long pixels, const float* gamma,
                                const float* beta, float eps, float* affine, cudaStream_t st) {
-  gn_finalize_kernel<<<B * groups, 1024, 0, st>>>(stats, tiles, cpad, C, groups, pixels, gamma, beta, eps, affine);
+  gn_finalize_kernel<<<B * groups, 256, 0, st>>>(stats, tiles, cpad, C, groups, pixels, gamma, beta, eps, affine);
   return cudaGetLastError();
 }
 cudaError_t launch_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks, long long pixels,
