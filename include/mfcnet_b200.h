@@ -172,6 +172,45 @@ int mfc_affine_silu_add(const void* a, const float* affine, const void* r, void*
                         int B, int chunks, long long pixels, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * HRNet resampling (models/hrnet.py).
+ * ---------------------------------------------------------------------------------- */
+
+/* Fuse step of HighResolutionModule.forward (models/hrnet.py:237-260) and the head's
+ * upsample+concat (:464-471): out = act(scale * sum_j T_j + shift), where term j is a C8
+ * tensor either at the output size or at a lower resolution that is bilinearly upsampled
+ * (F.interpolate, mode='bilinear', align_corners=False) while being read.  Terms are added
+ * in order, in fp32.  scale/shift: per output channel [chunks*8] or NULL. */
+typedef struct MfcFuseTerm {
+  const void* ptr;          /* C8 [B][chunks][H][W][8] */
+  long long batch_stride;   /* bytes */
+  int H, W;
+} MfcFuseTerm;
+typedef struct MfcFuseArgs {
+  int B, chunks, H, W;      /* output geometry */
+  int nterms;               /* 1..MFC_MAX_SRC */
+  int act;                  /* 0 none, 1 ReLU */
+  int dtype;
+  int reserved;
+  MfcFuseTerm term[MFC_MAX_SRC];
+  const float* scale;
+  const float* shift;
+  void* out;
+  long long out_batch_stride;
+} MfcFuseArgs;
+int mfc_fuse_sum(const MfcFuseArgs* a, void* stream);
+
+/* F.interpolate(x, size=(Hout,Wout), mode='bilinear', align_corners=False) of fp32 NCHW maps
+ * (models/hrnet.py:473-474).  Writes fp32 NCHW and / or the first ceil(C/8) C8 planes. */
+typedef struct MfcResizeArgs {
+  const float* src;         /* [B][C][Hin][Win] */
+  float* dst_nchw;          /* [B][C][Hout][Wout] or NULL */
+  void* dst_c8;             /* C8 [B][ceil(C/8)][Hout][Wout][8] or NULL */
+  long long c8_batch_stride;
+  int B, C, Hin, Win, Hout, Wout, dtype, reserved;
+} MfcResizeArgs;
+int mfc_bilinear_resize(const MfcResizeArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Temporal fusion pieces.
  * ---------------------------------------------------------------------------------- */
 
@@ -266,6 +305,8 @@ int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* o
 #define MFC_OP_AFFINE_SILU_ADD 3 /* a = MfcAddArgs*                   */
 #define MFC_OP_GATHER 4          /* a = MfcGatherArgs*                */
 #define MFC_OP_WARP 5            /* a = MfcWarpArgs*                  */
+#define MFC_OP_FUSE_SUM 6        /* a = MfcFuseArgs*                  */
+#define MFC_OP_RESIZE 7          /* a = MfcResizeArgs*                */
 
 typedef struct MfcGnArgs {
   const float* stats;

@@ -4,10 +4,11 @@ from .correlation import FunctionCorrelation, ModuleCorrelation, correlation
 from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
 from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxima_and_estimate_centroids, gaussian_blur,
                       heatmap_head, predicted_keypoints)
-from .multiframe import ResUNetMultiBasic, ResUNetMultiLarge
+from .hrnet import HighResolutionNet
+from .multiframe import HRNetMultiBasic, HRNetMultiLarge, ResUNetMultiBasic, ResUNetMultiLarge
 from .resunet import ResUnet_VB
 
-__all__ = ["abi", "engine", "ResUnet_VB", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
+__all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic", "HRNetMultiLarge", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
            "FunctionCorrelation", "ModuleCorrelation", "correlation", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
            "get_tooltip_segmentation_model", "get_multiframe_segmentation_model"]
@@ -15,9 +16,13 @@ __all__ = ["abi", "engine", "ResUnet_VB", "MultiFrameNetBasic", "MultiFrameNetLa
 
 def get_tooltip_segmentation_model(args):
     """Factory with the reference's signature (models/__init__.py:23-52).  Model types served by
-    the B200 engine: 'ResUNet' (absent upstream)."""
+    the B200 engine: 'ResUNet' (absent upstream) and 'HRNet'."""
     if args.model_type == "ResUNet":
         return ResUnet_VB(channels=3, dim=getattr(args, "resunet_dim", 16), out_dim=args.num_classes)
+    if args.model_type == "HRNet":
+        # models/__init__.py:39-47 loads a Cityscapes checkpoint and swaps the head; offline the head is
+        # simply built with args.num_classes (load weights with load_state_dict as usual)
+        return HighResolutionNet(num_classes=args.num_classes)
     raise ValueError(f"Model type {args.model_type} not recognized")
 
 
@@ -30,4 +35,8 @@ def get_multiframe_segmentation_model(args):
         return ResUNetMultiBasic(**kw)
     if args.model_type == "ResUNetMulti-Large":
         return ResUNetMultiLarge(**kw)
+    if args.model_type == "HRNetMulti-Basic":
+        return HRNetMultiBasic(**kw)
+    if args.model_type == "HRNetMulti-Large":
+        return HRNetMultiLarge(**kw)
     raise ValueError(f"Model type {args.model_type} not recognized")

@@ -12,7 +12,7 @@ from . import build as _build
 
 MFC_F16, MFC_BF16 = 0, 1
 MFC_MAX_SRC = 8
-OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP = 1, 2, 3, 4, 5
+OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP, OP_FUSE_SUM, OP_RESIZE = 1, 2, 3, 4, 5, 6, 7
 
 c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -67,6 +67,22 @@ class MfcGatherArgs(C.Structure):
                 ("W", c_int), ("dtype", c_int)]
 
 
+class MfcFuseTerm(C.Structure):
+    _fields_ = [("ptr", c_void_p), ("batch_stride", c_ll), ("H", c_int), ("W", c_int)]
+
+
+class MfcFuseArgs(C.Structure):
+    _fields_ = [("B", c_int), ("chunks", c_int), ("H", c_int), ("W", c_int), ("nterms", c_int), ("act", c_int),
+                ("dtype", c_int), ("reserved", c_int), ("term", MfcFuseTerm * MFC_MAX_SRC), ("scale", c_void_p),
+                ("shift", c_void_p), ("out", c_void_p), ("out_batch_stride", c_ll)]
+
+
+class MfcResizeArgs(C.Structure):
+    _fields_ = [("src", c_void_p), ("dst_nchw", c_void_p), ("dst_c8", c_void_p), ("c8_batch_stride", c_ll),
+                ("B", c_int), ("C", c_int), ("Hin", c_int), ("Win", c_int), ("Hout", c_int), ("Wout", c_int),
+                ("dtype", c_int), ("reserved", c_int)]
+
+
 class MfcCmd(C.Structure):
     _fields_ = [("op", c_int), ("reserved", c_int), ("a", c_void_p), ("b", c_void_p)]
 
@@ -85,6 +101,8 @@ _SIGNATURES = {
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
     "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p], c_int),
     "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),
+    "mfc_fuse_sum": ([C.POINTER(MfcFuseArgs), c_void_p], c_int),
+    "mfc_bilinear_resize": ([C.POINTER(MfcResizeArgs), c_void_p], c_int),
     "mfc_heatmap_head": ([c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "mfc_argmax_u8": ([c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p], c_int),
     "mfc_correlation_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),

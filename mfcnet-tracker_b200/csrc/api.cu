@@ -283,6 +283,30 @@ int mfc_argmax_u8(const float* x, int B, int N, long long pixels, uint8_t* out, 
   MFC_LAUNCH(mfc::launch_argmax_u8(x, B, N, pixels, out, (cudaStream_t)stream), "argmax_u8");
 }
 
+// ---- HRNet resampling ---------------------------------------------------------------------------
+int mfc_fuse_sum(const MfcFuseArgs* a, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!a || a->B < 1 || a->chunks < 1 || a->H < 1 || a->W < 1 || a->nterms < 1 || a->nterms > MFC_MAX_SRC || !a->out || !dtype_ok(a->dtype))
+    return fail(MFC_EINVAL, "fuse_sum: bad argument");
+  if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(MFC_EINVAL, "fuse_sum: scale and shift come together");
+  for (int j = 0; j < a->nterms; ++j) {
+    const MfcFuseTerm& t = a->term[j];
+    if (!t.ptr || t.H < 1 || t.W < 1 || t.H > a->H || t.W > a->W) return fail(MFC_EINVAL, "fuse_sum: term %d invalid (only upsampling)", j);
+    if (((uintptr_t)t.ptr & 15) || (t.batch_stride & 15)) return fail(MFC_EINVAL, "fuse_sum: term %d not 16-byte aligned", j);
+  }
+  MFC_LAUNCH(mfc::launch_fuse_sum(*a, (cudaStream_t)stream), "fuse_sum");
+}
+
+int mfc_bilinear_resize(const MfcResizeArgs* a, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!a || !a->src || (!a->dst_nchw && !a->dst_c8) || a->B < 1 || a->C < 1 || a->Hin < 1 || a->Win < 1 || a->Hout < 1 || a->Wout < 1 ||
+      !dtype_ok(a->dtype))
+    return fail(MFC_EINVAL, "bilinear_resize: bad argument");
+  MFC_LAUNCH(mfc::launch_bilinear_resize(a->src, a->B, a->C, a->Hin, a->Win, a->Hout, a->Wout, a->dst_nchw, a->dst_c8,
+                                         a->c8_batch_stride, a->dtype == MFC_BF16, (cudaStream_t)stream),
+             "bilinear_resize");
+}
+
 // ---- correlation -------------------------------------------------------------------------------
 int mfc_correlation_fwd(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp, int stride2,
                         int exact_order, void* stream) {
@@ -347,6 +371,12 @@ int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
       }
       case MFC_OP_WARP:
         rc = mfc_flow_warp((const MfcWarpArgs*)c.a, stream);
+        break;
+      case MFC_OP_FUSE_SUM:
+        rc = mfc_fuse_sum((const MfcFuseArgs*)c.a, stream);
+        break;
+      case MFC_OP_RESIZE:
+        rc = mfc_bilinear_resize((const MfcResizeArgs*)c.a, stream);
         break;
       default:
         rc = fail(MFC_EINVAL, "run_list: unknown op %d at %d", c.op, i);

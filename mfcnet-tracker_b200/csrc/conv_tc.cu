@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   const int total_items = p.B * p.t.tiles_x * p.t.tiles_y * p.t.nblk;
   const int ksteps_per_stage = p.t.CBc / 2;
 
-  // ---- one-time setup (independent of the previous kernel's output)
+  // ---- one-time setup (independent of the previous kernel's output: overlaps its tail under PDL)
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < p.t.nstages; ++i) {
       mbar_init(&bar_full[i], kProdWarps);
@@ -499,6 +500,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // from here on the previous kernel's outputs (activations, GroupNorm affines) are read
   const long long t_setup = clock64();
 
   if (warp >= kProdWarp0) {
@@ -834,8 +836,17 @@ static cudaError_t launch_conv_inst(const ConvParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured_for = dev;
   }
-  conv_tc_kernel<BF16, MODE, NB16><<<(unsigned)p.t.grid, kConvThreads, p.t.smem_bytes, st>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p.t.grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = p.t.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BF16, MODE, NB16>, p);
 }
 
 template <bool BF16, int MODE>

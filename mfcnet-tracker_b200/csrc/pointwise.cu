@@ -8,6 +8,8 @@ namespace mfc {
 // ---- fp32 NCHW planes -> one C8 plane ---------------------------------------------------------
 template <bool BF16>
 __global__ void gather_nchw_to_c8_kernel(MfcGather g, uint8_t* __restrict__ dst, long long dst_bs, int B, long long pixels) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * pixels;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / pixels);
@@ -96,6 +98,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, int tiles, i
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float* __restrict__ affine) {
   __shared__ double red[2][32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / groups, g = blockIdx.x % groups;
   const int cpg = C / groups;
   const int c0 = g * cpg;
@@ -148,6 +152,8 @@ template <bool BF16>
 __global__ void affine_silu_add_kernel(const uint8_t* __restrict__ a, const float* __restrict__ affine,
                                        const uint8_t* __restrict__ r, uint8_t* __restrict__ out, int B, int chunks,
                                        long long pixels) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * chunks * pixels;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long bc = i / pixels;  // b*chunks + chunk
@@ -173,9 +179,8 @@ static inline int grid_for(long long n, int threads) {
 cudaError_t launch_gather(const MfcGather& g, void* dst, long long dst_bs, int B, int H, int W, bool bf16, cudaStream_t st) {
   const long long pixels = (long long)H * W;
   const int grid = grid_for((long long)B * pixels, 256);
-  if (bf16) gather_nchw_to_c8_kernel<true><<<grid, 256, 0, st>>>(g, (uint8_t*)dst, dst_bs, B, pixels);
-  else gather_nchw_to_c8_kernel<false><<<grid, 256, 0, st>>>(g, (uint8_t*)dst, dst_bs, B, pixels);
-  return cudaGetLastError();
+  if (bf16) return launch_pdl(gather_nchw_to_c8_kernel<true>, dim3(grid), dim3(256), 0, st, g, (uint8_t*)dst, dst_bs, B, pixels);
+  return launch_pdl(gather_nchw_to_c8_kernel<false>, dim3(grid), dim3(256), 0, st, g, (uint8_t*)dst, dst_bs, B, pixels);
 }
 cudaError_t launch_c8_to_nchw(const void* src, long long src_bs, float* dst, int B, int C, int H, int W, bool bf16, cudaStream_t st) {
   const long long pixels = (long long)H * W;
@@ -195,15 +200,16 @@ cudaError_t launch_bn_fold(const float* g, const float* b, const float* m, const
 }
 cudaError_t launch_gn_finalize(const float* stats, int B, int tiles, int cpad, int C, int groups, long long pixels, const float* gamma,
                                const float* beta, float eps, float* affine, cudaStream_t st) {
-  gn_finalize_kernel<<<B * groups, 256, 0, st>>>(stats, tiles, cpad, C, groups, pixels, gamma, beta, eps, affine);
-  return cudaGetLastError();
+  return launch_pdl(gn_finalize_kernel, dim3(B * groups), dim3(256), 0, st, stats, tiles, cpad, C, groups, pixels, gamma, beta, eps, affine);
 }
 cudaError_t launch_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks, long long pixels,
                                    bool bf16, cudaStream_t st) {
   const int grid = grid_for((long long)B * chunks * pixels, 256);
-  if (bf16) affine_silu_add_kernel<true><<<grid, 256, 0, st>>>((const uint8_t*)a, affine, (const uint8_t*)r, (uint8_t*)out, B, chunks, pixels);
-  else affine_silu_add_kernel<false><<<grid, 256, 0, st>>>((const uint8_t*)a, affine, (const uint8_t*)r, (uint8_t*)out, B, chunks, pixels);
-  return cudaGetLastError();
+  if (bf16)
+    return launch_pdl(affine_silu_add_kernel<true>, dim3(grid), dim3(256), 0, st, (const uint8_t*)a, affine, (const uint8_t*)r,
+                      (uint8_t*)out, B, chunks, pixels);
+  return launch_pdl(affine_silu_add_kernel<false>, dim3(grid), dim3(256), 0, st, (const uint8_t*)a, affine, (const uint8_t*)r,
+                    (uint8_t*)out, B, chunks, pixels);
 }
 
 }  // namespace mfc

@@ -1,0 +1,160 @@
+// resample.cu -- HBM-bound resampling kernels of the HRNet path (models/hrnet.py):
+//   fuse_sum_kernel      : HighResolutionModule fuse step (models/hrnet.py:237-260): y = relu(sum_j t_j) where a
+//                          term is either at the output resolution or a lower-resolution map that is bilinearly
+//                          upsampled (align_corners=False) on the fly; optional per-channel affine before the ReLU
+//                          (used by the segmentation head, where the 1x1 conv is commuted with the upsampling).
+//   bilinear_resize_kernel: F.interpolate(mode='bilinear', align_corners=False) of fp32 NCHW maps
+//                          (models/hrnet.py:473-474, the final x4 upsampling of the logits), writing fp32 NCHW
+//                          and / or C8.
+// One 16-byte pixel-chunk per thread, 128-bit loads and stores, fp32 arithmetic in PyTorch's own order.
+#include "common.cuh"
+#include "launch.h"
+
+namespace mfc {
+
+// PyTorch's area_pixel_compute_source_index for align_corners=False (never negative for bilinear)
+__device__ __forceinline__ void src_index(int dst, float ratio, int in_size, int& i0, int& step, float& lam) {
+  float s = ratio * ((float)dst + 0.5f) - 0.5f;
+  s = s < 0.0f ? 0.0f : s;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  step = (i0 < in_size - 1) ? 1 : 0;
+  lam = s - (float)i0;
+}
+
+struct FuseParams {
+  int B, chunks, H, W, nterms, act;
+  const uint8_t* ptr[MFC_MAX_SRC];
+  long long bs[MFC_MAX_SRC];
+  int h[MFC_MAX_SRC], w[MFC_MAX_SRC];
+  const float* scale;
+  const float* shift;
+  uint8_t* out;
+  long long out_bs;
+};
+
+template <bool BF16>
+__global__ void fuse_sum_kernel(const __grid_constant__ FuseParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long pixels = (long long)p.H * p.W;
+  const long long total = (long long)p.B * p.chunks * pixels;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % pixels;
+    const long long t = i / pixels;
+    const int ch = (int)(t % p.chunks);
+    const int b = (int)(t / p.chunks);
+    const int y = (int)(pix / p.W), x = (int)(pix - (long long)y * p.W);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    for (int j = 0; j < p.nterms; ++j) {
+      const uint8_t* base = p.ptr[j] + (long long)b * p.bs[j] + (long long)ch * p.h[j] * p.w[j] * 16;
+      float v[8];
+      if (p.h[j] == p.H && p.w[j] == p.W) {
+        unpack8<BF16>(ldg_nc16(base + pix * 16), v);
+      } else {
+        int y0, ys, x0, xs;
+        float ly, lx;
+        src_index(y, (float)p.h[j] / (float)p.H, p.h[j], y0, ys, ly);
+        src_index(x, (float)p.w[j] / (float)p.W, p.w[j], x0, xs, lx);
+        float v00[8], v01[8], v10[8], v11[8];
+        const uint8_t* r0 = base + ((long long)y0 * p.w[j] + x0) * 16;
+        const uint8_t* r1 = r0 + (long long)ys * p.w[j] * 16;
+        unpack8<BF16>(ldg_nc16(r0), v00);
+        unpack8<BF16>(ldg_nc16(r0 + xs * 16), v01);
+        unpack8<BF16>(ldg_nc16(r1), v10);
+        unpack8<BF16>(ldg_nc16(r1 + xs * 16), v11);
+        const float hy = 1.0f - ly, hx = 1.0f - lx;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
+      }
+      if (j == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = v[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    }
+    if (p.scale) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(acc[e], __ldg(p.scale + ch * 8 + e), __ldg(p.shift + ch * 8 + e));
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.0f);
+    }
+    *reinterpret_cast<uint4*>(p.out + (long long)b * p.out_bs + ((long long)ch * pixels + pix) * 16) = pack8<BF16>(acc);
+  }
+}
+
+template <bool BF16>
+__global__ void bilinear_resize_kernel(const float* __restrict__ src, int B, int C, int Hin, int Win, int Hout, int Wout,
+                                       float* __restrict__ dst_nchw, uint8_t* __restrict__ dst_c8, long long c8_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long opix = (long long)Hout * Wout, ipix = (long long)Hin * Win;
+  const long long total = (long long)B * opix;
+  const float ry = (float)Hin / (float)Hout, rx = (float)Win / (float)Wout;
+  const int chunks = (C + 7) / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / opix);
+    const long long pix = i - (long long)b * opix;
+    const int y = (int)(pix / Wout), x = (int)(pix - (long long)y * Wout);
+    int y0, ys, x0, xs;
+    float ly, lx;
+    src_index(y, ry, Hin, y0, ys, ly);
+    src_index(x, rx, Win, x0, xs, lx);
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const long long o00 = (long long)y0 * Win + x0, o10 = o00 + (long long)ys * Win;
+    for (int q = 0; q < chunks; ++q) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = q * 8 + e;
+        if (c < C) {
+          const float* pl = src + ((long long)b * C + c) * ipix;
+          v[e] = hy * (hx * __ldg(pl + o00) + lx * __ldg(pl + o00 + xs)) + ly * (hx * __ldg(pl + o10) + lx * __ldg(pl + o10 + xs));
+          if (dst_nchw) dst_nchw[((long long)b * C + c) * opix + pix] = v[e];
+        } else {
+          v[e] = 0.0f;
+        }
+      }
+      if (dst_c8) *reinterpret_cast<uint4*>(dst_c8 + (long long)b * c8_bs + ((long long)q * opix + pix) * 16) = pack8<BF16>(v);
+    }
+  }
+}
+
+static inline int grid_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = (long long)kSmCount * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+cudaError_t launch_fuse_sum(const MfcFuseArgs& a, cudaStream_t st) {
+  FuseParams p;
+  p.B = a.B; p.chunks = a.chunks; p.H = a.H; p.W = a.W; p.nterms = a.nterms; p.act = a.act;
+  for (int j = 0; j < MFC_MAX_SRC; ++j) {
+    p.ptr[j] = j < a.nterms ? (const uint8_t*)a.term[j].ptr : nullptr;
+    p.bs[j] = j < a.nterms ? a.term[j].batch_stride : 0;
+    p.h[j] = j < a.nterms ? a.term[j].H : 0;
+    p.w[j] = j < a.nterms ? a.term[j].W : 0;
+  }
+  p.scale = a.scale; p.shift = a.shift; p.out = (uint8_t*)a.out; p.out_bs = a.out_batch_stride;
+  const int grid = grid_for((long long)a.B * a.chunks * a.H * a.W, 256);
+  if (a.dtype == MFC_BF16) return launch_pdl(fuse_sum_kernel<true>, dim3(grid), dim3(256), 0, st, p);
+  return launch_pdl(fuse_sum_kernel<false>, dim3(grid), dim3(256), 0, st, p);
+}
+
+cudaError_t launch_bilinear_resize(const float* src, int B, int C, int Hin, int Win, int Hout, int Wout, float* dst_nchw,
+                                   void* dst_c8, long long c8_bs, bool bf16, cudaStream_t st) {
+  const int grid = grid_for((long long)B * Hout * Wout, 256);
+  if (bf16)
+    return launch_pdl(bilinear_resize_kernel<true>, dim3(grid), dim3(256), 0, st, src, B, C, Hin, Win, Hout, Wout, dst_nchw,
+                      (uint8_t*)dst_c8, c8_bs);
+  return launch_pdl(bilinear_resize_kernel<false>, dim3(grid), dim3(256), 0, st, src, B, C, Hin, Win, Hout, Wout, dst_nchw,
+                    (uint8_t*)dst_c8, c8_bs);
+}
+
+}  // namespace mfc

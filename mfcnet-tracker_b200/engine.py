@@ -318,6 +318,37 @@ class Program:
                                                     "bytes": 3 * a_act.B * a_act.C * a_act.H * a_act.W * 2})
         return Act(out_t, a_act.C)
 
+    def fuse_sum(self, terms, out_t, C_, scale=None, shift=None, act=1):
+        """out = act(scale * sum(terms) + shift); terms: Acts at the output size or lower (bilinear
+        align_corners=False upsampling on read).  Returns the output Act."""
+        a = abi.MfcFuseArgs()
+        B, chunks, H, W = out_t.shape[0], out_t.shape[1], out_t.shape[2], out_t.shape[3]
+        a.B, a.chunks, a.H, a.W, a.nterms, a.act, a.dtype = B, chunks, H, W, len(terms), act, self.cdtype
+        nbytes = B * C_ * H * W * 2
+        for j, t in enumerate(terms):
+            if t.affine is not None or t.chunks != chunks or t.B != B:
+                raise ValueError("fuse_sum terms must be materialised C8 tensors with the output's channels")
+            a.term[j].ptr, a.term[j].batch_stride, a.term[j].H, a.term[j].W = t.t.data_ptr(), t.bstride, t.H, t.W
+            self.keep.append(t.t)
+            nbytes += B * C_ * t.H * t.W * 2
+        a.scale, a.shift = abi.ptr(scale), abi.ptr(shift)
+        a.out, a.out_batch_stride = out_t.data_ptr(), out_t.stride(0) * out_t.element_size()
+        self.keep += [out_t, scale, shift]
+        self._push(abi.OP_FUSE_SUM, a, meta={"kind": "fuse_sum", "name": "", "flops": 0, "bytes": nbytes})
+        return Act(out_t, C_)
+
+    def resize(self, src_nchw, Hout, Wout, dst_nchw=None, dst_c8=None):
+        """Bilinear (align_corners=False) resize of an fp32 NCHW tensor into fp32 NCHW and/or C8."""
+        a = abi.MfcResizeArgs()
+        B, C_, Hin, Win = src_nchw.shape
+        a.src, a.dst_nchw, a.dst_c8 = src_nchw.data_ptr(), abi.ptr(dst_nchw), abi.ptr(dst_c8)
+        a.c8_batch_stride = 0 if dst_c8 is None else dst_c8.stride(0) * dst_c8.element_size()
+        a.B, a.C, a.Hin, a.Win, a.Hout, a.Wout, a.dtype = B, C_, Hin, Win, Hout, Wout, self.cdtype
+        self.keep += [src_nchw, dst_nchw, dst_c8]
+        nbytes = B * C_ * (Hin * Win * 4 + Hout * Wout * ((4 if dst_nchw is not None else 0) + (2 if dst_c8 is not None else 0)))
+        self._push(abi.OP_RESIZE, a, meta={"kind": "resize", "name": "", "flops": 0, "bytes": nbytes})
+        return a
+
     def warp(self, args, nbytes=0):
         self._push(abi.OP_WARP, args, meta={"kind": "flow_warp", "name": "", "flops": 0, "bytes": nbytes})
 

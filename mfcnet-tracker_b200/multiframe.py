@@ -22,6 +22,7 @@ from torch import nn
 from . import engine
 from .engine import Act, Ext
 from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
+from .hrnet import HighResolutionNet
 from .resunet import ResUnet_VB
 
 
@@ -144,3 +145,19 @@ class ResUNetMultiLarge(_MultiFrame):
     def __init__(self, num_classes, num_frames, pretrained=True, loadpath=None, optflow_inputs=False, depth_inputs=False, dim=16):
         base = ResUnet_VB(channels=3, dim=dim, out_dim=num_classes)
         super().__init__(base, MultiFrameNetLarge, num_classes, num_frames, optflow_inputs, depth_inputs)
+
+
+class HRNetMultiBasic(_MultiFrame):
+    """Drop-in for models/multiframe_model.py:408-438 (HRNet-W48 base, raw logits into the fusion head)."""
+
+    def __init__(self, num_classes=2, num_frames=1, pretrained=True, loadpath=None, optflow_inputs=False, depth_inputs=False):
+        super().__init__(HighResolutionNet(num_classes=num_classes), MultiFrameNetBasic, num_classes, num_frames, optflow_inputs,
+                         depth_inputs)
+
+
+class HRNetMultiLarge(_MultiFrame):
+    """Drop-in for models/multiframe_model.py:441-471."""
+
+    def __init__(self, num_classes=2, num_frames=1, pretrained=True, loadpath=None, optflow_inputs=False, depth_inputs=False):
+        super().__init__(HighResolutionNet(num_classes=num_classes), MultiFrameNetLarge, num_classes, num_frames, optflow_inputs,
+                         depth_inputs)

@@ -82,6 +82,26 @@ def main():
         _save(tag, man, {"kind": "mfcnet", "base": "resunet16", "variant": variant, "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 3},
               out=out.numpy())
 
+    # ---- SFC: HighResolutionNet (HRNet-W48, BASELINE config 4 base) at reduced resolution
+    tag = "hrnet_w48_64x96"
+    m = ref.hrnet.HighResolutionNet(num_classes=N)
+    man = _load_sd(m, seed=4)
+    x = synth.frames(tag, 1, 64, 96, seed=4)
+    _save(tag, man, {"kind": "hrnet", "B": 1, "H": 64, "W": 96, "seed": 4, "classes": N}, logits=m(_t(x)).numpy())
+
+    # ---- full MFCNet with the HRNet base (reference HRNetMultiLarge, K=3)
+    K, B, H, W = 3, 1, 64, 96
+    tag = f"mfcnet_hrnet_large_k{K}_64x96"
+    m = ref.multiframe.HRNetMultiLarge(num_classes=N, num_frames=K, pretrained=False, loadpath=None, optflow_inputs=True,
+                                       depth_inputs=True)
+    man = _load_sd(m, seed=5)
+    xs = [synth.frames(f"{tag}/{i}", B, H, W, 5) for i in range(K)]
+    fl = [synth.flow(f"{tag}/{i}", B, H, W, 5) for i in range(K - 1)]
+    dp = [synth.depth(f"{tag}/{i}", B, H, W, 5) for i in range(K)]
+    out = m([_t(a) for a in xs], optflow=[_t(a) for a in fl], depth=[_t(a) for a in dp])
+    _save(tag, man, {"kind": "mfcnet", "base": "hrnet", "variant": "large", "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 5},
+          out=out.numpy())
+
     # ---- the 576x720 grid buffer itself
     g = ref.multiframe.MultiFrameNetBasic(N, 3, False, True, True).grid.numpy()
     assert np.array_equal(g, synth.mesh_grid_576x720()), "synth grid != reference grid"

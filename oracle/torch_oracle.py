@@ -185,3 +185,98 @@ def correlation(first, second, max_disp=20, stride2=2):
             dx = (ix - D // 2) * stride2 + max_disp
             out[:, iy * D + ix] = (first * pad[:, :, dy : dy + H, dx : dx + W]).sum(1) / C
     return out
+
+
+# ----------------------------------------------------------------------------
+# HighResolutionNet  (models/hrnet.py:271-476)
+# ----------------------------------------------------------------------------
+def _bn_eval(sd, p, x, eps=1e-5):
+    """Eval-mode BatchNorm2d / SyncBatchNorm (models/hrnet.py:31): running statistics."""
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, eps)
+
+
+def _conv_bn(sd, p_conv, p_bn, x, stride=1, relu=False):
+    w = sd[p_conv + "weight"]
+    y = F.conv2d(x, w, sd.get(p_conv + "bias"), stride=stride, padding=w.shape[-1] // 2)
+    y = _bn_eval(sd, p_bn, y)
+    return F.relu(y) if relu else y
+
+
+def _hr_block(sd, p, x):
+    """BasicBlock (models/hrnet.py:58-74) or Bottleneck (:97-115), told apart by the presence of conv3."""
+    res = x
+    if p + "downsample.0.weight" in sd:
+        res = _conv_bn(sd, p + "downsample.0.", p + "downsample.1.", x)
+    h = _conv_bn(sd, p + "conv1.", p + "bn1.", x, relu=True)
+    if p + "conv3.weight" in sd:
+        h = _conv_bn(sd, p + "conv2.", p + "bn2.", h, relu=True)
+        h = _conv_bn(sd, p + "conv3.", p + "bn3.", h)
+    else:
+        h = _conv_bn(sd, p + "conv2.", p + "bn2.", h)
+    return F.relu(h + res)
+
+
+def _count(sd, prefix):
+    """number of consecutive integer children `prefix<i>.` present in the state dict"""
+    n = 0
+    while any(k.startswith("%s%d." % (prefix, n)) for k in sd):
+        n += 1
+    return n
+
+
+def _hr_chain(sd, p, x, relu_last):
+    """Sequential of stride-2 (conv3x3, bn[, relu]) units `p<k>.{0,1}` (fuse down-paths :213-231, transitions :371-387)."""
+    n = _count(sd, p)
+    for k in range(n):
+        x = _conv_bn(sd, "%s%d.0." % (p, k), "%s%d.1." % (p, k), x, stride=2, relu=relu_last or k < n - 1)
+    return x
+
+
+def _hr_module(sd, p, xs):
+    """HighResolutionModule.forward (models/hrnet.py:237-260)."""
+    nb = len(xs)
+    ys = []
+    for i in range(nb):
+        x = xs[i]
+        for k in range(_count(sd, "%sbranches.%d." % (p, i))):
+            x = _hr_block(sd, "%sbranches.%d.%d." % (p, i, k), x)
+        ys.append(x)
+    out = []
+    for i in range(nb):
+        acc = None
+        for j in range(nb):
+            q = "%sfuse_layers.%d.%d." % (p, i, j)
+            if j == i:
+                t = ys[j]
+            elif j > i:
+                t = _conv_bn(sd, q + "0.", q + "1.", ys[j])
+                t = F.interpolate(t, size=ys[i].shape[-2:], mode="bilinear", align_corners=False)
+            else:
+                t = _hr_chain(sd, q, ys[j], relu_last=False)
+            acc = t if acc is None else acc + t
+        out.append(F.relu(acc))
+    return out
+
+
+def hrnet_forward(sd, x, prefix=""):
+    """HighResolutionNet.forward (models/hrnet.py:424-476) -> raw logits at the input resolution."""
+    if prefix:
+        sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    x = _conv_bn(sd, "conv1.", "bn1.", x, stride=2, relu=True)
+    x = _conv_bn(sd, "conv2.", "bn2.", x, stride=2, relu=True)
+    for k in range(_count(sd, "layer1.")):
+        x = _hr_block(sd, "layer1.%d." % k, x)
+    xs = [_conv_bn(sd, "transition1.0.0.", "transition1.0.1.", x, relu=True), _hr_chain(sd, "transition1.1.", x, relu_last=True)]
+    for m in range(_count(sd, "stage2.")):
+        xs = _hr_module(sd, "stage2.%d." % m, xs)
+    xs = xs + [_hr_chain(sd, "transition2.2.", xs[-1], relu_last=True)]
+    for m in range(_count(sd, "stage3.")):
+        xs = _hr_module(sd, "stage3.%d." % m, xs)
+    xs = xs + [_hr_chain(sd, "transition3.3.", xs[-1], relu_last=True)]
+    for m in range(_count(sd, "stage4.")):
+        xs = _hr_module(sd, "stage4.%d." % m, xs)
+    size = xs[0].shape[-2:]
+    cat = torch.cat([xs[0]] + [F.interpolate(t, size=size, mode="bilinear", align_corners=False) for t in xs[1:]], 1)
+    y = F.relu(_bn_eval(sd, "last_layer.1.", F.conv2d(cat, sd["last_layer.0.weight"], sd["last_layer.0.bias"])))
+    y = F.conv2d(y, sd["last_layer.3.weight"], sd["last_layer.3.bias"])
+    return F.interpolate(y, size=(size[0] * 4, size[1] * 4), mode="bilinear", align_corners=False)

@@ -120,6 +120,35 @@ def test_mfcnet_resunet_matches_reference(M, variant, dt):
         assert err <= 10 * LOGIT_TOL, err
 
 
+def test_hrnet_matches_reference(M):
+    """HRNet-W48 (models/hrnet.py) against the real reference output; 307 fused conv+BN(+ReLU/+residual)
+    layers, the fuse upsampling and the commuted head."""
+    tag = "hrnet_w48_64x96"
+    meta, man, arr = G.load(tag)
+    net = M.HighResolutionNet(num_classes=meta["classes"])
+    net.load_state_dict(G.state_dict(man, meta["seed"]), strict=True)
+    net = net.cuda().eval()
+    x = torch.from_numpy(synth.frames(tag, meta["B"], meta["H"], meta["W"], meta["seed"])).cuda()
+    with torch.no_grad():
+        y = net(x)
+    err, agree = _cmp("hrnet/" + tag, y, arr["logits"], "fp16")
+    assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE_SMALL, (err, agree)
+
+
+def test_mfcnet_hrnet_matches_reference(M):
+    tag = "mfcnet_hrnet_large_k3_64x96"
+    meta, man, arr = G.load(tag)
+    net = M.HRNetMultiLarge(num_classes=meta["N"], num_frames=meta["K"], pretrained=False, loadpath=None, optflow_inputs=True,
+                            depth_inputs=True)
+    net.load_state_dict(G.state_dict(man, meta["seed"]), strict=True)
+    net = net.cuda().eval()
+    xs, fl, dp = G.mfcnet_inputs(tag, meta)
+    with torch.no_grad():
+        y = net([t.cuda() for t in xs], optflow=[t.cuda() for t in fl], depth=[t.cuda() for t in dp])
+    err, agree = _cmp("mfcnet/" + tag, y, arr["out"], "fp16")
+    assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE_SMALL, (err, agree)
+
+
 def test_mfcnet_full_size_vs_oracle_on_gpu(M):
     """BASELINE config 2 shape (480x640, K=3, flow+depth) at B=1 against the torch oracle run in
     fp32 on the same GPU (stock torch ops as the checker, not the product)."""

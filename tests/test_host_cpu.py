@@ -116,6 +116,30 @@ def test_mfcnet_wrapper_keys_and_plan(M, variant):
         net.train()(xs, optflow=[torch.zeros(2, 2, 64, 96)] * 2, depth=[torch.zeros(2, 1, 64, 96)] * 3)
 
 
+def test_hrnet_state_dict_keys_and_plan(M):
+    """Checkpoint compatibility of the HRNet-W48 shell (1 839 tensors) and a plan-only forward."""
+    meta, man, _ = G.load("hrnet_w48_64x96")
+    net = M.HighResolutionNet(num_classes=meta["classes"]).eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    y = net(torch.zeros(1, 3, 64, 96))
+    assert y.shape == (1, meta["classes"], 64, 96)
+    prog = net._plans[(1, 64, 96)][0]
+    kinds = [m["kind"] for m in prog.meta]
+    # 307 reference convs, of which the 720x720 head conv is applied per branch (4 launches): 310
+    assert kinds.count("conv") == 310 and kinds.count("fuse_sum") == 2 + 4 * 3 + 3 * 4 + 1 and kinds.count("resize") == 1
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 3, 48, 96))             # not divisible by 32
+
+
+def test_hrnet_multi_wrapper_keys(M):
+    meta, man, _ = G.load("mfcnet_hrnet_large_k3_64x96")
+    net = M.HRNetMultiLarge(num_classes=5, num_frames=3, pretrained=False, loadpath=None, optflow_inputs=True, depth_inputs=True).eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    xs = [torch.zeros(1, 3, 64, 96)] * 3
+    y = net(xs, optflow=[torch.zeros(1, 2, 64, 96)] * 2, depth=[torch.zeros(1, 1, 64, 96)] * 3)
+    assert y.shape == (1, 5, 64, 96)
+
+
 def test_factories(M):
     class A:
         model_type = "ResUNetMulti-Large"
@@ -123,6 +147,8 @@ def test_factories(M):
         add_optflow_inputs, add_depth_inputs = True, True
     net = M.get_multiframe_segmentation_model(A)
     assert type(net).__name__ == "ResUNetMultiLarge" and net.multiframe_net.in_channels == 22
+    A.model_type = "HRNetMulti-Basic"
+    assert type(M.get_multiframe_segmentation_model(A)).__name__ == "HRNetMultiBasic"
     A.model_type = "nope"
     with pytest.raises(ValueError):
         M.get_multiframe_segmentation_model(A)

@@ -49,6 +49,28 @@ def test_mfcnet_resunet_matches_reference_output(variant):
     assert np.abs(y.numpy() - arr["out"]).max() < TOL
 
 
+def test_hrnet_matches_reference_output():
+    """HighResolutionNet (HRNet-W48): the restatement vs the real models/hrnet.py output."""
+    tag = "hrnet_w48_64x96"
+    meta, man, arr = G.load(tag)
+    sd = G.state_dict(man, meta["seed"])
+    x = torch.from_numpy(synth.frames(tag, meta["B"], meta["H"], meta["W"], meta["seed"]))
+    with torch.no_grad():
+        y = TO.hrnet_forward(sd, x)
+    assert y.shape == arr["logits"].shape
+    assert np.abs(y.numpy() - arr["logits"]).max() < TOL * max(1.0, float(np.abs(arr["logits"]).max()))
+
+
+def test_mfcnet_hrnet_matches_reference_output():
+    tag = "mfcnet_hrnet_large_k3_64x96"
+    meta, man, arr = G.load(tag)
+    sd = G.state_dict(man, meta["seed"])
+    xs, fl, dp = G.mfcnet_inputs(tag, meta)
+    with torch.no_grad():
+        y = TO.mfcnet_forward(sd, xs, fl, dp, base=TO.hrnet_forward, variant="large", N=meta["N"])
+    assert np.abs(y.numpy() - arr["out"]).max() < TOL * max(1.0, float(np.abs(arr["out"]).max()))
+
+
 def test_synth_is_stable():
     """Known-answer check of the platform-independent generator itself."""
     a = synth.normal("kat", (4,), seed=5)
