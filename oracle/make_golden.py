@@ -18,9 +18,14 @@ from . import refload, synth
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def _load_sd(module, seed):
+def _load_sd(module, seed, scale_keys=None):
+    """scale_keys {key: factor}: post-scaling of some tensors, recorded in the fixture's meta (HRNet: the
+    random-init 300-layer stack grows activations to ~6e3, the head is scaled down so that logits are O(5)
+    like a trained net's and the absolute 2e-2 logit tolerance of BASELINE.json means what it says)."""
     man = refload.manifest_of(module)
     sd = synth.fill_state_dict(man, seed)
+    for k, f in (scale_keys or {}).items():
+        sd[k] = (sd[k] * np.float32(f)).astype(np.float32)
     module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
     module.eval()
     return man
@@ -85,21 +90,25 @@ def main():
     # ---- SFC: HighResolutionNet (HRNet-W48, BASELINE config 4 base) at reduced resolution
     tag = "hrnet_w48_64x96"
     m = ref.hrnet.HighResolutionNet(num_classes=N)
-    man = _load_sd(m, seed=4)
+    sk = {"last_layer.3.weight": 1e-3, "last_layer.3.bias": 1e-3}
+    man = _load_sd(m, seed=4, scale_keys=sk)
     x = synth.frames(tag, 1, 64, 96, seed=4)
-    _save(tag, man, {"kind": "hrnet", "B": 1, "H": 64, "W": 96, "seed": 4, "classes": N}, logits=m(_t(x)).numpy())
+    _save(tag, man, {"kind": "hrnet", "B": 1, "H": 64, "W": 96, "seed": 4, "classes": N, "scale_keys": sk},
+          logits=m(_t(x)).numpy())
 
     # ---- full MFCNet with the HRNet base (reference HRNetMultiLarge, K=3)
     K, B, H, W = 3, 1, 64, 96
     tag = f"mfcnet_hrnet_large_k{K}_64x96"
     m = ref.multiframe.HRNetMultiLarge(num_classes=N, num_frames=K, pretrained=False, loadpath=None, optflow_inputs=True,
                                        depth_inputs=True)
-    man = _load_sd(m, seed=5)
+    sk = {"base_model.last_layer.3.weight": 1e-3, "base_model.last_layer.3.bias": 1e-3}
+    man = _load_sd(m, seed=5, scale_keys=sk)
     xs = [synth.frames(f"{tag}/{i}", B, H, W, 5) for i in range(K)]
     fl = [synth.flow(f"{tag}/{i}", B, H, W, 5) for i in range(K - 1)]
     dp = [synth.depth(f"{tag}/{i}", B, H, W, 5) for i in range(K)]
     out = m([_t(a) for a in xs], optflow=[_t(a) for a in fl], depth=[_t(a) for a in dp])
-    _save(tag, man, {"kind": "mfcnet", "base": "hrnet", "variant": "large", "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 5},
+    _save(tag, man, {"kind": "mfcnet", "base": "hrnet", "variant": "large", "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 5,
+                      "scale_keys": sk},
           out=out.numpy())
 
     # ---- the 576x720 grid buffer itself

@@ -19,8 +19,11 @@ def load(tag):
     return j["meta"], man, arrays
 
 
-def state_dict(man, seed, device="cpu"):
+def state_dict(man, seed, device="cpu", scale_keys=None):
+    """scale_keys: the fixture's meta["scale_keys"] (see oracle/make_golden.py::_load_sd)."""
     sd = synth.fill_state_dict(man, seed)
+    for k, f in (scale_keys or {}).items():
+        sd[k] = (sd[k] * np.float32(f)).astype(np.float32)
     return {k: torch.from_numpy(v).to(device) for k, v in sd.items()}
 
 

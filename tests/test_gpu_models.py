@@ -126,7 +126,7 @@ def test_hrnet_matches_reference(M):
     tag = "hrnet_w48_64x96"
     meta, man, arr = G.load(tag)
     net = M.HighResolutionNet(num_classes=meta["classes"])
-    net.load_state_dict(G.state_dict(man, meta["seed"]), strict=True)
+    net.load_state_dict(G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"]), strict=True)
     net = net.cuda().eval()
     x = torch.from_numpy(synth.frames(tag, meta["B"], meta["H"], meta["W"], meta["seed"])).cuda()
     with torch.no_grad():
@@ -140,7 +140,7 @@ def test_mfcnet_hrnet_matches_reference(M):
     meta, man, arr = G.load(tag)
     net = M.HRNetMultiLarge(num_classes=meta["N"], num_frames=meta["K"], pretrained=False, loadpath=None, optflow_inputs=True,
                             depth_inputs=True)
-    net.load_state_dict(G.state_dict(man, meta["seed"]), strict=True)
+    net.load_state_dict(G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"]), strict=True)
     net = net.cuda().eval()
     xs, fl, dp = G.mfcnet_inputs(tag, meta)
     with torch.no_grad():

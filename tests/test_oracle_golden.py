@@ -53,7 +53,7 @@ def test_hrnet_matches_reference_output():
     """HighResolutionNet (HRNet-W48): the restatement vs the real models/hrnet.py output."""
     tag = "hrnet_w48_64x96"
     meta, man, arr = G.load(tag)
-    sd = G.state_dict(man, meta["seed"])
+    sd = G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"])
     x = torch.from_numpy(synth.frames(tag, meta["B"], meta["H"], meta["W"], meta["seed"]))
     with torch.no_grad():
         y = TO.hrnet_forward(sd, x)
@@ -64,7 +64,7 @@ def test_hrnet_matches_reference_output():
 def test_mfcnet_hrnet_matches_reference_output():
     tag = "mfcnet_hrnet_large_k3_64x96"
     meta, man, arr = G.load(tag)
-    sd = G.state_dict(man, meta["seed"])
+    sd = G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"])
     xs, fl, dp = G.mfcnet_inputs(tag, meta)
     with torch.no_grad():
         y = TO.mfcnet_forward(sd, xs, fl, dp, base=TO.hrnet_forward, variant="large", N=meta["N"])
