@@ -787,26 +787,33 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
         nstages = std::min(nstages, kMaxStages);
         if (nstages < 1) continue;
         const uint32_t smem = (uint32_t)(off_stage + (uint64_t)nstages * stage_bytes + 128);
-        // ---- cost model (SM cycles per work item; the three roles overlap when there are >= 2 stages)
+        // ---- cost model: SM cycles, calibrated on B200 with the per-role timing switches of this kernel
+        // (MFC_CONV_DEBUG) and tools/ubench/mma_rate2.cu.  Every role pays a fixed cost per work item
+        // (decode, barriers, loop set-up) on top of its per-element work, so small tiles are expensive:
+        //   producers: ~600 per (item, K stage) + ~2.0 per 16-byte slot (+1.0 with the affine+SiLU pass)
+        //   MMA      : ~500 per item + ~62 per MMA for N <= 64 (single-thread issue), N/2+8 above; a
+        //              dependent accumulate chain costs 167 per MMA divided by the accumulators in rotation
+        //   epilogue : ~400 per item + ~475 per (run, 16-column) step of a warp
         const double load_items = (double)cin_chunks * s * s * rows_sub * P;
-        // producers: cp.async issue (~0.3 cyc per 16-byte item) or the HBM share of one SM (~0.7), plus the
-        // in-place affine+SiLU pass; streamed weights come from L2
-        const double L = load_items * (any_aff ? 1.0 : 0.7) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.3) + 60.0 * kstages;
-        const double indep = std::max(1, (R * kacc) / kMmaWarps);  // accumulators each issuing warp rotates over
-        const double per_mma = std::max(std::max(NB / 2.0, 32.0 + NB / 4.0) + 3.0, 167.0 / indep / kMmaWarps);
-        const double M = (double)R * taps * ksteps * per_mma;
-        const double e_run = 120.0 + (d.nsrc > 0 ? 0.0 : 0.0);
-        const double E = (double)((R + 1) / 2) * (NB / 16) * (e_run + 40.0 * (kacc - 1)) + 200.0;
+        const double L = 600.0 * kstages + load_items * (any_aff ? 3.0 : 2.0) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.5);
+        // per (tap, K step) entry each issuing warp pays ~120 cycles of loop overhead + ~45 per run pair it issues;
+        // the tensor pipe needs max(39, 32+N/4, N/2) per MMA; a dependent accumulate chain needs 167 cycles
+        // divided by the accumulators the warp rotates over
+        const double runs_w = std::ceil((double)R / kMmaWarps);
+        const double indep = std::max(1.0, std::floor((double)R * kacc / kMmaWarps));
+        const double pipe = std::max(39.0, std::max(32.0 + NB / 4.0, NB / 2.0 + 4.0));
+        const double per_entry = std::max(std::max(120.0 + 45.0 * R, R * pipe), runs_w * 167.0 / std::min(indep, 4.0));
+        const double M = 500.0 + (double)taps * ksteps * per_entry;
+        const double E = 400.0 + (double)((R + 1) / 2) * (NB / 16) * (475.0 + 120.0 * (kacc - 1));
         const int G = (int)std::min<long long>(items, kSmCount);
         const double rounds = std::ceil((double)items / G);
         double per_item;
         if (nstages >= 2) {
-          const double mx = std::max(L, std::max(M, nacc == 2 ? E : 0.0));
-          per_item = mx + 0.15 * (L + M + E - mx) + (nacc == 2 ? 0.0 : E) + 150.0;
+          per_item = std::max(L, std::max(M, nacc == 2 ? E : 0.0)) + (nacc == 2 ? 0.0 : E);
         } else {
-          per_item = L + std::max(M, E) + (nacc == 2 ? 0.0 : std::min(M, E)) + 300.0;
+          per_item = L + std::max(M, E) + (nacc == 2 ? 0.0 : std::min(M, E));
         }
-        const double cost = rounds * per_item + (L + M + E) * 0.5 + (resident ? (double)(w_bytes_nblk / 16) * 0.05 : 0.0);
+        const double cost = (rounds - 1.0) * per_item + (L + M + E) + (resident ? (double)(w_bytes_nblk / 16) * 0.3 : 0.0);
         if (cost < best_cost) {
           best_cost = cost;
           found = true;

@@ -32,6 +32,14 @@ def require_cuda(t, what):
                            % (what, t.device.type))
 
 
+def canonical_device(device):
+    """torch.device('cuda') and torch.device('cuda:0') compare unequal: always carry the index."""
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None and torch.cuda.is_available():
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
 def device_guard(device):
     import contextlib
     return torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()
@@ -96,7 +104,7 @@ class Arena:
     another on one stream) share their intermediate buffers."""
 
     def __init__(self, device):
-        self.device = torch.device(device)
+        self.device = canonical_device(device)
         self.slots = []
         self.pos = 0
 
@@ -125,7 +133,7 @@ class Program:
 
     def __init__(self, device, dtype_name):
         self.lib = abi.load()
-        self.device = torch.device(device)
+        self.device = canonical_device(device)
         self.dtype_name = dtype_name
         self.tdtype, self.cdtype = _DTYPES[dtype_name]
         self.cmds = []       # (op, struct_a, struct_b)
@@ -377,7 +385,7 @@ class WeightPacker:
 
     def __init__(self, device, dtype_name):
         self.lib = abi.load()
-        self.device = torch.device(device)
+        self.device = canonical_device(device)
         self.tdtype, self.cdtype = _DTYPES[dtype_name]
         self.cache = {}
 

@@ -41,7 +41,7 @@ class StreamingMFCNet:
         self.model = model
         self.K, self.N = model.num_frames, model.num_classes
         self.H, self.W = H, W
-        self.device = torch.device(device)
+        self.device = engine.canonical_device(device)
         self.dt = dtype_name or model.dtype_name or engine.default_dtype()
         self.t = 0
         self._build()
