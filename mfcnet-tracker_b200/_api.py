@@ -7,11 +7,12 @@ from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxi
 from .hrnet import HighResolutionNet
 from .multiframe import HRNetMultiBasic, HRNetMultiLarge, ResUNetMultiBasic, ResUNetMultiLarge
 from .resunet import ResUnet_VB
+from .stream import HostPipeline, StreamingMFCNet, shard_frames
 
 __all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic", "HRNetMultiLarge", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
            "FunctionCorrelation", "ModuleCorrelation", "correlation", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
-           "get_tooltip_segmentation_model", "get_multiframe_segmentation_model"]
+           "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames"]
 
 
 def get_tooltip_segmentation_model(args):

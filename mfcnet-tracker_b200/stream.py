@@ -115,3 +115,51 @@ class StreamingMFCNet:
         for t in tensors.values():
             engine.record_stream(t)
         return y
+
+
+class HostPipeline:
+    """Double-buffered host -> device staging for streaming inference.
+
+    The reference loop uploads every window synchronously before the forward
+    (scripts/test_multiframe_segmentation_on_videos_v3.py:256-263: `.cuda()` on the frame, flow and depth
+    tensors).  Here the H2D copies of step i+1 run on a dedicated copy stream while step i computes:
+    `submit(host_tensors)` enqueues the copies of one step into the next free slot, `acquire()` makes the
+    compute stream wait for the oldest submitted slot and returns its device tensors, `release()` marks the
+    slot reusable once the work enqueued so far has consumed it.  Host tensors should be pinned."""
+
+    def __init__(self, like, device="cuda", slots=2):
+        self.device = engine.canonical_device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in like] for _ in range(slots)]
+        self.copied = [torch.cuda.Event() for _ in range(slots)]
+        self.consumed = [None] * slots
+        self.head = self.tail = 0      # next slot to fill / next slot to hand out
+        self.in_flight = 0
+
+    def submit(self, host_tensors):
+        if self.in_flight == len(self.slots):
+            raise RuntimeError("HostPipeline: all slots are in flight; acquire()/release() one first")
+        s = self.head
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[s] is not None:
+                self.copy_stream.wait_event(self.consumed[s])   # the previous user of this slot is done
+            for d, h in zip(self.slots[s], host_tensors):
+                d.copy_(h, non_blocking=True)
+            self.copied[s].record(self.copy_stream)
+        self.head = (s + 1) % len(self.slots)
+        self.in_flight += 1
+
+    def acquire(self):
+        if self.in_flight == 0:
+            raise RuntimeError("HostPipeline: nothing submitted")
+        s = self.tail
+        torch.cuda.current_stream(self.device).wait_event(self.copied[s])
+        return self.slots[s]
+
+    def release(self):
+        s = self.tail
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.consumed[s] = ev
+        self.tail = (s + 1) % len(self.slots)
+        self.in_flight -= 1
