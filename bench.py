@@ -72,7 +72,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -199,6 +199,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout must carry exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     import mfcnet_tracker_b200 as M
     M.abi.load()
@@ -220,12 +223,14 @@ def run_b200(args):
 
     W_ = max(3, args.warmup)
     with torch.no_grad():
+        # nvidia-smi needs a few hundred ms to start sampling: launch it before the warm-up so that it is
+        # already running (20 ms period) when the timed region begins
+        sampler = ClockSampler(local) if rank == 0 else None
         for _ in range(W_):
             out = step()
         torch.cuda.synchronize()
         prog = net._plans[(B, H, W)]["prog"]
         # ---- resident-input throughput ("value")
-        sampler = ClockSampler(local) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         torch.cuda.synchronize()
