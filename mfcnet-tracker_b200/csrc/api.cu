@@ -175,7 +175,7 @@ int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info) {
   info->grid = t.grid;
   info->smem_bytes = (int)t.smem_bytes;
   info->tmem_cols = (int)t.tmem_cols;
-  info->packed_weight_bytes = (long long)t.nblk * t.ksteps * d->kh * d->kw * 2 * t.NB * 16;
+  info->packed_weight_bytes = (long long)t.nblk * t.ksteps * t.entries * 2 * t.NB * 16;
   return MFC_OK;
 }
 
@@ -187,7 +187,8 @@ int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w
   mfc::ConvTiling t;
   rc = get_tiling(d, &t);
   if (rc != MFC_OK) return rc;
-  MFC_LAUNCH(mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, d->kh * d->kw, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk, packed,
+  MFC_LAUNCH(mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,
+                                      t.pair ? d->kw : 0, d->kh * d->kw, packed,
                                       d->dtype == MFC_BF16, (cudaStream_t)stream),
              "conv_pack");
 }

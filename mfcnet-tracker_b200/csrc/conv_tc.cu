@@ -27,12 +27,51 @@ namespace mfc {
 // ---- producers: phase 1, asynchronous raw copy of one 8-channel plane of the halo tile --------------
 // Every thread enumerates the same (idx -> row, col) items in phase 1 and phase 2, so a thread only ever
 // touches smem slots it filled itself: cp.async.wait_group is the only synchronisation between the phases.
+// Incremental (row, col) walk of the flattened halo tile for the stride-1, no-upsample case (most layers):
+// idx advances by NT slots = (step_r rows, step_c cols) with one carry, so there is no division and the
+// global pointer is a running 64-bit add.
+struct TileWalk {
+  int r, c;
+  int step_r, step_c;
+};
+template <int NT>
+__device__ __forceinline__ TileWalk tile_walk(const ConvParams& p, int tid) {
+  TileWalk w;
+  w.r = (int)fdiv((uint32_t)tid, p.divP);
+  w.c = tid - w.r * p.t.P;
+  w.step_r = (int)fdiv((uint32_t)NT, p.divP);
+  w.step_c = NT - w.step_r * p.t.P;
+  return w;
+}
+
 template <int NT>
 __device__ __forceinline__ void issue_plane(const ConvParams& p, uint8_t* plane, const uint8_t* __restrict__ src, int iy_base,
                                             int ix_base, int tid) {
   const int s = p.stride;
   const int P = p.t.P;
   const int items = p.t.rows_sub * P;
+  if (s == 1 && p.upsample == 1) {
+    TileWalk w = tile_walk<NT>(p, tid);
+    const uint32_t H = (uint32_t)p.Hin, W = (uint32_t)p.Win;
+    uint32_t dst = smem_u32(plane) + (uint32_t)tid * 16u;
+    const long long gstep = ((long long)w.step_r * p.Win + w.step_c) * 16, gwrap = ((long long)p.Win - P) * 16;
+    const uint8_t* g = src + ((long long)(iy_base + w.r) * p.Win + (ix_base + w.c)) * 16;
+#pragma unroll 2
+    for (int idx = tid; idx < items; idx += NT) {
+      const bool ok = (uint32_t)(iy_base + w.r) < H && (uint32_t)(ix_base + w.c) < W;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? g : src), "r"(ok ? 16 : 0) : "memory");
+      dst += NT * 16u;
+      g += gstep;
+      w.r += w.step_r;
+      w.c += w.step_c;
+      if (w.c >= P) {
+        w.c -= P;
+        ++w.r;
+        g += gwrap;
+      }
+    }
+    return;
+  }
   const int Hup = p.Hin * p.upsample, Wup = p.Win * p.upsample;
   const int ush = p.upsample == 2 ? 1 : 0;
   for (int sub = 0; sub < s * s; ++sub) {
@@ -52,13 +91,27 @@ __device__ __forceinline__ void issue_plane(const ConvParams& p, uint8_t* plane,
 }
 
 // ---- producers: phase 2, in-place GroupNorm-affine + SiLU of the thread's own slots ----------------
+template <bool BF16>
+__device__ __forceinline__ void affine_silu_slot(uint32_t saddr, const float (&sc)[8], const float (&sh)[8]) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  float f[8];
+  unpack8<BF16>(v, f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float h = fmaf(f[i], sc[i], sh[i]);
+    f[i] = fmaf(h, tanh_fast(h), h);
+  }
+  v = pack8<BF16>(f);
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <bool BF16, int NT>
 __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* plane, const float* __restrict__ aff, int iy_base,
                                                 int ix_base, int tid) {
   const int s = p.stride;
   const int P = p.t.P;
   const int items = p.t.rows_sub * P;
-  const int Hup = p.Hin * p.upsample, Wup = p.Win * p.upsample;
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -66,6 +119,24 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
     sc[i] = 0.5f * a.x;  // silu(y) = h + h*tanh(h) with h = y/2: the halving is folded into the affine
     sh[i] = 0.5f * a.y;
   }
+  if (s == 1 && p.upsample == 1) {
+    TileWalk w = tile_walk<NT>(p, tid);
+    const uint32_t H = (uint32_t)p.Hin, W = (uint32_t)p.Win;
+    uint32_t dst = smem_u32(plane) + (uint32_t)tid * 16u;
+#pragma unroll 2
+    for (int idx = tid; idx < items; idx += NT) {
+      if ((uint32_t)(iy_base + w.r) < H && (uint32_t)(ix_base + w.c) < W) affine_silu_slot<BF16>(dst, sc, sh);  // padding stays zero
+      dst += NT * 16u;
+      w.r += w.step_r;
+      w.c += w.step_c;
+      if (w.c >= P) {
+        w.c -= P;
+        ++w.r;
+      }
+    }
+    return;
+  }
+  const int Hup = p.Hin * p.upsample, Wup = p.Win * p.upsample;
   for (int sub = 0; sub < s * s; ++sub) {
     const int py = sub / s, px = sub - py * s;
     uint8_t* sp = plane + (size_t)sub * p.t.slots_sub * 16;
@@ -75,16 +146,7 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
       const int c2 = idx - r2 * P;
       const int iy = iy_base + r2 * s + py;
       const int ix = ix_base + c2 * s + px;
-      if (iy >= 0 && iy < Hup && ix >= 0 && ix < Wup) {  // padding stays exactly zero
-        float f[8];
-        unpack8<BF16>(lds16(sp + (size_t)idx * 16), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float h = fmaf(f[i], sc[i], sh[i]);
-          f[i] = fmaf(h, tanh_fast(h), h);
-        }
-        sts16(sp + (size_t)idx * 16, pack8<BF16>(f));
-      }
+      if (iy >= 0 && iy < Hup && ix >= 0 && ix < Wup) affine_silu_slot<BF16>(smem_u32(sp) + (uint32_t)idx * 16u, sc, sh);
     }
   }
 }
@@ -118,7 +180,7 @@ __device__ __forceinline__ void issue_stage(const ConvParams& p, uint8_t* abuf, 
   const int ksteps_per_stage = p.t.CBc / 2;
   const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
   if (!p.t.b_resident) {
-    const int taps = p.kh * p.kw;
+    const int taps = p.t.entries;
     uint8_t* bbuf = abuf + p.t.a_stage_bytes;
     const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * taps * (size_t)(2 * p.t.NB * 16);
     const int n16 = nks * taps * 2 * p.t.NB;
@@ -129,7 +191,7 @@ __device__ __forceinline__ void issue_stage(const ConvParams& p, uint8_t* abuf, 
     const int k = ks * p.t.CBc + q;
     uint8_t* plane = abuf + (size_t)q * p.t.plane_bytes;
     if (k >= p.t.cin_chunks) {
-      zero_plane<NT>(p, plane, tid);
+      if (!p.t.pair) zero_plane<NT>(p, plane, tid);  // tap pairing reads the one real plane twice: no pad plane
       continue;
     }
     issue_plane<NT>(p, plane, locate_plane(p, b, k).src, iy_base, ix_base, tid);
@@ -459,7 +521,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NB = p.t.NB;
-  const int taps = p.kh * p.kw;
+  const int taps = p.t.entries;  // MMA entries (= B-operand blocks) per K step
   const int total_items = p.B * p.t.tiles_x * p.t.tiles_y * p.t.nblk;
   const int ksteps_per_stage = p.t.CBc / 2;
 
@@ -484,6 +546,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     }
     if (p.stats)
       for (int i = tid; i < kEpiWarps * cpad * 2; i += kConvThreads) s_stats[i] = 0.0f;
+  }
+  if (p.t.pair) {
+    // tap pairing: the second K half of the last horizontal pair of an odd-width kernel reads one slot past
+    // the loaded tile (times a zero weight); that slot must hold finite data, so clear the ring once
+    const int n16 = (int)(((size_t)p.t.nstages * p.t.stage_bytes) >> 4);
+    for (int i = tid; i < n16; i += kConvThreads) sts16(stage0 + (size_t)i * 16, make_uint4(0, 0, 0, 0));
+    fence_async_smem();
   }
   if (p.t.b_resident) {
     const int n16 = p.t.ksteps * taps * 2 * NB;
@@ -580,7 +649,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
           const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
           // Descriptors differ only in their 14-bit start-address field (16-byte units), so the whole
           // issue loop is integer adds on the low word: no divisions, ~10 instructions per MMA.
-          const uint64_t da0 = make_smem_desc(smem_u32(abuf), p.t.plane_bytes, 128);
+          const uint64_t da0 = make_smem_desc(smem_u32(abuf), p.t.pair ? 16u : p.t.plane_bytes, 128);  // LBO: next plane, or next pixel
           const uint64_t db0 = make_smem_desc(smem_u32(bbuf), (uint32_t)(NB * 16), 128);
           const uint32_t da_hi = (uint32_t)(da0 >> 32), db_hi = (uint32_t)(db0 >> 32);
           const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
@@ -588,10 +657,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
           // back-to-back MMAs never accumulate into the same TMEM columns (a dependent accumulate
           // chain serialises on the tensor pipe's latency, which dwarfs an N=16 MMA's busy cycles).
           uint32_t b_t = db_lo0;
+          const int kw_eff = p.t.pair ? (p.kw + 1) >> 1 : p.kw;   // tap pairing: entry j covers kx = 2j, 2j+1
+          const uint32_t kx_step = p.t.pair ? 2u : 1u;
           for (int ky = 0; ky < kh_eff; ++ky) {
             const uint32_t a_row = da_lo0 + (s2 ? (uint32_t)(ky & 1) * 2u * sub + (uint32_t)(ky >> 1) * P : (uint32_t)ky * P);
-            for (int kx = 0; kx < p.kw; ++kx) {
-              const uint32_t a_tap = a_row + (s2 ? (uint32_t)(kx & 1) * sub + (uint32_t)(kx >> 1) : (uint32_t)kx);
+            for (int kx = 0; kx < kw_eff; ++kx) {
+              const uint32_t a_tap = a_row + (s2 ? (uint32_t)(kx & 1) * sub + (uint32_t)(kx >> 1) : (uint32_t)kx * kx_step);
               uint32_t b_lo = b_t;
               uint32_t a_sk = a_tap;
               for (int sk = 0; sk < nks; ++sk) {
@@ -684,9 +755,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> [nblk][kstep][tap][khalf][NB][8] fp16/bf16
 // ------------------------------------------------------------------------------------------------
+// With tap pairing (pair_kw > 0: a single input plane, kernel width pair_kw) entry (ky, j) holds tap (ky, 2j) in
+// its first K half and tap (ky, 2j+1) -- or zeros past the kernel edge -- in the second.
 template <bool BF16>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin_w, int taps, const int* __restrict__ chan_map,
-                                    int cin_chunks, int ksteps, int NB, int nblk, uint16_t* __restrict__ out) {
+                                    int cin_chunks, int ksteps, int NB, int nblk, int pair_kw, int taps_w,
+                                    uint16_t* __restrict__ out) {
   const size_t total = (size_t)nblk * ksteps * taps * 2 * NB * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
@@ -697,11 +771,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
     const int ks = r % ksteps; r /= ksteps;
     const int nb = (int)r;
     const int co = nb * NB + n;
-    const int kp = (ks * 2 + kh) * 8 + e;  // padded concat channel
+    int kp = (ks * 2 + kh) * 8 + e;  // padded concat channel
+    int tw = t;                      // tap index in the OIHW weight
+    if (pair_kw > 0) {
+      const int per_row = (pair_kw + 1) >> 1;
+      const int ky = t / per_row, kx = (t - ky * per_row) * 2 + kh;
+      kp = e;
+      tw = kx < pair_kw ? ky * pair_kw + kx : -1;
+    }
     float v = 0.0f;
-    if (co < Cout && kp < cin_chunks * 8) {
+    if (co < Cout && kp < cin_chunks * 8 && tw >= 0) {
       const int ci = chan_map ? chan_map[kp] : kp;
-      if (ci >= 0 && ci < Cin_w) v = w[((size_t)co * Cin_w + ci) * taps + t];
+      if (ci >= 0 && ci < Cin_w) v = w[((size_t)co * Cin_w + ci) * taps_w + tw];
     }
     if constexpr (BF16) {
       __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -733,13 +814,16 @@ int conv_nb(int cout, int* nblk) {
 bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
   const int s = d.stride;
   const int hy = (d.kh - 1) / s, hx = (d.kw - 1) / s;
-  const int taps = d.kh * d.kw;
   int cin_chunks = 0;
   bool any_aff = false;
   for (int i = 0; i < d.nsrc; ++i) {
     cin_chunks += d.src[i].nchunks;
     any_aff = any_aff || d.src[i].affine != nullptr;
   }
+  // tap pairing: with ONE 8-channel input plane (the RGB stem) half of every K=16 MMA would multiply zeros;
+  // instead its second K half reads the same plane one pixel to the right = the next horizontal tap
+  const bool pair = cin_chunks == 1 && s == 1 && d.upsample == 1 && d.kw > 1;
+  const int taps = pair ? d.kh * ((d.kw + 1) / 2) : d.kh * d.kw;  // MMA entries per K step
   const int ksteps = ceil_div(cin_chunks, 2);
   int nblk;
   const int NB = conv_nb(d.Cout, &nblk);
@@ -818,7 +902,7 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
           best_cost = cost;
           found = true;
           best.TH = TH; best.TW = TW; best.P = P; best.R = R; best.rows_sub = rows_sub; best.slots_sub = slots_sub;
-          best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.b_resident = resident ? 1 : 0;
+          best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.pair = pair ? 1 : 0; best.entries = taps; best.b_resident = resident ? 1 : 0;
           best.tiles_x = tiles_x; best.tiles_y = tiles_y;
           best.NB = NB; best.nblk = nblk; best.ksteps = ksteps; best.cin_chunks = cin_chunks;
           best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;
@@ -876,14 +960,16 @@ cudaError_t launch_conv(const ConvParams& p, bool bf16, cudaStream_t st) {
 }
 
 cudaError_t launch_pack_weights(const float* w, int Cout, int Cin_w, int taps, const int* chan_map, int cin_chunks,
-                                int ksteps, int NB, int nblk, void* out, bool bf16, cudaStream_t st) {
+                                int ksteps, int NB, int nblk, int pair_kw, int taps_w, void* out, bool bf16, cudaStream_t st) {
   const size_t total = (size_t)nblk * ksteps * taps * 2 * NB * 8;
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 4096);
   if (bf16)
-    pack_weights_kernel<true><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, (uint16_t*)out);
+    pack_weights_kernel<true><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, pair_kw, taps_w,
+                                                          (uint16_t*)out);
   else
-    pack_weights_kernel<false><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, (uint16_t*)out);
+    pack_weights_kernel<false><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, pair_kw, taps_w,
+                                                           (uint16_t*)out);
   return cudaGetLastError();
 }
 

@@ -26,6 +26,9 @@ struct ConvTiling {
   int kstages;       // K stages per work item
   int nstages;       // depth of the shared-memory stage ring
   int nacc;          // TMEM accumulator buffers (2 = the epilogue of item i overlaps the MMAs of item i+1)
+  int pair;          // 1: single 8-channel input plane, stride 1: one K=16 MMA covers the taps (ky,kx) and (ky,kx+1)
+                     //    (second K half = the same plane one pixel to the right, LBO = 16 bytes) -> ceil(kw/2) entries per row
+  int entries;       // MMA entries per K step: kh*kw, or kh*ceil(kw/2) with tap pairing
   int kacc;          // K-split accumulator sets per buffer (1, 2 or 4): consecutive taps rotate over them so that
                      // back-to-back MMAs are independent even when the tile has a single run; the epilogue sums them
   int b_resident;    // 1: the whole packed weight blob is loaded once per CTA; 0: streamed with each stage
