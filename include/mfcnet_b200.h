@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MFC_ABI_VERSION 2
+#define MFC_ABI_VERSION 3
 
 /* error codes */
 #define MFC_OK 0
@@ -123,6 +123,14 @@ typedef struct MfcConvDesc {
   int act;                 /* 0 none, 1 ReLU (after scale/shift and residual)     */
   int dtype;               /* MFC_F16 / MFC_BF16 (inputs, weights, C8 outputs)    */
   int nsrc;                /* channel-concat sources, in order                    */
+  /* Output-parity mode for ConvTranspose2d(k=4, s=2, p=1) (models/ternausnet.py:35): the transposed conv is
+   * four 2x2 convs, one per output parity (py,px).  in_off_{y,x} (0 or 1) shift the input window
+   * (input row = oy*stride - pad + in_off_y + ky); out_stride 2 makes the epilogue store pixel (oy,ox) at
+   * (oy*2 + out_off_y, ox*2 + out_off_x) of a [2*Hout][2*Wout] output tensor.  out_stride 1 (default, 0
+   * is read as 1) and zero offsets = an ordinary conv. */
+  int in_off_y, in_off_x;
+  int out_stride, out_off_y, out_off_x;
+  int reserved;
   MfcSrc src[MFC_MAX_SRC];
 } MfcConvDesc;
 
@@ -170,6 +178,10 @@ int mfc_gn_finalize(const float* stats, int B, int stats_per_image, int cpad, in
  * models/resunet.py:90-95).  All C8 [B][chunks][H][W][8]. */
 int mfc_affine_silu_add(const void* a, const float* affine, const void* r, void* out,
                         int B, int chunks, long long pixels, int dtype, void* stream);
+
+/* nn.MaxPool2d(2, 2) (models/ternausnet.py:56,107) on a C8 tensor [B][chunks][H][W][8] -> [H/2][W/2]. */
+int mfc_maxpool2(const void* src, long long src_bstride_bytes, void* dst, long long dst_bstride_bytes,
+                 int B, int chunks, int H, int W, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * HRNet resampling (models/hrnet.py).
@@ -307,6 +319,8 @@ int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* o
 #define MFC_OP_WARP 5            /* a = MfcWarpArgs*                  */
 #define MFC_OP_FUSE_SUM 6        /* a = MfcFuseArgs*                  */
 #define MFC_OP_RESIZE 7          /* a = MfcResizeArgs*                */
+#define MFC_OP_MAXPOOL2 8        /* a = MfcPoolArgs*                  */
+#define MFC_OP_HEATMAP 9         /* a = MfcHeatmapArgs*               */
 
 typedef struct MfcGnArgs {
   const float* stats;
@@ -334,6 +348,22 @@ typedef struct MfcGatherArgs {
   long long dst_bstride_bytes;
   int B, H, W, dtype;
 } MfcGatherArgs;
+
+typedef struct MfcPoolArgs {
+  const void* src;
+  void* dst;
+  long long src_bstride_bytes, dst_bstride_bytes;
+  int B, chunks, H, W, dtype, reserved;
+} MfcPoolArgs;
+
+typedef struct MfcHeatmapArgs {   /* mfc_heatmap_head as a list command (TernausNet's log_softmax head) */
+  const float* logits;
+  float* logp;
+  float* prob;
+  uint8_t* argmax;
+  long long pixels;
+  int B, N;
+} MfcHeatmapArgs;
 
 typedef struct MfcCmd {
   int op;

@@ -5,11 +5,13 @@ from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
 from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxima_and_estimate_centroids, gaussian_blur,
                       heatmap_head, predicted_keypoints)
 from .hrnet import HighResolutionNet
-from .multiframe import HRNetMultiBasic, HRNetMultiLarge, ResUNetMultiBasic, ResUNetMultiLarge
+from .multiframe import (HRNetMultiBasic, HRNetMultiLarge, ResUNetMultiBasic, ResUNetMultiLarge, TernausNetMultiBasic,
+                         TernausNetMultiLarge)
 from .resunet import ResUnet_VB
+from .ternausnet import TernausNet11, TernausNet16
 from .stream import HostPipeline, StreamingMFCNet, shard_frames
 
-__all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic", "HRNetMultiLarge", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
+__all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic", "HRNetMultiLarge", "TernausNet11", "TernausNet16", "TernausNetMultiBasic", "TernausNetMultiLarge", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
            "FunctionCorrelation", "ModuleCorrelation", "correlation", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
            "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames"]
@@ -20,6 +22,9 @@ def get_tooltip_segmentation_model(args):
     the B200 engine: 'ResUNet' (absent upstream) and 'HRNet'."""
     if args.model_type == "ResUNet":
         return ResUnet_VB(channels=3, dim=getattr(args, "resunet_dim", 16), out_dim=args.num_classes)
+    if args.model_type in ("TernausNet11", "TernausNet16"):   # models/__init__.py:24-27
+        cls = TernausNet11 if args.model_type == "TernausNet11" else TernausNet16
+        return cls(num_classes=args.num_classes, num_filters=64, pretrained=False)
     if args.model_type == "HRNet":
         # models/__init__.py:39-47 loads a Cityscapes checkpoint and swaps the head; offline the head is
         # simply built with args.num_classes (load weights with load_state_dict as usual)
@@ -36,6 +41,10 @@ def get_multiframe_segmentation_model(args):
         return ResUNetMultiBasic(**kw)
     if args.model_type == "ResUNetMulti-Large":
         return ResUNetMultiLarge(**kw)
+    if args.model_type == "TernausNetMulti-Basic":
+        return TernausNetMultiBasic(**{k: v for k, v in kw.items() if k != "pretrained"})
+    if args.model_type == "TernausNetMulti-Large":
+        return TernausNetMultiLarge(**{k: v for k, v in kw.items() if k != "pretrained"})
     if args.model_type == "HRNetMulti-Basic":
         return HRNetMultiBasic(**kw)
     if args.model_type == "HRNetMulti-Large":

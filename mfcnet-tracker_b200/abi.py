@@ -12,7 +12,7 @@ from . import build as _build
 
 MFC_F16, MFC_BF16 = 0, 1
 MFC_MAX_SRC = 8
-OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP, OP_FUSE_SUM, OP_RESIZE = 1, 2, 3, 4, 5, 6, 7
+OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP, OP_FUSE_SUM, OP_RESIZE, OP_MAXPOOL2, OP_HEATMAP = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -34,7 +34,8 @@ class MfcSrc(C.Structure):
 class MfcConvDesc(C.Structure):
     _fields_ = [("B", c_int), ("Hin", c_int), ("Win", c_int), ("Hout", c_int), ("Wout", c_int), ("Cout", c_int),
                 ("kh", c_int), ("kw", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int), ("act", c_int),
-                ("dtype", c_int), ("nsrc", c_int), ("src", MfcSrc * MFC_MAX_SRC)]
+                ("dtype", c_int), ("nsrc", c_int), ("in_off_y", c_int), ("in_off_x", c_int), ("out_stride", c_int),
+                ("out_off_y", c_int), ("out_off_x", c_int), ("reserved", c_int), ("src", MfcSrc * MFC_MAX_SRC)]
 
 
 class MfcConvIO(C.Structure):
@@ -83,6 +84,16 @@ class MfcResizeArgs(C.Structure):
                 ("dtype", c_int), ("reserved", c_int)]
 
 
+class MfcPoolArgs(C.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("src_bstride_bytes", c_ll), ("dst_bstride_bytes", c_ll),
+                ("B", c_int), ("chunks", c_int), ("H", c_int), ("W", c_int), ("dtype", c_int), ("reserved", c_int)]
+
+
+class MfcHeatmapArgs(C.Structure):
+    _fields_ = [("logits", c_void_p), ("logp", c_void_p), ("prob", c_void_p), ("argmax", c_void_p), ("pixels", c_ll),
+                ("B", c_int), ("N", c_int)]
+
+
 class MfcCmd(C.Structure):
     _fields_ = [("op", c_int), ("reserved", c_int), ("a", c_void_p), ("b", c_void_p)]
 
@@ -101,6 +112,7 @@ _SIGNATURES = {
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
     "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p], c_int),
     "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),
+    "mfc_maxpool2": ([c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_fuse_sum": ([C.POINTER(MfcFuseArgs), c_void_p], c_int),
     "mfc_bilinear_resize": ([C.POINTER(MfcResizeArgs), c_void_p], c_int),
     "mfc_heatmap_head": ([c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
@@ -151,7 +163,7 @@ def load(build_if_missing=True):
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.argtypes = args
             fn.restype = res
-        if lib.mfc_abi_version() != 2:
+        if lib.mfc_abi_version() != 3:
             raise RuntimeError("libmfcnet_b200.so ABI version mismatch")
         _lib = _PlanOnly(lib) if plan_only() else lib
     return _lib

@@ -77,7 +77,18 @@ int validate_desc(const MfcConvDesc* d) {
   if (d->nsrc < 1 || d->nsrc > MFC_MAX_SRC) return fail(MFC_EINVAL, "conv: nsrc %d out of range", d->nsrc);
   if (d->pad < 0 || d->pad > 5) return fail(MFC_EINVAL, "conv: pad %d unsupported", d->pad);
   const int Hup = d->Hin * d->upsample, Wup = d->Win * d->upsample;
-  const int ho = (Hup + 2 * d->pad - d->kh) / d->stride + 1, wo = (Wup + 2 * d->pad - d->kw) / d->stride + 1;
+  int ho = (Hup + 2 * d->pad - d->kh) / d->stride + 1, wo = (Wup + 2 * d->pad - d->kw) / d->stride + 1;
+  if (d->out_stride != 0 && d->out_stride != 1 && d->out_stride != 2) return fail(MFC_EINVAL, "conv: out_stride %d unsupported", d->out_stride);
+  if ((unsigned)d->in_off_y > 1u || (unsigned)d->in_off_x > 1u || (unsigned)d->out_off_y > 1u || (unsigned)d->out_off_x > 1u)
+    return fail(MFC_EINVAL, "conv: parity offsets must be 0 or 1");
+  if (d->out_stride == 2) {  // one output parity of ConvTranspose2d(4,2,1): a 2x2 pad-1 conv restricted to Hin x Win outputs
+    if (d->kh != 2 || d->kw != 2 || d->stride != 1 || d->pad != 1 || d->upsample != 1)
+      return fail(MFC_EINVAL, "conv: out_stride 2 is the k4 s2 p1 transposed-conv parity mode (k=2, s=1, p=1)");
+    ho = d->Hin;
+    wo = d->Win;
+  } else if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) {
+    return fail(MFC_EINVAL, "conv: parity offsets need out_stride 2");
+  }
   if (ho != d->Hout || wo != d->Wout)
     return fail(MFC_EINVAL, "conv: Hout/Wout %dx%d inconsistent with input %dx%d (expected %dx%d)", d->Hout, d->Wout, Hup, Wup, ho, wo);
   for (int i = 0; i < d->nsrc; ++i)
@@ -205,6 +216,9 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
   if (rc != MFC_OK) return rc;
   p.B = d->B; p.Hin = d->Hin; p.Win = d->Win; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.upsample = d->upsample; p.act = d->act;
+  p.in_off_y = d->in_off_y; p.in_off_x = d->in_off_x; p.out_stride = d->out_stride == 2 ? 2 : 1;
+  p.out_off_y = d->out_off_y; p.out_off_x = d->out_off_x;
+  if (p.out_stride == 2 && (io->residual || io->stats)) return fail(MFC_EINVAL, "conv: transposed-conv parity mode has no residual / statistics");
   p.nsrc = d->nsrc;
   int end = 0;
   for (int i = 0; i < MFC_MAX_SRC; ++i) {
@@ -282,6 +296,13 @@ int mfc_argmax_u8(const float* x, int B, int N, long long pixels, uint8_t* out, 
   MFC_REQUIRE_ARCH();
   if (!x || !out || B < 1 || N < 1 || N > 255 || pixels < 1) return fail(MFC_EINVAL, "argmax_u8: bad argument");
   MFC_LAUNCH(mfc::launch_argmax_u8(x, B, N, pixels, out, (cudaStream_t)stream), "argmax_u8");
+}
+
+int mfc_maxpool2(const void* src, long long src_bs, void* dst, long long dst_bs, int B, int chunks, int H, int W, int dtype, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!src || !dst || B < 1 || chunks < 1 || H < 2 || W < 2 || !dtype_ok(dtype)) return fail(MFC_EINVAL, "maxpool2: bad argument");
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15) || (src_bs & 15) || (dst_bs & 15)) return fail(MFC_EINVAL, "maxpool2: not 16-byte aligned");
+  MFC_LAUNCH(mfc::launch_maxpool2(src, src_bs, dst, dst_bs, B, chunks, H, W, dtype == MFC_BF16, (cudaStream_t)stream), "maxpool2");
 }
 
 // ---- HRNet resampling ---------------------------------------------------------------------------
@@ -379,6 +400,16 @@ int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
       case MFC_OP_RESIZE:
         rc = mfc_bilinear_resize((const MfcResizeArgs*)c.a, stream);
         break;
+      case MFC_OP_MAXPOOL2: {
+        const MfcPoolArgs* g = (const MfcPoolArgs*)c.a;
+        rc = mfc_maxpool2(g->src, g->src_bstride_bytes, g->dst, g->dst_bstride_bytes, g->B, g->chunks, g->H, g->W, g->dtype, stream);
+        break;
+      }
+      case MFC_OP_HEATMAP: {
+        const MfcHeatmapArgs* g = (const MfcHeatmapArgs*)c.a;
+        rc = mfc_heatmap_head(g->logits, g->B, g->N, g->pixels, g->logp, g->prob, g->argmax, stream);
+        break;
+      }
       default:
         rc = fail(MFC_EINVAL, "run_list: unknown op %d at %d", c.op, i);
     }

@@ -276,7 +276,7 @@ __device__ __forceinline__ PixRef run_pixel(const ConvParams& p, int r, int lq, 
   const int oy = oy0 + row, ox = ox0 + col;
   PixRef q;
   q.valid = row < p.t.TH && col < p.t.TW && oy < p.Hout && ox < p.Wout;
-  q.pix = (size_t)oy * p.Wout + ox;
+  q.pix = (size_t)(oy * p.out_stride + p.out_off_y) * (size_t)(p.Wout * p.out_stride) + (size_t)(ox * p.out_stride + p.out_off_x);
   return q;
 }
 
@@ -312,7 +312,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   const int NB = NB16 ? 16 : p.t.NB;
   const int cpad = NB * p.t.nblk;
   const int cc_out = (p.Cout + 7) >> 3;
-  const size_t HWo = (size_t)p.Hout * p.Wout;
+  const size_t HWo = (size_t)p.Hout * p.Wout * p.out_stride * p.out_stride;
   const bool has_res = kRes && p.res != nullptr;
   const bool has_stats = kStats && p.stats != nullptr;
   const bool has_nchw = kNchw && p.y_nchw != nullptr;
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         mbar_wait(&bar_empty[slot_i], phase_i ^ 1u);  // the MMAs that read this slot have drained
         if (!(p.debug & 1))
           issue_stage<kProdThreads>(p, stage0 + (size_t)slot_i * p.t.stage_bytes, c.b, c.nbk, ksi,
-                                    c.oy0 * p.stride - p.pad, c.ox0 * p.stride - p.pad, ptid);
+                                    c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x, ptid);
         if (++ksi == p.t.kstages) {
           ksi = 0;
           wi += gridDim.x;
@@ -607,8 +607,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // this thread's copies of the hand-off stage have landed
       const ItemCoord c = decode_item(p, wt);
       if (!(p.debug & 1))
-        transform_stage<BF16, kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, c.b, kst, c.oy0 * p.stride - p.pad,
-                                            c.ox0 * p.stride - p.pad, ptid);
+        transform_stage<BF16, kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, c.b, kst,
+                                            c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x, ptid);
       fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[slot_t]);

@@ -50,6 +50,7 @@ struct ConvTiling {
 struct ConvParams {
   int B, Hin, Win, Hout, Wout, Cout;
   int kh, kw, stride, pad, upsample, act;
+  int in_off_y, in_off_x, out_stride, out_off_y, out_off_x;  // output-parity mode of the k4 s2 transposed conv
   int nsrc;
   const uint8_t* src_ptr[MFC_MAX_SRC];
   const float* src_aff[MFC_MAX_SRC];

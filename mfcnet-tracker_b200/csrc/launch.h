@@ -32,6 +32,8 @@ cudaError_t launch_heatmap_head(const float* logits, int B, int N, long long pix
 cudaError_t launch_argmax_u8(const float* x, int B, int N, long long pixels, uint8_t* out, cudaStream_t st);
 
 // resample.cu
+cudaError_t launch_maxpool2(const void* src, long long src_bs, void* dst, long long dst_bs, int B, int chunks, int H, int W,
+                            bool bf16, cudaStream_t st);
 cudaError_t launch_fuse_sum(const MfcFuseArgs& a, cudaStream_t st);
 cudaError_t launch_bilinear_resize(const float* src, int B, int C, int Hin, int Win, int Hout, int Wout, float* dst_nchw,
                                    void* dst_c8, long long c8_bs, bool bf16, cudaStream_t st);

@@ -126,10 +126,44 @@ __global__ void bilinear_resize_kernel(const float* __restrict__ src, int B, int
   }
 }
 
+// nn.MaxPool2d(2, 2): max over the 2x2 window, per channel, on C8 planes (floor(H/2) x floor(W/2) outputs)
+template <bool BF16>
+__global__ void maxpool2_kernel(const uint8_t* __restrict__ src, long long src_bs, uint8_t* __restrict__ dst, long long dst_bs,
+                                int B, int chunks, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long opix = (long long)Ho * Wo;
+  const long long total = (long long)B * chunks * opix;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % opix;
+    const long long t = i / opix;
+    const int ch = (int)(t % chunks);
+    const int b = (int)(t / chunks);
+    const int y = (int)(pix / Wo), x = (int)(pix - (long long)y * Wo);
+    const uint8_t* p0 = src + (long long)b * src_bs + (((long long)ch * H + 2 * y) * W + 2 * x) * 16;
+    float a[8], c[8], d[8], e[8];
+    unpack8<BF16>(ldg_nc16(p0), a);
+    unpack8<BF16>(ldg_nc16(p0 + 16), c);
+    unpack8<BF16>(ldg_nc16(p0 + (long long)W * 16), d);
+    unpack8<BF16>(ldg_nc16(p0 + (long long)W * 16 + 16), e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaxf(fmaxf(a[k], c[k]), fmaxf(d[k], e[k]));
+    *reinterpret_cast<uint4*>(dst + (long long)b * dst_bs + ((long long)ch * opix + pix) * 16) = pack8<BF16>(a);
+  }
+}
+
 static inline int grid_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   const long long cap = (long long)kSmCount * 16;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+cudaError_t launch_maxpool2(const void* src, long long src_bs, void* dst, long long dst_bs, int B, int chunks, int H, int W,
+                            bool bf16, cudaStream_t st) {
+  const int grid = grid_for((long long)B * chunks * (H / 2) * (W / 2), 256);
+  if (bf16) return launch_pdl(maxpool2_kernel<true>, dim3(grid), dim3(256), 0, st, (const uint8_t*)src, src_bs, (uint8_t*)dst, dst_bs, B, chunks, H, W);
+  return launch_pdl(maxpool2_kernel<false>, dim3(grid), dim3(256), 0, st, (const uint8_t*)src, src_bs, (uint8_t*)dst, dst_bs, B, chunks, H, W);
 }
 
 cudaError_t launch_fuse_sum(const MfcFuseArgs& a, cudaStream_t st) {

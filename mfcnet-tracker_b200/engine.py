@@ -229,13 +229,18 @@ class Program:
                                            "bytes": B * H * W * (4 * nreal + 16)})
         return a
 
-    def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act):
+    def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act, parity=None):
+        """parity=(py, px): one output parity of ConvTranspose2d(4, 2, 1), a 2x2 conv whose result lands on
+        the pixels (2y+py, 2x+px) of a [2H][2W] output (include/mfcnet_b200.h, MfcConvDesc)."""
         d = abi.MfcConvDesc()
         s0 = srcs[0]
         d.B, d.Hin, d.Win = s0.B, s0.H, s0.W
         Hup, Wup = s0.H * upsample, s0.W * upsample
         d.Hout = (Hup + 2 * pad - k) // stride + 1
         d.Wout = (Wup + 2 * pad - k) // stride + 1
+        if parity is not None:
+            d.Hout, d.Wout = s0.H, s0.W
+            d.in_off_y, d.in_off_x, d.out_stride, d.out_off_y, d.out_off_x = parity[0], parity[1], 2, parity[0], parity[1]
         d.Cout, d.kh, d.kw, d.stride, d.pad, d.upsample, d.act = Cout, k, k, stride, pad, upsample, act
         d.dtype = self.cdtype
         if len(srcs) > abi.MFC_MAX_SRC:
@@ -271,9 +276,10 @@ class Program:
             self.keep += [residual.t, residual.affine]
         out = None
         B, Cout = d.B, d.Cout
+        os_ = 2 if d.out_stride == 2 else 1
         if out_c8:
             if y_c8 is None:
-                y_c8 = arena.alloc((B, (Cout + 7) // 8, d.Hout, d.Wout, 8), self.tdtype)
+                y_c8 = arena.alloc((B, (Cout + 7) // 8, d.Hout * os_, d.Wout * os_, 8), self.tdtype)
             out = Act(y_c8, Cout)
             io.y_c8 = y_c8.data_ptr()
             io.y_batch_stride = out.bstride
@@ -355,6 +361,28 @@ class Program:
         self.keep += [src_nchw, dst_nchw, dst_c8]
         nbytes = B * C_ * (Hin * Win * 4 + Hout * Wout * ((4 if dst_nchw is not None else 0) + (2 if dst_c8 is not None else 0)))
         self._push(abi.OP_RESIZE, a, meta={"kind": "resize", "name": "", "flops": 0, "bytes": nbytes})
+        return a
+
+    def maxpool2(self, x, out_t):
+        """nn.MaxPool2d(2, 2) on a materialised C8 Act."""
+        if x.affine is not None:
+            raise ValueError("maxpool2 needs a materialised tensor")
+        a = abi.MfcPoolArgs()
+        a.src, a.dst = x.t.data_ptr(), out_t.data_ptr()
+        a.src_bstride_bytes, a.dst_bstride_bytes = x.bstride, out_t.stride(0) * out_t.element_size()
+        a.B, a.chunks, a.H, a.W, a.dtype = x.B, x.chunks, x.H, x.W, self.cdtype
+        self.keep += [x.t, out_t]
+        self._push(abi.OP_MAXPOOL2, a, meta={"kind": "maxpool2", "name": "", "flops": 0, "bytes": int(x.B * x.C * x.H * x.W * 2 * 1.25)})
+        return Act(out_t, x.C)
+
+    def heatmap(self, logits, logp=None, prob=None, argmax=None):
+        """log-softmax / softmax / argmax over the channel axis of fp32 NCHW logits, as a list command."""
+        a = abi.MfcHeatmapArgs()
+        B, N = logits.shape[0], logits.shape[1]
+        a.logits, a.logp, a.prob, a.argmax = logits.data_ptr(), abi.ptr(logp), abi.ptr(prob), abi.ptr(argmax)
+        a.pixels, a.B, a.N = logits.shape[2] * logits.shape[3], B, N
+        self.keep += [logits, logp, prob, argmax]
+        self._push(abi.OP_HEATMAP, a, meta={"kind": "heatmap_head", "name": "", "flops": 0, "bytes": B * N * a.pixels * 8})
         return a
 
     def warp(self, args, nbytes=0):
@@ -458,12 +486,12 @@ class Builder:
         self.tdtype = self.prog.tdtype
 
     def conv(self, key, srcs, w_oihw, k, *, bias=None, scale=None, shift=None, stride=1, pad=0, upsample=1, act=0,
-             residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None):
+             residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None, parity=None):
         """srcs: list of Act (channel concat in order).  w_oihw: fp32 device weight whose Cin axis
         is the concat of the sources' REAL channels (or, with first_weight_channel=[...], starts
         at the given offsets).  Returns (Act|None, stats|None, info, io)."""
         Cout = w_oihw.shape[0]
-        d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act)
+        d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity)
         info = self.prog.query(d)
         layout = []
         off = 0

@@ -24,6 +24,7 @@ from .engine import Act, Ext
 from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
 from .hrnet import HighResolutionNet
 from .resunet import ResUnet_VB
+from .ternausnet import TernausNet16
 
 
 def _sub_batch(n_frames, H, W):
@@ -164,3 +165,22 @@ class HRNetMultiLarge(_MultiFrame):
     def __init__(self, num_classes=2, num_frames=1, pretrained=True, loadpath=None, optflow_inputs=False, depth_inputs=False):
         super().__init__(HighResolutionNet(num_classes=num_classes), MultiFrameNetLarge, num_classes, num_frames, optflow_inputs,
                          depth_inputs)
+
+
+class TernausNetMultiBasic(_MultiFrame):
+    """Drop-in for models/multiframe_model.py:207-238: TernausNet16(num_filters=64) base whose softmax
+    probabilities (`base_model(x).exp()`, :227) feed the fusion head."""
+    head = "probs"
+
+    def __init__(self, num_classes, num_frames, pretrained=True, loadpath=None, optflow_inputs=False, depth_inputs=False):
+        super().__init__(TernausNet16(num_classes=num_classes, num_filters=64, pretrained=False), MultiFrameNetBasic, num_classes,
+                         num_frames, optflow_inputs, depth_inputs)
+
+
+class TernausNetMultiLarge(_MultiFrame):
+    """Drop-in for models/multiframe_model.py:240-271."""
+    head = "probs"
+
+    def __init__(self, num_classes, num_frames, pretrained=True, loadpath=None, optflow_inputs=False, depth_inputs=False):
+        super().__init__(TernausNet16(num_classes=num_classes, num_filters=64, pretrained=False), MultiFrameNetLarge, num_classes,
+                         num_frames, optflow_inputs, depth_inputs)

@@ -23,9 +23,7 @@ def _load_sd(module, seed, scale_keys=None):
     random-init 300-layer stack grows activations to ~6e3, the head is scaled down so that logits are O(5)
     like a trained net's and the absolute 2e-2 logit tolerance of BASELINE.json means what it says)."""
     man = refload.manifest_of(module)
-    sd = synth.fill_state_dict(man, seed)
-    for k, f in (scale_keys or {}).items():
-        sd[k] = (sd[k] * np.float32(f)).astype(np.float32)
+    sd = synth.apply_fixture_rules(synth.fill_state_dict(man, seed), scale_keys)
     module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
     module.eval()
     return man
@@ -110,6 +108,31 @@ def main():
     _save(tag, man, {"kind": "mfcnet", "base": "hrnet", "variant": "large", "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 5,
                       "scale_keys": sk},
           out=out.numpy())
+
+    # ---- SFC: TernausNet16 (VGG16 encoder, k4 s2 transposed-conv decoder, log_softmax head), num_filters=64 as
+    # at the reference call sites (models/__init__.py:27, models/multiframe_model.py:216).  Fixture rules: all conv
+    # weights x sqrt(2) (He gain: the plain ReLU stack would otherwise shrink activations to ~1e-3 and every
+    # pixel would be a near-tie) and the aliased convK.* entries copy encoder.* (the same Parameter upstream).
+    tag = "ternaus16_64x96"
+    m = ref.ternaus.TernausNet16(num_classes=N, num_filters=64, pretrained=False)
+    sk = {"__all_4d__": 1.4142135, "__alias__": "ternaus"}
+    man = _load_sd(m, seed=6, scale_keys=sk)
+    x = synth.frames(tag, 1, 64, 96, seed=6)
+    _save(tag, man, {"kind": "ternaus16", "B": 1, "H": 64, "W": 96, "seed": 6, "classes": N, "scale_keys": sk},
+          logp=m(_t(x)).numpy())
+
+    tag = "mfcnet_ternaus16_basic_k3_64x96"
+    m = ref.multiframe.TernausNetMultiBasic(num_classes=N, num_frames=3, pretrained=False, loadpath=None, optflow_inputs=True,
+                                            depth_inputs=True)
+    sk = {"__all_4d__": 1.4142135, "__alias__": "ternaus"}
+    man = _load_sd(m, seed=7, scale_keys=sk)
+    K, B, H, W = 3, 1, 64, 96
+    xs = [synth.frames(f"{tag}/{i}", B, H, W, 7) for i in range(K)]
+    fl = [synth.flow(f"{tag}/{i}", B, H, W, 7) for i in range(K - 1)]
+    dp = [synth.depth(f"{tag}/{i}", B, H, W, 7) for i in range(K)]
+    out = m([_t(a) for a in xs], optflow=[_t(a) for a in fl], depth=[_t(a) for a in dp])
+    _save(tag, man, {"kind": "mfcnet", "base": "ternaus16", "variant": "basic", "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 7,
+                     "scale_keys": sk}, out=out.numpy())
 
     # ---- the 576x720 grid buffer itself
     g = ref.multiframe.MultiFrameNetBasic(N, 3, False, True, True).grid.numpy()

@@ -86,6 +86,33 @@ def fill_state_dict(manifest, seed=0):
     return out
 
 
+_TERNAUS_ALIAS = {16: [[0, 2], [5, 7], [10, 12, 14], [17, 19, 21], [24, 26, 28]], 11: [[0], [3], [6, 8], [11, 13], [16, 18]]}
+
+
+def apply_fixture_rules(sd, rules):
+    """Post-processing of a generated state dict, recorded in a fixture's meta["scale_keys"]:
+      {key: factor}            scale one tensor
+      {"__all_4d__": factor}   scale every 4-D (conv / transposed-conv) weight
+      {"__alias__": "ternaus"} TernausNet registers the VGG convs twice (encoder.N and convK.M are the SAME
+                               Parameter, models/ternausnet.py:63-67,114-118): copy encoder.N over convK.M"""
+    for k, f in (rules or {}).items():
+        if k == "__all_4d__":
+            for name, v in sd.items():
+                if v.ndim == 4:
+                    sd[name] = (v * np.float32(f)).astype(np.float32)
+        elif k == "__alias__":
+            prefixes = sorted({name[: name.index("encoder.")] for name in sd if "encoder." in name})
+            for pre in prefixes:
+                depth = 16 if pre + "encoder.28.weight" in sd else 11
+                for si, idxs in enumerate(_TERNAUS_ALIAS[depth]):
+                    for pos, j in enumerate(idxs):
+                        for leaf in ("weight", "bias"):
+                            sd["%sconv%d.%d.%s" % (pre, si + 1, 2 * pos, leaf)] = sd["%sencoder.%d.%s" % (pre, j, leaf)]
+        else:
+            sd[k] = (sd[k] * np.float32(f)).astype(np.float32)
+    return sd
+
+
 def mesh_grid_576x720():
     """`MultiFrameNetBasic._create_mesh_grid` (models/multiframe_model.py:172-185):
     x,y in [-1,1] for a fixed 576x720 image, stacked (x, y), float32.

@@ -280,3 +280,45 @@ def hrnet_forward(sd, x, prefix=""):
     y = F.relu(_bn_eval(sd, "last_layer.1.", F.conv2d(cat, sd["last_layer.0.weight"], sd["last_layer.0.bias"])))
     y = F.conv2d(y, sd["last_layer.3.weight"], sd["last_layer.3.bias"])
     return F.interpolate(y, size=(size[0] * 4, size[1] * 4), mode="bilinear", align_corners=False)
+
+
+# ----------------------------------------------------------------------------
+# TernausNet11 / TernausNet16  (models/ternausnet.py:45-149)
+# ----------------------------------------------------------------------------
+_TERNAUS_STAGES = {11: [[0], [3], [6, 8], [11, 13], [16, 18]],
+                   16: [[0, 2], [5, 7], [10, 12, 14], [17, 19, 21], [24, 26, 28]]}
+
+
+def _decoder_block(sd, p, x):
+    """DecoderBlock (models/ternausnet.py:25-43): ConvRelu -> ConvTranspose2d(4, 2, 1) -> ReLU."""
+    x = F.relu(F.conv2d(x, sd[p + "block.0.conv.weight"], sd[p + "block.0.conv.bias"], padding=1))
+    return F.relu(F.conv_transpose2d(x, sd[p + "block.1.weight"], sd[p + "block.1.bias"], stride=2, padding=1))
+
+
+def ternaus_forward(sd, x, prefix=""):
+    """TernausNet{11,16}.forward (models/ternausnet.py:77-95, 127-148): log_softmax output when num_classes > 1.
+    The depth is read off the state dict (vgg16 has encoder.28)."""
+    if prefix:
+        sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    depth = 16 if "encoder.28.weight" in sd else 11
+    feats = []
+    for i, idxs in enumerate(_TERNAUS_STAGES[depth]):
+        if i > 0:
+            x = F.max_pool2d(x, 2, 2)
+        for j in idxs:
+            x = F.relu(F.conv2d(x, sd["encoder.%d.weight" % j], sd["encoder.%d.bias" % j], padding=1))
+        feats.append(x)
+    c1, c2, c3, c4, c5 = feats
+    d = _decoder_block(sd, "center.", F.max_pool2d(c5, 2, 2))
+    d = _decoder_block(sd, "dec5.", torch.cat([d, c5], 1))
+    d = _decoder_block(sd, "dec4.", torch.cat([d, c4], 1))
+    d = _decoder_block(sd, "dec3.", torch.cat([d, c3], 1))
+    d = _decoder_block(sd, "dec2.", torch.cat([d, c2], 1))
+    d = F.relu(F.conv2d(torch.cat([d, c1], 1), sd["dec1.conv.weight"], sd["dec1.conv.bias"], padding=1))
+    y = F.conv2d(d, sd["final.weight"], sd["final.bias"])
+    return F.log_softmax(y, dim=1) if y.shape[1] > 1 else y
+
+
+def ternaus_probs(sd, x, prefix=""):
+    """What TernausNetMulti* feed to the fusion head: base_model(x).exp() (models/multiframe_model.py:227,260)."""
+    return ternaus_forward(sd, x, prefix).exp()

@@ -21,9 +21,7 @@ def load(tag):
 
 def state_dict(man, seed, device="cpu", scale_keys=None):
     """scale_keys: the fixture's meta["scale_keys"] (see oracle/make_golden.py::_load_sd)."""
-    sd = synth.fill_state_dict(man, seed)
-    for k, f in (scale_keys or {}).items():
-        sd[k] = (sd[k] * np.float32(f)).astype(np.float32)
+    sd = synth.apply_fixture_rules(synth.fill_state_dict(man, seed), scale_keys)
     return {k: torch.from_numpy(v).to(device) for k, v in sd.items()}
 
 

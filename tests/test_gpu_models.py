@@ -149,6 +149,34 @@ def test_mfcnet_hrnet_matches_reference(M):
     assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE_SMALL, (err, agree)
 
 
+def test_ternaus16_matches_reference(M):
+    """TernausNet16: VGG convs, max-pools, the k4 s2 transposed convs as four parity convs, log_softmax head."""
+    tag = "ternaus16_64x96"
+    meta, man, arr = G.load(tag)
+    net = M.TernausNet16(num_classes=meta["classes"], num_filters=64)
+    net.load_state_dict(G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"]), strict=True)
+    net = net.cuda().eval()
+    x = torch.from_numpy(synth.frames(tag, meta["B"], meta["H"], meta["W"], meta["seed"])).cuda()
+    with torch.no_grad():
+        y = net(x)
+    err, agree = _cmp("ternaus/" + tag, y, arr["logp"], "fp16")
+    assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE_SMALL, (err, agree)
+
+
+def test_mfcnet_ternaus_matches_reference(M):
+    tag = "mfcnet_ternaus16_basic_k3_64x96"
+    meta, man, arr = G.load(tag)
+    net = M.TernausNetMultiBasic(num_classes=meta["N"], num_frames=meta["K"], pretrained=False, loadpath=None, optflow_inputs=True,
+                                 depth_inputs=True)
+    net.load_state_dict(G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"]), strict=True)
+    net = net.cuda().eval()
+    xs, fl, dp = G.mfcnet_inputs(tag, meta)
+    with torch.no_grad():
+        y = net([t.cuda() for t in xs], optflow=[t.cuda() for t in fl], depth=[t.cuda() for t in dp])
+    err, agree = _cmp("mfcnet/" + tag, y, arr["out"], "fp16")
+    assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE_SMALL, (err, agree)
+
+
 def test_mfcnet_full_size_vs_oracle_on_gpu(M):
     """BASELINE config 2 shape (480x640, K=3, flow+depth) at B=1 against the torch oracle run in
     fp32 on the same GPU (stock torch ops as the checker, not the product)."""

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     assert sorted(m.abi.EXPORTS) == names          # the ctypes binding covers the whole header
     lib.mfc_abi_version.restype = C.c_int
-    assert lib.mfc_abi_version() == 2
+    assert lib.mfc_abi_version() == 3
 
 
 def test_struct_sizes_match_header():
@@ -50,6 +50,7 @@ def test_struct_sizes_match_header():
     if gcc is None:
         pytest.skip("gcc not available")
     names = ["MfcGather", "MfcConvInfo", "MfcSrc", "MfcConvDesc", "MfcConvIO", "MfcWarpArgs", "MfcGnArgs", "MfcAddArgs",
+             "MfcFuseTerm", "MfcFuseArgs", "MfcResizeArgs", "MfcPoolArgs", "MfcHeatmapArgs",
              "MfcGatherArgs", "MfcCmd"]
     prog = '#include <stdio.h>\n#include "mfcnet_b200.h"\nint main(){' + "".join(
         'printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in names) + "return 0;}"
@@ -134,6 +135,27 @@ def test_hrnet_state_dict_keys_and_plan(M):
 def test_hrnet_multi_wrapper_keys(M):
     meta, man, _ = G.load("mfcnet_hrnet_large_k3_64x96")
     net = M.HRNetMultiLarge(num_classes=5, num_frames=3, pretrained=False, loadpath=None, optflow_inputs=True, depth_inputs=True).eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    xs = [torch.zeros(1, 3, 64, 96)] * 3
+    y = net(xs, optflow=[torch.zeros(1, 2, 64, 96)] * 2, depth=[torch.zeros(1, 1, 64, 96)] * 3)
+    assert y.shape == (1, 5, 64, 96)
+
+
+def test_ternaus16_state_dict_keys_and_plan(M):
+    meta, man, _ = G.load("ternaus16_64x96")
+    net = M.TernausNet16(num_classes=meta["classes"], num_filters=64).eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    net.load_state_dict(G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"]), strict=True)
+    y = net(torch.zeros(1, 3, 64, 96))
+    assert y.shape == (1, meta["classes"], 64, 96)
+    kinds = [m["kind"] for m in net._plans[(1, 64, 96)][0].meta]
+    # 13 VGG convs + 5 decoder ConvRelu + 5 x 4 parity convs of the transposed convs + dec1 + final; 5 pools
+    assert kinds.count("conv") == 13 + 5 + 20 + 1 + 1 and kinds.count("maxpool2") == 5 and kinds.count("heatmap_head") == 1
+
+
+def test_ternaus_multi_wrapper_keys(M):
+    meta, man, _ = G.load("mfcnet_ternaus16_basic_k3_64x96")
+    net = M.TernausNetMultiBasic(num_classes=5, num_frames=3, pretrained=False, loadpath=None, optflow_inputs=True, depth_inputs=True).eval()
     assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
     xs = [torch.zeros(1, 3, 64, 96)] * 3
     y = net(xs, optflow=[torch.zeros(1, 2, 64, 96)] * 2, depth=[torch.zeros(1, 1, 64, 96)] * 3)

@@ -71,6 +71,27 @@ def test_mfcnet_hrnet_matches_reference_output():
     assert np.abs(y.numpy() - arr["out"]).max() < TOL * max(1.0, float(np.abs(arr["out"]).max()))
 
 
+def test_ternaus16_matches_reference_output():
+    """TernausNet16 (VGG16 encoder, ConvTranspose2d(4,2,1) decoder, log_softmax head) vs models/ternausnet.py."""
+    tag = "ternaus16_64x96"
+    meta, man, arr = G.load(tag)
+    sd = G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"])
+    x = torch.from_numpy(synth.frames(tag, meta["B"], meta["H"], meta["W"], meta["seed"]))
+    with torch.no_grad():
+        y = TO.ternaus_forward(sd, x)
+    assert np.abs(y.numpy() - arr["logp"]).max() < TOL * max(1.0, float(np.abs(arr["logp"]).max()))
+
+
+def test_mfcnet_ternaus_matches_reference_output():
+    tag = "mfcnet_ternaus16_basic_k3_64x96"
+    meta, man, arr = G.load(tag)
+    sd = G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"])
+    xs, fl, dp = G.mfcnet_inputs(tag, meta)
+    with torch.no_grad():
+        y = TO.mfcnet_forward(sd, xs, fl, dp, base=TO.ternaus_probs, variant="basic", N=meta["N"])
+    assert np.abs(y.numpy() - arr["out"]).max() < TOL * max(1.0, float(np.abs(arr["out"]).max()))
+
+
 def test_synth_is_stable():
     """Known-answer check of the platform-independent generator itself."""
     a = synth.normal("kat", (4,), seed=5)
