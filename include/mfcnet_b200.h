@@ -263,6 +263,19 @@ int mfc_heatmap_head(const float* logits, int B, int N, long long pixels,
 int mfc_argmax_u8(const float* x, int B, int N, long long pixels, uint8_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Training loss, forward (src/engine.py:65-66, src/loss.py:6-63): log_softmax of the model output,
+ * weighted NLL (nn.NLLLoss(weight=class_weights), mean reduction) and the soft-Jaccard term over the
+ * foreground classes; total = w_nll*nll + w_jaccard*jaccard.  logits: fp32 [B][N][pixels], N <= 16;
+ * target: int64 [B][pixels] in [0,N); class_weights: [N] or NULL.  workspace: fp64
+ * [mfc_segmentation_loss_workspace(B,pixels)] (bytes).  out: float[3] = {total, nll, jaccard} (device).
+ * Deterministic (fixed-order two-level reduction).
+ * ---------------------------------------------------------------------------------- */
+long long mfc_segmentation_loss_workspace(int B, int N, long long pixels);
+int mfc_segmentation_loss(const float* logits, const long long* target, const float* class_weights,
+                          int B, int N, long long pixels, float w_nll, float w_jaccard,
+                          void* workspace, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * UnFlow correlation cost volume (models/unflow_correlation.py:10-105,282-337).
  * first/second: fp32 NCHW contiguous; out: fp32 [B][D*D][H][W], D = 2*(max_disp/stride2)+1,
  * out[b,(iy*D+ix),y,x] = mean_c first[b,c,y,x]*second[b,c,y+dy,x+dx], zero outside.

@@ -5,6 +5,7 @@ from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
 from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxima_and_estimate_centroids, gaussian_blur,
                       heatmap_head, predicted_keypoints)
 from .hrnet import HighResolutionNet
+from .loss import segmentation_loss
 from .multiframe import (HRNetMultiBasic, HRNetMultiLarge, ResUNetMultiBasic, ResUNetMultiLarge, TernausNetMultiBasic,
                          TernausNetMultiLarge)
 from .resunet import ResUnet_VB
@@ -14,7 +15,7 @@ from .stream import HostPipeline, StreamingMFCNet, shard_frames
 __all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic", "HRNetMultiLarge", "TernausNet11", "TernausNet16", "TernausNetMultiBasic", "TernausNetMultiLarge", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
            "FunctionCorrelation", "ModuleCorrelation", "correlation", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
-           "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames"]
+           "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames", "segmentation_loss"]
 
 
 def get_tooltip_segmentation_model(args):

@@ -329,6 +329,21 @@ int mfc_bilinear_resize(const MfcResizeArgs* a, void* stream) {
              "bilinear_resize");
 }
 
+// ---- loss ----------------------------------------------------------------------------------------
+long long mfc_segmentation_loss_workspace(int B, int N, long long pixels) {
+  if (B < 1 || N < 2 || N > 16 || pixels < 1) return 0;
+  return (long long)mfc::loss_blocks(B, pixels) * (2 + 3 * (N - 1)) * (long long)sizeof(double);
+}
+
+int mfc_segmentation_loss(const float* logits, const long long* target, const float* class_weights, int B, int N, long long pixels,
+                          float w_nll, float w_jaccard, void* workspace, float* out, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!logits || !target || !workspace || !out || B < 1 || N < 2 || N > 16 || pixels < 1) return fail(MFC_EINVAL, "segmentation_loss: bad argument");
+  MFC_LAUNCH(mfc::launch_segmentation_loss(logits, target, class_weights, B, N, pixels, w_nll, w_jaccard, (double*)workspace, out,
+                                           (cudaStream_t)stream),
+             "segmentation_loss");
+}
+
 // ---- correlation -------------------------------------------------------------------------------
 int mfc_correlation_fwd(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp, int stride2,
                         int exact_order, void* stream) {

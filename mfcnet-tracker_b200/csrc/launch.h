@@ -38,6 +38,11 @@ cudaError_t launch_fuse_sum(const MfcFuseArgs& a, cudaStream_t st);
 cudaError_t launch_bilinear_resize(const float* src, int B, int C, int Hin, int Win, int Hout, int Wout, float* dst_nchw,
                                    void* dst_c8, long long c8_bs, bool bf16, cudaStream_t st);
 
+// loss.cu
+int loss_blocks(int B, long long pixels);
+cudaError_t launch_segmentation_loss(const float* logits, const long long* target, const float* cw, int B, int N, long long pixels,
+                                     float w_nll, float w_jacc, double* partials, float* out, cudaStream_t st);
+
 // correlation.cu
 cudaError_t launch_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp,
                                int stride2, int exact_order, cudaStream_t st);

@@ -134,6 +134,21 @@ def main():
     _save(tag, man, {"kind": "mfcnet", "base": "ternaus16", "variant": "basic", "K": K, "N": N, "B": B, "H": H, "W": W, "seed": 7,
                      "scale_keys": sk}, out=out.numpy())
 
+    # ---- training loss forward: the reference's own get_loss (src/loss.py) on seeded cases
+    class LA:
+        num_classes = N
+        class_weights = np.array([1.0, 1000.0, 1000.0, 1000.0, 1000.0])
+    lres = {}
+    for tag, (B, H, W, fg) in {"small": (2, 48, 64, 0.05), "sparse": (1, 96, 128, 0.01), "dense": (2, 32, 32, 0.6)}.items():
+        o, t = synth.loss_case(tag, B, N, H, W, seed=8, fg=fg)
+        logp = torch.nn.functional.log_softmax(_t(o), dim=1)               # src/engine.py:65
+        total, d = ref.loss.get_loss(logp, _t(t), ["nll", "soft_jaccard"], [0.7, 0.3], LA)
+        lres[tag] = {"B": B, "H": H, "W": W, "fg": fg, "seed": 8, "total": float(total), "nll": d["loss_nll"],
+                     "soft_jaccard": d["loss_soft_jaccard"]}
+    with open(os.path.join(OUT, "loss_cases.json"), "w") as f:
+        json.dump({"class_weights": [1.0, 1000.0, 1000.0, 1000.0, 1000.0], "loss_wts": [0.7, 0.3], "N": N, "cases": lres}, f, indent=1)
+    print("wrote loss_cases", lres)
+
     # ---- the 576x720 grid buffer itself
     g = ref.multiframe.MultiFrameNetBasic(N, 3, False, True, True).grid.numpy()
     assert np.array_equal(g, synth.mesh_grid_576x720()), "synth grid != reference grid"

@@ -35,6 +35,7 @@ def load():
     ns.multiframe = importlib.import_module("models.multiframe_model")
     ns.hrnet = importlib.import_module("models.hrnet")
     ns.ternaus = importlib.import_module("models.ternausnet")
+    ns.loss = importlib.import_module("src.loss")
     loc = importlib.import_module("utils.localization_utils_v2")
     ns.localization = loc
     return ns

@@ -136,3 +136,14 @@ def depth(tag, B, H, W, seed=0):
 
 def flow(tag, B, H, W, seed=0, scale=4.0):
     return normal("flow/" + tag, (B, 2, H, W), seed, std=scale)
+
+
+def loss_case(tag, B, N, H, W, seed=0, fg=0.05):
+    """Model output (B,N,H,W) ~ 2*N(0,1) and an int64 target map with ~`fg` foreground pixels spread over the
+    N-1 tool classes (SURVEY.md section 8d, config 5 inputs)."""
+    out = normal("loss/out/" + tag, (B, N, H, W), seed, std=2.0)
+    u = uniform("loss/tgt/" + tag, (B, H, W), seed)
+    t = np.zeros((B, H, W), dtype=np.int64)
+    for c in range(1, N):
+        t[(u >= (c - 1) * fg / (N - 1)) & (u < c * fg / (N - 1))] = c
+    return out, t

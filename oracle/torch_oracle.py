@@ -322,3 +322,24 @@ def ternaus_forward(sd, x, prefix=""):
 def ternaus_probs(sd, x, prefix=""):
     """What TernausNetMulti* feed to the fusion head: base_model(x).exp() (models/multiframe_model.py:227,260)."""
     return ternaus_forward(sd, x, prefix).exp()
+
+
+# ----------------------------------------------------------------------------
+# Training loss, forward  (src/loss.py:6-63, src/engine.py:65-66)
+# ----------------------------------------------------------------------------
+def segmentation_loss(output, targets, class_weights=None, w_nll=0.7, w_jaccard=0.3):
+    """total = w_nll * NLLLoss(weight)(log_softmax(output), t) + w_jaccard * LossSoftJaccard (src/loss.py:31-63).
+    Returns (total, nll, jaccard) as python floats, accumulated in float64."""
+    logp = F.log_softmax(output.double(), dim=1)
+    N = output.shape[1]
+    w = torch.ones(N, dtype=torch.float64) if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float64)
+    nll = F.nll_loss(logp, targets, weight=w)
+    jac = 0.0
+    for c in range(1, N):
+        tgt = (targets == c).double()
+        p = logp[:, c].exp()
+        inter = (p * tgt).sum()
+        union = p.sum() + tgt.sum() - inter
+        jac = jac - torch.log((inter + 1e-15) / (union + 1e-15))
+    jac = jac / N
+    return float(w_nll * nll + w_jaccard * jac), float(nll), float(jac)

@@ -132,3 +132,63 @@ def test_keypoints_bit_exact_on_identical_heatmaps(M):
         got = M.predicted_keypoints(torch.from_numpy(p).cuda())
         want = LO.predicted_keypoints(p)
         assert str(got) == str(want), seed
+
+
+# ---------------------------------------------------------------- training loss (forward)
+def test_segmentation_loss_matches_reference(M):
+    """mfc_segmentation_loss vs the reference's get_loss values (golden) and the fp64 oracle; the fp32 per-thread
+    partial sums give ~1e-6 relative error, asserted at 2e-5."""
+    from oracle import torch_oracle as TO
+    with open(os.path.join(ROOT, "tests", "golden", "loss_cases.json")) as f:
+        j = json.load(f)
+    for tag, c in j["cases"].items():
+        o, t = synth.loss_case(tag, c["B"], j["N"], c["H"], c["W"], seed=c["seed"], fg=c["fg"])
+        total, d = M.segmentation_loss(torch.from_numpy(o).cuda(), torch.from_numpy(t).cuda(), j["class_weights"],
+                                       ("nll", "soft_jaccard"), j["loss_wts"])
+        want = TO.segmentation_loss(torch.from_numpy(o), torch.from_numpy(t), j["class_weights"], *j["loss_wts"])
+        for got, ref_v, orc in ((d["loss_total"], c["total"], want[0]), (d["loss_nll"], c["nll"], want[1]),
+                                (d["loss_soft_jaccard"], c["soft_jaccard"], want[2])):
+            assert abs(got - ref_v) <= 2e-5 * abs(ref_v), (tag, got, ref_v)
+            assert abs(got - orc) <= 2e-5 * abs(orc), (tag, got, orc)
+        total2, _ = M.segmentation_loss(torch.from_numpy(o).cuda(), torch.from_numpy(t).cuda(), j["class_weights"])
+        assert float(total2) == float(total)          # deterministic reduction
+    with pytest.raises(ValueError):
+        M.segmentation_loss(torch.zeros(1, 5, 8, 8, device="cuda"), torch.zeros(1, 8, 8, dtype=torch.int64, device="cuda"),
+                            loss_fns=("mse",), loss_wts=(1.0,))
+
+
+def test_resample_kernels_match_torch(M):
+    """fuse_sum (bilinear align_corners=False upsampling on read) and bilinear_resize vs F.interpolate."""
+    import torch.nn.functional as F
+    from mfcnet_tracker_b200 import engine
+    from mfcnet_tracker_b200.engine import Act
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    B, Cc, H, W = 2, 24, 24, 40
+    prog = engine.Program(dev, "fp16")
+
+    def c8(x):
+        return x.view(B, Cc // 8, 8, x.shape[2], x.shape[3]).permute(0, 1, 3, 4, 2).contiguous().half()
+    xs = [torch.randn(B, Cc, H >> k, W >> k, generator=g).to(dev) for k in range(4)]
+    out = torch.empty(B, Cc // 8, H, W, 8, dtype=torch.float16, device=dev)
+    sc = (1.0 + 0.1 * torch.randn(Cc, generator=g)).to(dev)
+    sh = (0.1 * torch.randn(Cc, generator=g)).to(dev)
+    prog.fuse_sum([Act(c8(x), Cc) for x in xs], out, Cc, scale=sc, shift=sh, act=1)
+    low = torch.randn(B, 5, 12, 20, generator=g).to(dev)
+    up = torch.empty(B, 5, 48, 80, device=dev)
+    up8 = torch.zeros(B, 1, 48, 80, 8, dtype=torch.float16, device=dev)
+    prog.resize(low, 48, 80, dst_nchw=up, dst_c8=up8)
+    pooled = torch.empty(B, Cc // 8, H // 2, W // 2, 8, dtype=torch.float16, device=dev)
+    prog.maxpool2(Act(c8(xs[0]), Cc), pooled)
+    prog.run()
+    torch.cuda.synchronize()
+    ref = sum(F.interpolate(x.half().float(), size=(H, W), mode="bilinear", align_corners=False) if x.shape[2] != H else x.half().float()
+              for x in xs)
+    ref = F.relu(ref * sc[None, :, None, None] + sh[None, :, None, None])
+    got = out.float().permute(0, 1, 4, 2, 3).reshape(B, Cc, H, W)
+    assert (got - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())      # fp16 output rounding
+    ref_up = F.interpolate(low, size=(48, 80), mode="bilinear", align_corners=False)
+    assert (up - ref_up).abs().max().item() <= 1e-6
+    assert (up8.float()[..., :5].permute(0, 1, 4, 2, 3).reshape(B, 5, 48, 80) - ref_up).abs().max().item() <= 2e-3 * ref_up.abs().max().item()
+    ref_pool = F.max_pool2d(xs[0].half().float(), 2, 2)
+    assert torch.equal(pooled.float().permute(0, 1, 4, 2, 3).reshape(B, Cc, H // 2, W // 2), ref_pool)   # bit-exact

@@ -92,6 +92,19 @@ def test_mfcnet_ternaus_matches_reference_output():
     assert np.abs(y.numpy() - arr["out"]).max() < TOL * max(1.0, float(np.abs(arr["out"]).max()))
 
 
+def test_loss_matches_reference_get_loss():
+    """oracle segmentation_loss vs the reference's own get_loss outputs (tests/golden/loss_cases.json)."""
+    import json, os
+    with open(os.path.join(G.GOLDEN, "loss_cases.json")) as f:
+        j = json.load(f)
+    for tag, c in j["cases"].items():
+        o, t = synth.loss_case(tag, c["B"], j["N"], c["H"], c["W"], seed=c["seed"], fg=c["fg"])
+        total, nll, jac = TO.segmentation_loss(torch.from_numpy(o), torch.from_numpy(t), j["class_weights"], *j["loss_wts"])
+        # the reference accumulates in fp32, the oracle in fp64: 1e-5 relative
+        assert abs(total - c["total"]) <= 1e-5 * abs(c["total"]), (tag, total, c["total"])
+        assert abs(nll - c["nll"]) <= 1e-5 * abs(c["nll"]) and abs(jac - c["soft_jaccard"]) <= 1e-5 * abs(c["soft_jaccard"])
+
+
 def test_synth_is_stable():
     """Known-answer check of the platform-independent generator itself."""
     a = synth.normal("kat", (4,), seed=5)
