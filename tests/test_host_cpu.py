@@ -25,7 +25,7 @@ def M(monkeypatch):
 def _declared():
     with open(os.path.join(ROOT, "include", "mfcnet_b200.h")) as f:
         src = f.read()
-    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(mfc_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|long long|const char\*)\s+(mfc_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_library_exports_every_declared_symbol():
