@@ -305,7 +305,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
 template <bool BF16, int MODE, bool NB16>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem_acc, uint32_t s_scale_addr, float* my_stats,
                                               float (&d1)[16], float (&d2)[16], const float (&sc)[16], const float (&sh)[16], int b,
-                                              int oy0, int ox0, int nbk, int lq, int half, int lane) {
+                                              int oy0, int ox0, int nbk, int lq, int half, int lane, bool res_aff_smem) {
   constexpr bool kRes = MODE == EPI_RES || MODE == EPI_GENERIC;
   constexpr bool kStats = MODE == EPI_STATS || MODE == EPI_GENERIC;
   constexpr bool kNchw = MODE == EPI_NCHW || MODE == EPI_GENERIC;
@@ -363,7 +363,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
       for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
     }
     float f[16];
-    if constexpr (NB16) {
+    // with the 32 GroupNorm accumulators live (STATS) the scale/shift registers would push the loop over the
+    // register budget: read them from smem there (8 broadcast LDS.128 per step)
+    if constexpr (NB16 && MODE != EPI_STATS && MODE != EPI_GENERIC) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(acc[i]), sc[i], sh[i]);
     } else {
@@ -386,11 +388,23 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
           float rf[8];
           unpack8<BF16>(rv[h], rf);
           if (p.res_aff) {
-            const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
+            if (res_aff_smem) {
+              // (s/2, t/2) of this sample's channels parked in the warp's smem slot: silu(y) = h + h*tanh(h), h = y/2
+              const uint32_t sa = smem_u32(my_stats) + (uint32_t)(co0 + h * 8) * 8u;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float2 a = __ldg(ra + i);
-              rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
+              for (int i = 0; i < 8; i += 2) {
+                const float4 a = lds_f4(sa + i * 8);
+                const float h0 = fmaf(rf[i], a.x, a.y), h1 = fmaf(rf[i + 1], a.z, a.w);
+                rf[i] = fmaf(h0, tanh_fast(h0), h0);
+                rf[i + 1] = fmaf(h1, tanh_fast(h1), h1);
+              }
+            } else {
+              const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float2 a = __ldg(ra + i);
+                rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
+              }
             }
           }
 #pragma unroll
@@ -719,7 +733,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       for (int bb = 0; bb < p.B; ++bb)
         for (int i = warp * 32 + lane; i < cpad * 2; i += kEpiWarps * 32) my_rec[(size_t)bb * img_stride + i] = 0.0f;
     }
-    int cur_b = -1;
+    int cur_b = -1, aff_b = -1;
+    const bool res_aff_smem = (MODE == EPI_RES || MODE == EPI_GENERIC) && p.res != nullptr && p.res_aff != nullptr && !has_stats && cpad <= 256;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
       const ItemCoord c = decode_item(p, w);
       if (has_stats && c.b != cur_b) {
@@ -730,9 +745,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       const uint32_t use = p.t.nacc == 2 ? (uint32_t)(item >> 1) : (uint32_t)item;
       mbar_wait(&bar_tfull[acc_i], use & 1u);
       tc_fence_after();
+      if (res_aff_smem && c.b != aff_b) {  // park (s/2, t/2) of this sample's residual affine in the warp's smem slot
+        aff_b = c.b;
+        const int nch = ((p.Cout + 7) >> 3) << 3;
+        __syncwarp();
+        for (int i = lane; i < nch; i += 32) {
+          const float2 a = __ldg(reinterpret_cast<const float2*>(p.res_aff) + (size_t)c.b * nch + i);
+          my_stats[i * 2] = 0.5f * a.x;
+          my_stats[i * 2 + 1] = 0.5f * a.y;
+        }
+        __syncwarp();
+      }
       if (!(p.debug & 2))
         epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
-                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane);
+                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc_i]);
