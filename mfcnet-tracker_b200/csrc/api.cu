@@ -122,6 +122,45 @@ int get_tiling(const MfcConvDesc* d, mfc::ConvTiling* out) {
   return MFC_OK;
 }
 
+// ---- TMA descriptors ---------------------------------------------------------------------------
+// cuTensorMapEncodeTiled lives in libcuda; it is resolved through the runtime (no link-time dependency on the
+// driver library, so the .so still loads -- and plans -- on a box without a GPU).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// Source i of a stride-1 conv as the 5-D tensor (8 channels = one 16-byte pixel slot, W, H, chunk, sample); the box is
+// one halo tile of one 8-channel plane: P x rows_sub slots, dense in shared memory = the tcgen05 operand layout.
+int encode_source_maps(const MfcConvDesc* d, mfc::ConvParams* p) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(MFC_ECUDA, "conv: cuTensorMapEncodeTiled is not available from this driver");
+  for (int i = 0; i < d->nsrc; ++i) {
+    const cuuint64_t plane = (cuuint64_t)d->Hin * d->Win * 16;
+    cuuint64_t dims[5] = {8, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->src[i].nchunks, (cuuint64_t)d->B};
+    cuuint64_t strides[4] = {16, (cuuint64_t)d->Win * 16, plane,
+                             d->B > 1 ? (cuuint64_t)d->src[i].batch_stride : plane * (cuuint64_t)d->src[i].nchunks};
+    cuuint32_t box[5] = {8, (cuuint32_t)p->t.P, (cuuint32_t)p->t.rows_sub, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&p->tmap[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(d->src[i].ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(MFC_ECUDA, "conv: cuTensorMapEncodeTiled failed for source %d (CUresult %d; %dx%d, %d chunks, box %dx%d)", i, (int)r,
+                  d->Hin, d->Win, d->src[i].nchunks, p->t.P, p->t.rows_sub);
+  }
+  return MFC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -250,6 +289,10 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
   {
     static const int dbg = getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0;
     p.debug = dbg;
+  }
+  if (p.t.tma) {
+    rc = encode_source_maps(d, &p);
+    if (rc != MFC_OK) return rc;
   }
   if (p.stats && p.t.NB * p.t.nblk > 256) return fail(MFC_EINVAL, "conv: GroupNorm statistics need Cout <= 256");
   if (((uintptr_t)p.w & 15) || ((uintptr_t)p.y & 15) || ((uintptr_t)p.res & 15) || (p.y_bs & 15) || (p.res_bs & 15))

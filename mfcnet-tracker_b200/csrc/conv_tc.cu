@@ -120,19 +120,38 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
     sh[i] = 0.5f * a.y;
   }
   if (s == 1 && p.upsample == 1) {
-    TileWalk w = tile_walk<NT>(p, tid);
+    // Four slots per iteration: all four LDS.128 are issued before the first value is needed and the stores come
+    // last, so one thread keeps four independent load -> FMA -> MUFU -> FMA -> pack chains in flight (the six
+    // producer warps alone cannot hide those latencies by multithreading).
     const uint32_t H = (uint32_t)p.Hin, W = (uint32_t)p.Win;
-    uint32_t dst = smem_u32(plane) + (uint32_t)tid * 16u;
-#pragma unroll 2
-    for (int idx = tid; idx < items; idx += NT) {
-      if ((uint32_t)(iy_base + w.r) < H && (uint32_t)(ix_base + w.c) < W) affine_silu_slot<BF16>(dst, sc, sh);  // padding stays zero
-      dst += NT * 16u;
-      w.r += w.step_r;
-      w.c += w.step_c;
-      if (w.c >= P) {
-        w.c -= P;
-        ++w.r;
+    const uint32_t base = smem_u32(plane);
+    constexpr int U = 4;
+    for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
+      uint4 v[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = idx0 + u * NT;
+        const int r = (int)fdiv((uint32_t)idx, p.divP);
+        const int c = idx - r * P;
+        ok[u] = idx < items && (uint32_t)(iy_base + r) < H && (uint32_t)(ix_base + c) < W;  // padding stays zero
+        if (ok[u]) v[u] = lds16_u32(base + (uint32_t)idx * 16u);
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float f[8];
+        unpack8<BF16>(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = fmaf(f[i], sc[i], sh[i]);
+          f[i] = fmaf(h, tanh_fast(h), h);
+        }
+        v[u] = pack8<BF16>(f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) sts16_u32(base + (uint32_t)(idx0 + u * NT) * 16u, v[u]);
     }
     return;
   }
@@ -195,6 +214,34 @@ __device__ __forceinline__ void issue_stage(const ConvParams& p, uint8_t* abuf, 
       continue;
     }
     issue_plane<NT>(p, plane, locate_plane(p, b, k).src, iy_base, ix_base, tid);
+  }
+}
+
+// TMA variant of phase 1, executed by ONE thread: one box load per 8-channel plane (the part of the box outside
+// the image arrives as zeros = the conv padding), the streamed weights as one flat bulk copy; everything
+// completes on `bar` by byte count.
+__device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* abuf, uint64_t* bar, int b, int nbk, int ks, int iy_base,
+                                                int ix_base) {
+  const int ksteps_per_stage = p.t.CBc / 2;
+  const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
+  const int nplanes = p.t.pair ? 1 : 2 * nks;
+  const uint32_t box_bytes = (uint32_t)(p.t.rows_sub * p.t.P) * 16u;
+  const uint32_t w_bytes = p.t.b_resident ? 0u : (uint32_t)(nks * p.t.entries * 2 * p.t.NB) * 16u;
+  mbar_arrive_expect_tx(bar, (uint32_t)nplanes * box_bytes + w_bytes);
+  if (w_bytes) {
+    const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * p.t.entries * (size_t)(2 * p.t.NB * 16);
+    bulk_load(abuf + p.t.a_stage_bytes, wsrc, w_bytes, bar);
+  }
+  for (int q = 0; q < nplanes; ++q) {
+    int k = ks * p.t.CBc + q, si = 0;
+    if (k >= p.t.cin_chunks) {  // odd plane count: the pad plane is a box one chunk past the last source (all zeros)
+      si = p.nsrc - 1;
+      k = p.src_end[si] - (si ? p.src_end[si - 1] : 0);
+    } else {
+      while (k >= p.src_end[si]) ++si;
+      k -= si ? p.src_end[si - 1] : 0;
+    }
+    tma_load_5d(abuf + (size_t)q * p.t.plane_bytes, &p.tmap[si], bar, 0, ix_base, iy_base, k, b);
   }
 }
 
@@ -500,6 +547,17 @@ __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_stats,
   epi_barrier();
 }
 
+// measurement only (MFC_CONV_DEBUG bit 3): cycles a role spends blocked on each of its barriers
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
+  if (!timed) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
 struct ItemCoord {
   int b, oy0, ox0, nbk, tile_lin;
 };
@@ -526,7 +584,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   uint64_t* bar_empty = bar_full + kMaxStages;                        // [kMaxStages] MMA (commit) -> producers
   uint64_t* bar_tfull = bar_empty + kMaxStages;                       // [2] MMA (commit) -> epilogue
   uint64_t* bar_tempty = bar_tfull + 2;                               // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_tma = bar_tempty + 2;                                 // [kMaxStages] TMA (complete_tx) -> producers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + kMaxStages);
   float* s_scale = reinterpret_cast<float*>(smem + p.t.off_scale);    // [NB*nblk]
   float* s_shift = s_scale + p.t.NB * p.t.nblk;
   float* s_stats = reinterpret_cast<float*>(smem + p.t.off_stats);    // [kEpiWarps][cpad][2] (cpad <= 256)
@@ -545,6 +604,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     for (int i = 0; i < p.t.nstages; ++i) {
       mbar_init(&bar_full[i], kProdWarps);
       mbar_init(&bar_empty[i], kMmaWarps);
+      mbar_init(&bar_tma[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], kMmaWarps);
@@ -585,6 +645,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // from here on the previous kernel's outputs (activations, GroupNorm affines) are read
   const long long t_setup = clock64();
+  const bool timed = (p.debug & 8) != 0;
+  long long wait_a = 0, wait_b = 0;  // per role: blocked on its input barrier / on its output (back-pressure) barrier
 
   if (warp >= kProdWarp0) {
     // =========================================================== producers
@@ -595,13 +657,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     int wi = blockIdx.x, ksi = 0, slot_i = 0;  // issue cursor
     uint32_t phase_i = 0;
     int wt = blockIdx.x, kst = 0, slot_t = 0;  // transform / hand-off cursor
+    const bool tma = p.t.tma != 0;
+    uint32_t phase_t = 0;
     auto issue_next = [&]() {
       if (wi < total_items) {
-        const ItemCoord c = decode_item(p, wi);
-        mbar_wait(&bar_empty[slot_i], phase_i ^ 1u);  // the MMAs that read this slot have drained
-        if (!(p.debug & 1))
-          issue_stage<kProdThreads>(p, stage0 + (size_t)slot_i * p.t.stage_bytes, c.b, c.nbk, ksi,
-                                    c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x, ptid);
+        if (!tma || ptid == 0 || (p.debug & 1)) {
+          const ItemCoord c = decode_item(p, wi);
+          mbar_wait_t(&bar_empty[slot_i], phase_i ^ 1u, timed, wait_b);  // the MMAs that read this slot have drained
+          uint8_t* abuf = stage0 + (size_t)slot_i * p.t.stage_bytes;
+          const int iy_base = c.oy0 * p.stride - p.pad + p.in_off_y, ix_base = c.ox0 * p.stride - p.pad + p.in_off_x;
+          if (!(p.debug & 1)) {
+            if (tma)
+              issue_stage_tma(p, abuf, &bar_tma[slot_i], c.b, c.nbk, ksi, iy_base, ix_base);
+            else
+              issue_stage<kProdThreads>(p, abuf, c.b, c.nbk, ksi, iy_base, ix_base, ptid);
+          }
+        }
         if (++ksi == p.t.kstages) {
           ksi = 0;
           wi += gridDim.x;
@@ -611,14 +682,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
           phase_i ^= 1u;
         }
       }
-      cp_async_commit();  // one group per pipeline step, empty or not: keeps wait_group(D) exact
+      if (!tma) cp_async_commit();  // one group per pipeline step, empty or not: keeps wait_group(D) exact
     };
     // Order matters: stage i is handed to the MMA warp BEFORE the copies of stage i+D are issued, because
     // that issue has to wait for the MMAs of stage i-1 to release their slot (D = nstages-1).
     for (int j = 0; j < D; ++j) issue_next();
     while (wt < total_items) {
       if (D == 0) issue_next();
-      cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // this thread's copies of the hand-off stage have landed
+      if (tma) {
+        if (!(p.debug & 1)) mbar_wait_t(&bar_tma[slot_t], phase_t, timed, wait_a);  // the box loads of the hand-off stage have landed
+      } else {
+        cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // this thread's copies of the hand-off stage have landed
+      }
       const ItemCoord c = decode_item(p, wt);
       if (!(p.debug & 1))
         transform_stage<BF16, kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, c.b, kst,
@@ -630,7 +705,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         kst = 0;
         wt += gridDim.x;
       }
-      if (++slot_t == p.t.nstages) slot_t = 0;
+      if (++slot_t == p.t.nstages) {
+        slot_t = 0;
+        phase_t ^= 1u;
+      }
       if (D > 0) issue_next();
     }
     cp_async_wait_group<0>();
@@ -649,12 +727,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
       const int acc_i = p.t.nacc == 2 ? (item & 1) : 0;
       const uint32_t use = p.t.nacc == 2 ? (uint32_t)(item >> 1) : (uint32_t)item;
-      mbar_wait(&bar_tempty[acc_i], (use & 1u) ^ 1u);  // the epilogue has drained this accumulator buffer
+      mbar_wait_t(&bar_tempty[acc_i], (use & 1u) ^ 1u, timed, wait_b);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)acc_i * p.t.acc_cols;
       int ecount = 0, aset = 0;
       for (int ks = 0; ks < p.t.kstages; ++ks) {
-        mbar_wait(&bar_full[stage], phase);
+        mbar_wait_t(&bar_full[stage], phase, timed, wait_a);
         tc_fence_after();
         if (elect_one_sync()) {
           const int kh_eff = (p.debug & 4) ? 0 : p.kh;
@@ -743,7 +821,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
       const int acc_i = p.t.nacc == 2 ? (item & 1) : 0;
       const uint32_t use = p.t.nacc == 2 ? (uint32_t)(item >> 1) : (uint32_t)item;
-      mbar_wait(&bar_tfull[acc_i], use & 1u);
+      mbar_wait_t(&bar_tfull[acc_i], use & 1u, timed, wait_a);
       tc_fence_after();
       if (res_aff_smem && c.b != aff_b) {  // park (s/2, t/2) of this sample's residual affine in the warp's smem slot
         aff_b = c.b;
@@ -768,8 +846,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
   // ---- teardown
   if ((p.debug & 8) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kMmaWarp0 || warp == kProdWarp0))
-    printf("mfc conv timing: warp %d role loop %lld cycles (items/cta %d)\n", warp, clock64() - t_setup,
-           (total_items + (int)gridDim.x - 1) / (int)gridDim.x);
+    printf("mfc conv timing: warp %d role loop %lld cycles, waiting for input %lld, for back-pressure %lld (items/cta %d)\n", warp,
+           clock64() - t_setup, wait_a, wait_b, (total_items + (int)gridDim.x - 1) / (int)gridDim.x);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -849,6 +927,9 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
   // tap pairing: with ONE 8-channel input plane (the RGB stem) half of every K=16 MMA would multiply zeros;
   // instead its second K half reads the same plane one pixel to the right = the next horizontal tap
   const bool pair = cin_chunks == 1 && s == 1 && d.upsample == 1 && d.kw > 1;
+  // stride-1, no-upsample convs stage their halo tiles with TMA box loads (one instruction per 8-channel plane,
+  // hardware zero fill outside the image); box extents are limited to 256 per dimension
+  const bool tma = s == 1 && d.upsample == 1;
   const int taps = pair ? d.kh * ((d.kw + 1) / 2) : d.kh * d.kw;  // MMA entries per K step
   const int ksteps = ceil_div(cin_chunks, 2);
   int nblk;
@@ -876,8 +957,9 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
       const uint32_t tmem = pow2_at_least((uint32_t)(nacc * R * NB * kacc), 32);
       const int rows_sub = TH + hy;
       const int slots_sub = std::max(R * 128 + hy * P + hx, rows_sub * P);
-      const uint32_t plane_bytes = (uint32_t)(s * s) * slots_sub * 16;
+      const uint32_t plane_bytes = ((uint32_t)(s * s) * slots_sub * 16 + 127u) & ~127u;  // TMA destinations: 128-byte aligned
       if (plane_bytes > 200000u) break;
+      if (tma && (P > 256 || rows_sub > 256)) continue;
       const int tiles_x = nx, tiles_y = ceil_div(d.Hout, TH);
       const long long items = (long long)d.B * tiles_x * tiles_y * nblk;
       // K staging options: all channels in one stage, or 16/32/64/128-channel stages
@@ -905,7 +987,10 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
         //              dependent accumulate chain costs 167 per MMA divided by the accumulators in rotation
         //   epilogue : ~400 per item + ~475 per (run, 16-column) step of a warp
         const double load_items = (double)cin_chunks * s * s * rows_sub * P;
-        const double L = 600.0 * kstages + load_items * (any_aff ? 3.0 : 2.0) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.5);
+        // with TMA the raw copy costs the producer warps nothing (one elected thread issues one box load per plane,
+        // ~0.4 cycles per slot of data-path time); only the in-place affine+SiLU pass is per-slot thread work
+        const double L = tma ? 300.0 * kstages + load_items * (any_aff ? 1.2 : 0.4) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.1)
+                             : 600.0 * kstages + load_items * (any_aff ? 3.0 : 2.0) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.5);
         // per (tap, K step) entry each issuing warp pays ~120 cycles of loop overhead + ~45 per run pair it issues;
         // the tensor pipe needs max(39, 32+N/4, N/2) per MMA; a dependent accumulate chain needs 167 cycles
         // divided by the accumulators the warp rotates over
@@ -928,7 +1013,7 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
           best_cost = cost;
           found = true;
           best.TH = TH; best.TW = TW; best.P = P; best.R = R; best.rows_sub = rows_sub; best.slots_sub = slots_sub;
-          best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.pair = pair ? 1 : 0; best.entries = taps; best.b_resident = resident ? 1 : 0;
+          best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.pair = pair ? 1 : 0; best.entries = taps; best.b_resident = resident ? 1 : 0; best.tma = tma ? 1 : 0;
           best.tiles_x = tiles_x; best.tiles_y = tiles_y;
           best.NB = NB; best.nblk = nblk; best.ksteps = ksteps; best.cin_chunks = cin_chunks;
           best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;

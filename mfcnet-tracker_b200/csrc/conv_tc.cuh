@@ -31,6 +31,7 @@ struct ConvTiling {
   int entries;       // MMA entries per K step: kh*kw, or kh*ceil(kw/2) with tap pairing
   int kacc;          // K-split accumulator sets per buffer (1, 2 or 4): consecutive taps rotate over them so that
                      // back-to-back MMAs are independent even when the tile has a single run; the epilogue sums them
+  int tma;           // 1: stride-1, no-upsample conv: the halo tile of every plane is ONE TMA box load (zero fill = padding)
   int b_resident;    // 1: the whole packed weight blob is loaded once per CTA; 0: streamed with each stage
   int tiles_x, tiles_y;
   int NB, nblk;
@@ -69,6 +70,7 @@ struct ConvParams {
   long long y_bs;
   float* y_nchw;
   float* stats;
+  alignas(64) CUtensorMap tmap[MFC_MAX_SRC];  // t.tma: source i as the 5-D tensor (8 ch, W, H, chunk, sample)
   int debug;  // measurement only (MFC_CONV_DEBUG): bit0 skip producer copies, bit1 skip epilogue body, bit2 skip MMAs
 };
 

@@ -24,6 +24,14 @@ CASES = [
     dict(name="32->16 k3 up2", B=4, H=240, W=320, cins=[32], Cout=16, k=3, ups=2),
     dict(name="fusion 11x11", B=8, H=480, W=640, cins=[5, 5, 5, 7], Cout=15, k=11, act=1),
     dict(name="16->5 k1 nchw", B=4, H=480, W=640, cins=[16], Cout=5, k=1, nchw=True),
+    # the headline step runs the SFC over 24 frames at once: tensors (236 MB) no longer fit the 126 MB L2
+    dict(name="B24 16->16 k3 plain", B=24, H=480, W=640, cins=[16], Cout=16, k=3),
+    dict(name="B24 16->16 k3 aff+stats", B=24, H=480, W=640, cins=[16], Cout=16, k=3, stats=True, aff=True),
+    dict(name="B24 32->16 k3 aff+stats", B=24, H=480, W=640, cins=[16, 16], Cout=16, k=3, stats=True, aff=True),
+    dict(name="B24 32->16 k1 res", B=24, H=480, W=640, cins=[16, 16], Cout=16, k=1, res=True),
+    dict(name="B24 128->128 k3 aff+stats", B=24, H=60, W=80, cins=[128], Cout=128, k=3, stats=True, aff=True),
+    dict(name="B24 64->64 k3 aff+stats", B=24, H=120, W=160, cins=[64], Cout=64, k=3, stats=True, aff=True),
+    dict(name="B24 32->32 k3 aff+stats", B=24, H=240, W=320, cins=[32], Cout=32, k=3, stats=True, aff=True),
 ]
 
 
