@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MFC_ABI_VERSION 3
+#define MFC_ABI_VERSION 4
 
 /* error codes */
 #define MFC_OK 0
@@ -104,6 +104,9 @@ typedef struct MfcConvInfo {
   int smem_bytes;      /* dynamic shared memory per CTA                               */
   int tmem_cols;       /* TMEM columns allocated per CTA                              */
   long long packed_weight_bytes;
+  int weight_layout;   /* 0 = one B block per filter tap, 1 = sliding-accumulate layout (vertical taps stacked along N);
+                          packed weights are only valid for descriptors that report the same layout and nb/nblk/ksteps */
+  int reserved;
 } MfcConvInfo;
 
 typedef struct MfcSrc {

@@ -24,7 +24,8 @@ class MfcGather(C.Structure):
 class MfcConvInfo(C.Structure):
     _fields_ = [("nb", c_int), ("nblk", c_int), ("cin_chunks", c_int), ("ksteps", c_int), ("tile_h", c_int),
                 ("tile_w", c_int), ("tiles_per_image", c_int), ("stats_per_image", c_int), ("runs", c_int),
-                ("kstages", c_int), ("nstages", c_int), ("grid", c_int), ("smem_bytes", c_int), ("tmem_cols", c_int), ("packed_weight_bytes", c_ll)]
+                ("kstages", c_int), ("nstages", c_int), ("grid", c_int), ("smem_bytes", c_int), ("tmem_cols", c_int), ("packed_weight_bytes", c_ll),
+                ("weight_layout", c_int), ("reserved", c_int)]
 
 
 class MfcSrc(C.Structure):
@@ -165,7 +166,7 @@ def load(build_if_missing=True):
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.argtypes = args
             fn.restype = res
-        if lib.mfc_abi_version() != 3:
+        if lib.mfc_abi_version() != 4:
             raise RuntimeError("libmfcnet_b200.so ABI version mismatch")
         _lib = _PlanOnly(lib) if plan_only() else lib
     return _lib

@@ -225,7 +225,8 @@ int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info) {
   info->grid = t.grid;
   info->smem_bytes = (int)t.smem_bytes;
   info->tmem_cols = (int)t.tmem_cols;
-  info->packed_weight_bytes = (long long)t.nblk * t.ksteps * t.entries * 2 * t.NB * 16;
+  info->packed_weight_bytes = (long long)t.nblk * t.ksteps * t.entries * 2 * t.nrows_b * 16;
+  info->weight_layout = t.slide;
   return MFC_OK;
 }
 
@@ -238,7 +239,7 @@ int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w
   rc = get_tiling(d, &t);
   if (rc != MFC_OK) return rc;
   MFC_LAUNCH(mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,
-                                      t.pair ? d->kw : 0, d->kh * d->kw, packed,
+                                      t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, packed,
                                       d->dtype == MFC_BF16, (cudaStream_t)stream),
              "conv_pack");
 }

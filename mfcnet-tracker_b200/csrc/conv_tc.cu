@@ -22,6 +22,10 @@
 //   D: TMEM, R runs x NB fp32 columns per accumulator buffer.
 #include "conv_tc.cuh"
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 namespace mfc {
 
 // ---- producers: phase 1, asynchronous raw copy of one 8-channel plane of the halo tile --------------
@@ -201,8 +205,8 @@ __device__ __forceinline__ void issue_stage(const ConvParams& p, uint8_t* abuf, 
   if (!p.t.b_resident) {
     const int taps = p.t.entries;
     uint8_t* bbuf = abuf + p.t.a_stage_bytes;
-    const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * taps * (size_t)(2 * p.t.NB * 16);
-    const int n16 = nks * taps * 2 * p.t.NB;
+    const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * taps * (size_t)(2 * p.t.nrows_b * 16);
+    const int n16 = nks * taps * 2 * p.t.nrows_b;
 #pragma unroll 4
     for (int i = tid; i < n16; i += NT) cp_async16(bbuf + (size_t)i * 16, wsrc + (size_t)i * 16);
   }
@@ -226,10 +230,10 @@ __device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* ab
   const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
   const int nplanes = p.t.pair ? 1 : 2 * nks;
   const uint32_t box_bytes = (uint32_t)(p.t.rows_sub * p.t.P) * 16u;
-  const uint32_t w_bytes = p.t.b_resident ? 0u : (uint32_t)(nks * p.t.entries * 2 * p.t.NB) * 16u;
+  const uint32_t w_bytes = p.t.b_resident ? 0u : (uint32_t)(nks * p.t.entries * 2 * p.t.nrows_b) * 16u;
   mbar_arrive_expect_tx(bar, (uint32_t)nplanes * box_bytes + w_bytes);
   if (w_bytes) {
-    const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * p.t.entries * (size_t)(2 * p.t.NB * 16);
+    const uint8_t* wsrc = p.w + ((size_t)nbk * p.t.ksteps + (size_t)ks * ksteps_per_stage) * p.t.entries * (size_t)(2 * p.t.nrows_b * 16);
     bulk_load(abuf + p.t.a_stage_bytes, wsrc, w_bytes, bar);
   }
   for (int q = 0; q < nplanes; ++q) {
@@ -402,6 +406,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
       if (has_res && more) fetch_res(r2, j2);
     }
     tmem_ld_wait();
+    if (p.t.slide) tmem_st16_zero(tm_lane + (uint32_t)(r * NB + j));  // slide mode accumulates into zeroed columns
     for (int a = 1; a < p.t.kacc; ++a) {  // K-split accumulator sets: add the partial sums
       uint32_t part[16];
       tmem_ld16(tm_lane + (uint32_t)((a * p.t.R + r) * NB + j), part);
@@ -515,6 +520,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     r = r2;
     j = j2;
   }
+  if (p.t.slide) tmem_st_wait();
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
@@ -629,7 +635,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     fence_async_smem();
   }
   if (p.t.b_resident) {
-    const int n16 = p.t.ksteps * taps * 2 * NB;
+    const int n16 = p.t.ksteps * taps * 2 * p.t.nrows_b;
     for (int i = tid; i < n16; i += kConvThreads) cp_async16(b_res + (size_t)i * 16, p.w + (size_t)i * 16);
     cp_async_commit();
     cp_async_wait_all();
@@ -643,6 +649,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.t.slide) {  // every MMA of this mode accumulates: start from zeroed accumulators (the epilogue re-zeroes what it drains)
+    if (warp < 4) {
+      for (uint32_t c = 0; c < p.t.tmem_cols; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   pdl_wait();  // from here on the previous kernel's outputs (activations, GroupNorm affines) are read
   const long long t_setup = clock64();
   const bool timed = (p.debug & 8) != 0;
@@ -742,9 +757,51 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
           // Descriptors differ only in their 14-bit start-address field (16-byte units), so the whole
           // issue loop is integer adds on the low word: no divisions, ~10 instructions per MMA.
           const uint64_t da0 = make_smem_desc(smem_u32(abuf), p.t.pair ? 16u : p.t.plane_bytes, 128);  // LBO: next plane, or next pixel
-          const uint64_t db0 = make_smem_desc(smem_u32(bbuf), (uint32_t)(NB * 16), 128);
+          const uint64_t db0 = make_smem_desc(smem_u32(bbuf), (uint32_t)(p.t.nrows_b * 16), 128);  // LBO: the other K half
           const uint32_t da_hi = (uint32_t)(da0 >> 32), db_hi = (uint32_t)(db0 >> 32);
           const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
+          if (p.t.slide) {
+            // Sliding accumulate: input row r (one 128-slot run) x horizontal entry e -> ONE MMA whose N spans the
+            // output rows lo..hi of the tile that row r contributes to (vertical tap ky = r - hy - y + hy ... stacked
+            // along N as group g' = kh-1-ky, so ascending N = ascending output row = ascending TMEM column block).
+            // Issued by warp 0 only (a fixed order keeps the fp32 sums bit-reproducible).
+            if (mw == 0 && !(p.debug & 4)) {
+              const int kh = p.kh, hy = kh - 1, TH = p.t.TH, rows = p.t.rows_sub;
+              const uint32_t b_blk = (uint32_t)(2 * p.t.nrows_b);
+              const uint32_t idesc0 = idesc & ~(0x3Fu << 17);
+              const uint32_t kx_step = p.t.pair ? 2u : 1u;
+              for (int sk = 0; sk < nks; ++sk) {
+                for (int e = 0; e < taps; ++e) {
+                  const uint32_t a_e = da_lo0 + (uint32_t)sk * a_kstep + (uint32_t)e * kx_step;
+                  const uint32_t b_e = db_lo0 + (uint32_t)(sk * taps + e) * b_blk;
+                  // rows whose window is clipped by the top / bottom edge of the tile use a narrower N; the rows in
+                  // between (the bulk) all issue the same full-window MMA, advancing A by one row and D by NB columns.
+                  // Consecutive MMAs accumulate into overlapping column windows: measured at the full pipe rate
+                  // (tools/ubench/mma_rate3.cu: N=48 sliding by 16 columns per MMA = 45 cycles each).
+                  const int top_end = min(hy, rows);
+                  for (int r = 0; r < top_end; ++r) {  // lo = 0
+                    const uint32_t n = (uint32_t)((min(TH - 1, r) + 1) * NB);
+                    umma_f16_ss(tmem_acc, ((uint64_t)da_hi << 32) | (a_e + 128u * (uint32_t)r),
+                                ((uint64_t)db_hi << 32) | (b_e + (uint32_t)((hy - r) * NB)), idesc0 | ((n >> 3) << 17), 1u);
+                  }
+                  {
+                    uint32_t a_lo = a_e + 128u * (uint32_t)hy, d_t = tmem_acc;
+                    const uint32_t idesc_full = idesc0 | (((uint32_t)(kh * NB) >> 3) << 17);
+                    for (int r = hy; r < TH; ++r) {  // full window: output rows r-hy .. r
+                      umma_f16_ss(d_t, ((uint64_t)da_hi << 32) | a_lo, ((uint64_t)db_hi << 32) | b_e, idesc_full, 1u);
+                      a_lo += 128u;
+                      d_t += (uint32_t)NB;
+                    }
+                  }
+                  for (int r = max(hy, TH); r < rows; ++r) {  // hi = TH-1, lo = r-hy
+                    const uint32_t n = (uint32_t)((TH - r + hy) * NB);
+                    umma_f16_ss(tmem_acc + (uint32_t)((r - hy) * NB), ((uint64_t)da_hi << 32) | (a_e + 128u * (uint32_t)r),
+                                ((uint64_t)db_hi << 32) | b_e, idesc0 | ((n >> 3) << 17), 1u);
+                  }
+                }
+              }
+            }
+          } else {
           // Loop order: taps outermost, the tile's R independent 128-pixel runs innermost, so that
           // back-to-back MMAs never accumulate into the same TMEM columns (a dependent accumulate
           // chain serialises on the tensor pipe's latency, which dwarfs an N=16 MMA's busy cycles).
@@ -777,6 +834,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
               }
               b_t += b_tap;
             }
+          }
           }
           umma_commit(&bar_empty[stage]);                              // smem slot free once these MMAs retire
           if (ks == p.t.kstages - 1) umma_commit(&bar_tfull[acc_i]);   // accumulators complete
@@ -861,23 +919,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // With tap pairing (pair_kw > 0: a single input plane, kernel width pair_kw) entry (ky, j) holds tap (ky, 2j) in
 // its first K half and tap (ky, 2j+1) -- or zeros past the kernel edge -- in the second.
+// Slide mode (slide_kh = kh > 0): one B block per (K step, horizontal entry) with N = kh*NB rows, row n = g'*NB + co
+// holding the vertical tap ky = kh-1-g' -- ascending rows = ascending output rows of the accumulator window.
 template <bool BF16>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin_w, int taps, const int* __restrict__ chan_map,
-                                    int cin_chunks, int ksteps, int NB, int nblk, int pair_kw, int taps_w,
+                                    int cin_chunks, int ksteps, int NB, int nblk, int pair_kw, int taps_w, int slide_kh, int kw,
                                     uint16_t* __restrict__ out) {
-  const size_t total = (size_t)nblk * ksteps * taps * 2 * NB * 8;
+  const int rows = slide_kh > 0 ? slide_kh * NB : NB;
+  const size_t total = (size_t)nblk * ksteps * taps * 2 * rows * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int e = r % 8; r /= 8;
-    const int n = r % NB; r /= NB;
+    const int nrow = r % rows; r /= rows;
     const int kh = r % 2; r /= 2;
     const int t = r % taps; r /= taps;
     const int ks = r % ksteps; r /= ksteps;
     const int nb = (int)r;
+    const int n = slide_kh > 0 ? nrow % NB : nrow;
     const int co = nb * NB + n;
     int kp = (ks * 2 + kh) * 8 + e;  // padded concat channel
     int tw = t;                      // tap index in the OIHW weight
-    if (pair_kw > 0) {
+    if (slide_kh > 0) {
+      const int ky = slide_kh - 1 - nrow / NB;
+      int kx = t;
+      if (pair_kw > 0) {
+        kx = t * 2 + kh;
+        kp = e;
+      }
+      tw = kx < kw ? ky * kw + kx : -1;
+    } else if (pair_kw > 0) {
       const int per_row = (pair_kw + 1) >> 1;
       const int ky = t / per_row, kx = (t - ky * per_row) * 2 + kh;
       kp = e;
@@ -930,7 +1000,6 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
   // stride-1, no-upsample convs stage their halo tiles with TMA box loads (one instruction per 8-channel plane,
   // hardware zero fill outside the image); box extents are limited to 256 per dimension
   const bool tma = s == 1 && d.upsample == 1;
-  const int taps = pair ? d.kh * ((d.kw + 1) / 2) : d.kh * d.kw;  // MMA entries per K step
   const int ksteps = ceil_div(cin_chunks, 2);
   int nblk;
   const int NB = conv_nb(d.Cout, &nblk);
@@ -938,59 +1007,74 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
   const uint32_t off_scale = 256;
   const uint32_t off_stats = off_scale + cpad * 8;
   const uint32_t off_bres = (off_stats + (cpad <= 256 ? (uint32_t)kEpiWarps * cpad * 8 : 0u) + 127) & ~127u;
-  const uint64_t w_bytes_nblk = (uint64_t)ksteps * taps * 2 * NB * 16;  // one N-block's packed weights
+  static const int force_slide = getenv("MFC_CONV_SLIDE") ? atoi(getenv("MFC_CONV_SLIDE")) : -1;  // measurement: 0 never, 1 always
+  const bool slide_ok = s == 1 && d.kh > 1 && nblk == 1 && d.kh * NB <= 256 && d.out_stride != 2 && force_slide != 0;
   double best_cost = 1e300;
   bool found = false;
-  for (int nx = 1; nx <= 40; ++nx) {
-    const int TW = ceil_div(d.Wout, nx);
-    if (nx > 1 && TW < 8) break;
-    if (nx > 1 && ceil_div(d.Wout, nx - 1) == TW) continue;
-    const int P = TW + hx;
-    for (int TH = 1; TH <= d.Hout && TH <= 64; ++TH) {
-      const int R = ceil_div((TH - 1) * P + TW, 128);
-      if ((uint32_t)(R * NB) > 512) break;
-      // a dependent accumulate costs ~167 cycles, an independent N<=32 MMA ~39: every issuing warp wants
-      // >= 4 accumulators to rotate over.  Tiles with few runs split K over kacc accumulator sets.
-      int kacc = 1;
-      while (kacc < 4 && ceil_div(R * kacc, kMmaWarps) < 4 && R * NB * kacc * 2 <= 512 && kacc * 2 <= taps * ksteps) kacc *= 2;
-      const int nacc = (2 * R * NB * kacc <= 512) ? 2 : 1;
-      const uint32_t tmem = pow2_at_least((uint32_t)(nacc * R * NB * kacc), 32);
-      const int rows_sub = TH + hy;
-      const int slots_sub = std::max(R * 128 + hy * P + hx, rows_sub * P);
-      const uint32_t plane_bytes = ((uint32_t)(s * s) * slots_sub * 16 + 127u) & ~127u;  // TMA destinations: 128-byte aligned
-      if (plane_bytes > 200000u) break;
-      if (tma && (P > 256 || rows_sub > 256)) continue;
-      const int tiles_x = nx, tiles_y = ceil_div(d.Hout, TH);
-      const long long items = (long long)d.B * tiles_x * tiles_y * nblk;
-      // K staging options: all channels in one stage, or 16/32/64/128-channel stages
-      const int opts[5] = {2 * ksteps, 16, 8, 4, 2};
-      for (int oi = 0; oi < 5; ++oi) {
-        const int CBc = opts[oi];
-        if (oi > 0 && CBc >= 2 * ksteps) continue;
-        const int kstages = ceil_div(2 * ksteps, CBc);
-        const bool resident = kstages == 1 && nblk == 1;
-        const uint32_t a_stage = (uint32_t)CBc * plane_bytes;
-        const uint64_t b_stage = (uint64_t)(CBc / 2) * taps * 2 * NB * 16;
-        const uint64_t stage_bytes = ((uint64_t)a_stage + (resident ? 0 : b_stage) + 127) & ~(uint64_t)127;
-        const uint64_t off_stage = ((uint64_t)off_bres + (resident ? w_bytes_nblk : 0) + 127) & ~(uint64_t)127;
-        if (off_stage + stage_bytes + 128 > (uint64_t)kSmemPerCtaMax) continue;
-        int nstages = (int)(((uint64_t)kSmemPerCtaMax - 128 - off_stage) / stage_bytes);
-        nstages = std::min(nstages, kstages > 1 ? 6 : 4);
-        nstages = std::min(nstages, kMaxStages);
-        if (nstages < 1) continue;
-        const uint32_t smem = (uint32_t)(off_stage + (uint64_t)nstages * stage_bytes + 128);
-        // ---- cost model: SM cycles, calibrated on B200 with the per-role timing switches of this kernel
-        // (MFC_CONV_DEBUG) and tools/ubench/mma_rate2.cu.  Every role pays a fixed cost per work item
-        // (decode, barriers, loop set-up) on top of its per-element work, so small tiles are expensive:
-        //   producers: ~600 per (item, K stage) + ~2.0 per 16-byte slot (+1.0 with the affine+SiLU pass)
-        //   MMA      : ~500 per item + ~62 per MMA for N <= 64 (single-thread issue), N/2+8 above; a
-        //              dependent accumulate chain costs 167 per MMA divided by the accumulators in rotation
-        //   epilogue : ~400 per item + ~475 per (run, 16-column) step of a warp
-        const double load_items = (double)cin_chunks * s * s * rows_sub * P;
-        // with TMA the raw copy costs the producer warps nothing (one elected thread issues one box load per plane,
-        // ~0.4 cycles per slot of data-path time); only the in-place affine+SiLU pass is per-slot thread work
-        const double L = tma ? 300.0 * kstages + load_items * (any_aff ? 1.2 : 0.4) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.1)
-                             : 600.0 * kstages + load_items * (any_aff ? 3.0 : 2.0) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.5);
+
+  // evaluates one tile shape; slide = sliding-accumulate mode (P must be 128: one MMA run per input row)
+  auto consider = [&](int TH, int TW, int nx, bool slide) -> bool {  // false: TH too large for this TW (stop growing it)
+    const int P = slide ? 128 : TW + hx;
+    const int entries = slide ? (pair ? (d.kw + 1) / 2 : d.kw) : (pair ? d.kh * ((d.kw + 1) / 2) : d.kh * d.kw);  // B blocks per K step
+    const int nrows_b = slide ? d.kh * NB : NB;
+    const uint64_t w_bytes_nblk = (uint64_t)ksteps * entries * 2 * nrows_b * 16;  // one N-block's packed weights
+    const int R = slide ? TH : ceil_div((TH - 1) * P + TW, 128);  // accumulator runs ([run][NB] column blocks)
+    if ((uint32_t)(R * NB) > 512) return false;
+    // a dependent accumulate costs ~167 cycles, an independent N<=32 MMA ~39: every issuing warp wants
+    // >= 4 accumulators to rotate over.  Tiles with few runs split K over kacc accumulator sets.
+    int kacc = 1;
+    if (!slide)
+      while (kacc < 4 && ceil_div(R * kacc, kMmaWarps) < 4 && R * NB * kacc * 2 <= 512 && kacc * 2 <= entries * ksteps) kacc *= 2;
+    const int nacc = (2 * R * NB * kacc <= 512) ? 2 : 1;
+    const uint32_t tmem = pow2_at_least((uint32_t)(nacc * R * NB * kacc), 32);
+    const int rows_sub = TH + hy;
+    const int slots_sub = slide ? rows_sub * P + hx + 1 : std::max(R * 128 + hy * P + hx, rows_sub * P);
+    const uint32_t plane_bytes = ((uint32_t)(s * s) * slots_sub * 16 + 127u) & ~127u;  // TMA destinations: 128-byte aligned
+    if (plane_bytes > 200000u) return false;
+    if (tma && (P > 256 || rows_sub > 256)) return true;
+    const int tiles_x = nx, tiles_y = ceil_div(d.Hout, TH);
+    const long long items = (long long)d.B * tiles_x * tiles_y * nblk;
+    // K staging options: all channels in one stage, or 16/32/64/128-channel stages
+    const int opts[5] = {2 * ksteps, 16, 8, 4, 2};
+    for (int oi = 0; oi < 5; ++oi) {
+      const int CBc = opts[oi];
+      if (oi > 0 && CBc >= 2 * ksteps) continue;
+      const int kstages = ceil_div(2 * ksteps, CBc);
+      const bool resident = kstages == 1 && nblk == 1;
+      const uint32_t a_stage = (uint32_t)CBc * plane_bytes;
+      const uint64_t b_stage = (uint64_t)(CBc / 2) * entries * 2 * nrows_b * 16;
+      const uint64_t stage_bytes = ((uint64_t)a_stage + (resident ? 0 : b_stage) + 127) & ~(uint64_t)127;
+      const uint64_t off_stage = ((uint64_t)off_bres + (resident ? w_bytes_nblk : 0) + 127) & ~(uint64_t)127;
+      if (off_stage + stage_bytes + 128 > (uint64_t)kSmemPerCtaMax) continue;
+      int nstages = (int)(((uint64_t)kSmemPerCtaMax - 128 - off_stage) / stage_bytes);
+      nstages = std::min(nstages, kstages > 1 ? 6 : 4);
+      nstages = std::min(nstages, kMaxStages);
+      if (nstages < 1) continue;
+      const uint32_t smem = (uint32_t)(off_stage + (uint64_t)nstages * stage_bytes + 128);
+      // ---- cost model: SM cycles, calibrated on B200 with the per-role timing switches of this kernel
+      // (MFC_CONV_DEBUG) and tools/ubench/mma_rate2.cu.  Every role pays a fixed cost per work item
+      // (decode, barriers, loop set-up) on top of its per-element work, so small tiles are expensive:
+      //   producers: ~600 per (item, K stage) + ~2.0 per 16-byte slot (+1.0 with the affine+SiLU pass)
+      //   MMA      : ~500 per item + ~62 per MMA for N <= 64 (single-thread issue), N/2+8 above; a
+      //              dependent accumulate chain costs 167 per MMA divided by the accumulators in rotation
+      //   epilogue : ~400 per item + ~475 per (run, 16-column) step of a warp
+      const double load_items = (double)cin_chunks * s * s * rows_sub * P;
+      // with TMA the raw copy costs the producer warps nothing (one elected thread issues one box load per plane,
+      // ~0.4 cycles per slot of data-path time); only the in-place affine+SiLU pass is per-slot thread work
+      const double L = tma ? 300.0 * kstages + load_items * (any_aff ? 1.2 : 0.4) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.1)
+                           : 600.0 * kstages + load_items * (any_aff ? 3.0 : 2.0) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.5);
+      double M;
+      if (slide) {
+        // one MMA per (K step, horizontal entry, input row); N = NB * (output rows of the tile inside the row's window).
+        // Overlapping accumulator windows of consecutive rows run at the full pipe rate (tools/ubench/mma_rate3.cu).
+        double sum = 0.0;
+        for (int r = 0; r < rows_sub; ++r) {
+          const int lo = std::max(0, r - hy), hi = std::min(TH - 1, r);
+          const double N = (double)NB * (hi - lo + 1);
+          sum += std::max(std::max(46.0, 32.0 + N / 4.0), N / 2.0 + 4.0);
+        }
+        M = 500.0 + (double)entries * ksteps * sum;
+      } else {
         // per (tap, K step) entry each issuing warp pays ~120 cycles of loop overhead + ~45 per run pair it issues;
         // the tensor pipe needs max(39, 32+N/4, N/2) per MMA; a dependent accumulate chain needs 167 cycles
         // divided by the accumulators the warp rotates over
@@ -998,31 +1082,53 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
         const double indep = std::max(1.0, std::floor((double)R * kacc / kMmaWarps));
         const double pipe = std::max(39.0, std::max(32.0 + NB / 4.0, NB / 2.0 + 4.0));
         const double per_entry = std::max(std::max(120.0 + 45.0 * R, R * pipe), runs_w * 167.0 / std::min(indep, 4.0));
-        const double M = 500.0 + (double)taps * ksteps * per_entry;
-        const double E = 400.0 + (double)((R + 1) / 2) * (NB / 16) * (475.0 + 120.0 * (kacc - 1));
-        const int G = (int)std::min<long long>(items, kSmCount);
-        const double rounds = std::ceil((double)items / G);
-        double per_item;
-        if (nstages >= 2) {
-          per_item = std::max(L, std::max(M, nacc == 2 ? E : 0.0)) + (nacc == 2 ? 0.0 : E);
-        } else {
-          per_item = L + std::max(M, E) + (nacc == 2 ? 0.0 : std::min(M, E));
-        }
-        const double cost = (rounds - 1.0) * per_item + (L + M + E) + (resident ? (double)(w_bytes_nblk / 16) * 0.3 : 0.0);
-        if (cost < best_cost) {
-          best_cost = cost;
-          found = true;
-          best.TH = TH; best.TW = TW; best.P = P; best.R = R; best.rows_sub = rows_sub; best.slots_sub = slots_sub;
-          best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.pair = pair ? 1 : 0; best.entries = taps; best.b_resident = resident ? 1 : 0; best.tma = tma ? 1 : 0;
-          best.tiles_x = tiles_x; best.tiles_y = tiles_y;
-          best.NB = NB; best.nblk = nblk; best.ksteps = ksteps; best.cin_chunks = cin_chunks;
-          best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;
-          best.stage_bytes = (uint32_t)stage_bytes;
-          best.smem_bytes = smem; best.tmem_cols = tmem; best.acc_cols = (uint32_t)(R * NB * kacc);
-          best.off_scale = off_scale; best.off_stats = off_stats; best.off_bres = off_bres; best.off_stage = (uint32_t)off_stage;
-          best.grid = G;
-        }
+        M = 500.0 + (double)entries * ksteps * per_entry;
       }
+      const double E = 400.0 + (double)((R + 1) / 2) * (NB / 16) * (475.0 + 120.0 * (kacc - 1) + (slide ? 30.0 : 0.0));
+      const int G = (int)std::min<long long>(items, kSmCount);
+      const double rounds = std::ceil((double)items / G);
+      double per_item;
+      if (nstages >= 2) {
+        per_item = std::max(L, std::max(M, nacc == 2 ? E : 0.0)) + (nacc == 2 ? 0.0 : E);
+      } else {
+        per_item = L + std::max(M, E) + (nacc == 2 ? 0.0 : std::min(M, E));
+      }
+      const double cost = (rounds - 1.0) * per_item + (L + M + E) + (resident ? (double)(w_bytes_nblk / 16) * 0.3 : 0.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        found = true;
+        best.TH = TH; best.TW = TW; best.P = P; best.R = R; best.rows_sub = rows_sub; best.slots_sub = slots_sub;
+        best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.pair = pair ? 1 : 0;
+        best.entries = entries; best.b_resident = resident ? 1 : 0; best.tma = tma ? 1 : 0;
+        best.slide = slide ? 1 : 0; best.nrows_b = nrows_b;
+        best.tiles_x = tiles_x; best.tiles_y = tiles_y;
+        best.NB = NB; best.nblk = nblk; best.ksteps = ksteps; best.cin_chunks = cin_chunks;
+        best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;
+        best.stage_bytes = (uint32_t)stage_bytes;
+        best.smem_bytes = smem; best.tmem_cols = tmem; best.acc_cols = (uint32_t)(R * NB * kacc);
+        best.off_scale = off_scale; best.off_stats = off_stats; best.off_bres = off_bres; best.off_stage = (uint32_t)off_stage;
+        best.grid = G;
+      }
+    }
+    return true;
+  };
+
+  if (force_slide != 1 || !slide_ok) {
+    for (int nx = 1; nx <= 40; ++nx) {
+      const int TW = ceil_div(d.Wout, nx);
+      if (nx > 1 && TW < 8) break;
+      if (nx > 1 && ceil_div(d.Wout, nx - 1) == TW) continue;
+      for (int TH = 1; TH <= d.Hout && TH <= 64; ++TH)
+        if (!consider(TH, TW, nx, false)) break;
+    }
+  }
+  if (slide_ok) {
+    const int tw_max = 128 - hx - (pair ? 1 : 0);
+    const int nx0 = ceil_div(d.Wout, tw_max);
+    for (int nx = nx0; nx <= nx0 + 1; ++nx) {
+      const int TW = ceil_div(d.Wout, nx);
+      for (int TH = 1; TH <= d.Hout && TH <= 64; ++TH)
+        if (!consider(TH, TW, nx, true)) break;
     }
   }
   return found;
@@ -1071,16 +1177,17 @@ cudaError_t launch_conv(const ConvParams& p, bool bf16, cudaStream_t st) {
 }
 
 cudaError_t launch_pack_weights(const float* w, int Cout, int Cin_w, int taps, const int* chan_map, int cin_chunks,
-                                int ksteps, int NB, int nblk, int pair_kw, int taps_w, void* out, bool bf16, cudaStream_t st) {
-  const size_t total = (size_t)nblk * ksteps * taps * 2 * NB * 8;
+                                int ksteps, int NB, int nblk, int pair_kw, int taps_w, int slide_kh, int kw, void* out, bool bf16,
+                                cudaStream_t st) {
+  const size_t total = (size_t)nblk * ksteps * taps * 2 * (slide_kh > 0 ? slide_kh * NB : NB) * 8;
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 4096);
   if (bf16)
     pack_weights_kernel<true><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, pair_kw, taps_w,
-                                                          (uint16_t*)out);
+                                                          slide_kh, kw, (uint16_t*)out);
   else
     pack_weights_kernel<false><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, pair_kw, taps_w,
-                                                           (uint16_t*)out);
+                                                           slide_kh, kw, (uint16_t*)out);
   return cudaGetLastError();
 }
 

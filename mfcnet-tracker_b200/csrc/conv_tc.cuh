@@ -31,6 +31,12 @@ struct ConvTiling {
   int entries;       // MMA entries per K step: kh*kw, or kh*ceil(kw/2) with tap pairing
   int kacc;          // K-split accumulator sets per buffer (1, 2 or 4): consecutive taps rotate over them so that
                      // back-to-back MMAs are independent even when the tile has a single run; the epilogue sums them
+  int slide;         // 1: "sliding accumulate" mode for stride-1 kh>1 convs with few output channels.  P = 128, so an MMA run
+                     //    is exactly one INPUT row of the tile; the kh vertical taps become N-groups of one wide MMA
+                     //    (N = window * NB): the MMA of input row r and horizontal tap kx adds W[ky][kx] * in[r] into the
+                     //    accumulator columns of the output rows r-ky, which are adjacent column blocks [row][NB] in TMEM.
+                     //    kh x fewer MMAs and A-operand reads than one MMA per tap; accumulators are zeroed by the epilogue.
+  int nrows_b;       // rows (N) of one packed B block: NB, or kh*NB in slide mode (N-group g' = kh-1-ky)
   int tma;           // 1: stride-1, no-upsample conv: the halo tile of every plane is ONE TMA box load (zero fill = padding)
   int b_resident;    // 1: the whole packed weight blob is loaded once per CTA; 0: streamed with each stage
   int tiles_x, tiles_y;

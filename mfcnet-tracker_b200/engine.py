@@ -445,7 +445,7 @@ class WeightPacker:
 
     def pack(self, key, prog, desc, info, w_oihw, cmap, scale=None, shift=None):
         """w_oihw fp32 [Cout][Cin_w][kh][kw] device tensor -> PackedConv for this geometry."""
-        k = ("pk", key, info.nb, info.nblk, info.ksteps, tuple(cmap) if cmap is not None else None)
+        k = ("pk", key, info.nb, info.nblk, info.ksteps, info.weight_layout, tuple(cmap) if cmap is not None else None)
         if k not in self.cache:
             w = w_oihw.detach().contiguous().float()
             packed = torch.empty(int(info.packed_weight_bytes), dtype=torch.uint8, device=self.device)

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     assert sorted(m.abi.EXPORTS) == names          # the ctypes binding covers the whole header
     lib.mfc_abi_version.restype = C.c_int
-    assert lib.mfc_abi_version() == 3
+    assert lib.mfc_abi_version() == 4
 
 
 def test_struct_sizes_match_header():
