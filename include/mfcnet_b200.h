@@ -170,6 +170,14 @@ typedef struct MfcConvIO {
 } MfcConvIO;
 int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream);
 
+/* Plan-time autotuning: measures the planner's shortlisted tilings (tile shape, K staging, weight layout) of `d` on the
+ * device with the caller's real buffers and keeps the fastest for every later mfc_conv2d_query / _pack_weights / _fwd of
+ * the same geometry.  io->w_packed is ignored; the raw OIHW weights are packed into `scratch_packed`
+ * (packed_weight_bytes of mfc_conv2d_query) once per weight layout.  io->stats, when given, must hold
+ * [B][148][nb*nblk][2] floats.  Synchronises `stream`.  Idempotent per geometry; call it BEFORE mfc_conv2d_query. */
+int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* w_oihw, int Cin_w, const int* chan_map,
+                        void* scratch_packed, int reps, void* stream);
+
 /* GroupNorm statistics -> per-(sample,channel) affine.  Replaces nn.GroupNorm
  * (models/resunet.py:72,77) split in two: partial sums come from the producing conv's
  * epilogue, this finalises them (fp64) into scale = g*rstd, shift = b - mean*g*rstd. */

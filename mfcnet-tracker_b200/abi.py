@@ -110,6 +110,7 @@ _SIGNATURES = {
     "mfc_conv2d_query": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvInfo)], c_int),
     "mfc_conv2d_pack_weights": ([C.POINTER(MfcConvDesc), c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "mfc_conv2d_fwd": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p], c_int),
+    "mfc_conv2d_autotune": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p], c_int),
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
     "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p], c_int),
     "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),

@@ -6,6 +6,7 @@
 
 #include <map>
 #include <mutex>
+#include <set>
 #include <tuple>
 #include <vector>
 
@@ -96,13 +97,19 @@ int validate_desc(const MfcConvDesc* d) {
   return MFC_OK;
 }
 
-int get_tiling(const MfcConvDesc* d, mfc::ConvTiling* out) {
+std::set<PlanKey> g_tuned;  // geometries whose plan was measured (mfc_conv2d_autotune)
+
+PlanKey plan_key(const MfcConvDesc* d) {
   int chunks = 0, aff = 0;
   for (int i = 0; i < d->nsrc; ++i) {
     chunks += d->src[i].nchunks;
     aff |= d->src[i].affine != nullptr;
   }
-  PlanKey key{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks, aff};
+  return PlanKey{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks, aff};
+}
+
+int get_tiling(const MfcConvDesc* d, mfc::ConvTiling* out) {
+  const PlanKey key = plan_key(d);
   {
     std::lock_guard<std::mutex> g(g_plan_mu);
     auto it = g_plans.find(key);
@@ -160,6 +167,61 @@ int encode_source_maps(const MfcConvDesc* d, mfc::ConvParams* p) {
   }
   return MFC_OK;
 }
+
+int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTiling& tiling, void* stream) {
+  int rc = MFC_OK;
+  if (!io || !io->w_packed) return fail(MFC_EINVAL, "conv: null io / weights");
+  if (!io->y_c8 && !io->y_nchw) return fail(MFC_EINVAL, "conv: no output buffer");
+  mfc::ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.t = tiling;
+  p.B = d->B; p.Hin = d->Hin; p.Win = d->Win; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.upsample = d->upsample; p.act = d->act;
+  p.in_off_y = d->in_off_y; p.in_off_x = d->in_off_x; p.out_stride = d->out_stride == 2 ? 2 : 1;
+  p.out_off_y = d->out_off_y; p.out_off_x = d->out_off_x;
+  if (p.out_stride == 2 && (io->residual || io->stats)) return fail(MFC_EINVAL, "conv: transposed-conv parity mode has no residual / statistics");
+  p.nsrc = d->nsrc;
+  int end = 0;
+  for (int i = 0; i < MFC_MAX_SRC; ++i) {
+    if (i < d->nsrc) {
+      if (!d->src[i].ptr) return fail(MFC_EINVAL, "conv: source %d is null", i);
+      if (((uintptr_t)d->src[i].ptr & 15) || (d->src[i].batch_stride & 15)) return fail(MFC_EINVAL, "conv: source %d not 16-byte aligned", i);
+      p.src_ptr[i] = (const uint8_t*)d->src[i].ptr;
+      p.src_aff[i] = d->src[i].affine;
+      p.src_bs[i] = d->src[i].batch_stride;
+      end += d->src[i].nchunks;
+    }
+    p.src_end[i] = end;
+  }
+  p.divP = mfc::make_fastdiv((uint32_t)p.t.P);
+  p.div_nblk = mfc::make_fastdiv((uint32_t)p.t.nblk);
+  p.div_tx = mfc::make_fastdiv((uint32_t)p.t.tiles_x);
+  p.div_ty = mfc::make_fastdiv((uint32_t)p.t.tiles_y);
+  p.idesc = mfc::make_idesc_f16(p.t.NB, d->dtype == MFC_BF16);
+  p.w = (const uint8_t*)io->w_packed;
+  p.scale = io->scale;
+  p.shift = io->shift;
+  p.res = (const uint8_t*)io->residual;
+  p.res_aff = io->res_affine;
+  p.res_bs = io->res_batch_stride;
+  p.y = (uint8_t*)io->y_c8;
+  p.y_bs = io->y_batch_stride;
+  p.y_nchw = io->y_nchw;
+  p.stats = io->stats;
+  {
+    static const int dbg = getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0;
+    p.debug = dbg;
+  }
+  if (p.t.tma) {
+    rc = encode_source_maps(d, &p);
+    if (rc != MFC_OK) return rc;
+  }
+  if (p.stats && p.t.NB * p.t.nblk > 256) return fail(MFC_EINVAL, "conv: GroupNorm statistics need Cout <= 256");
+  if (((uintptr_t)p.w & 15) || ((uintptr_t)p.y & 15) || ((uintptr_t)p.res & 15) || (p.y_bs & 15) || (p.res_bs & 15))
+    return fail(MFC_EINVAL, "conv: weights / output / residual not 16-byte aligned");
+  MFC_LAUNCH(mfc::launch_conv(p, d->dtype == MFC_BF16, (cudaStream_t)stream), "conv2d_fwd");
+}
+
 
 }  // namespace
 
@@ -248,57 +310,77 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
   MFC_REQUIRE_ARCH();
   int rc = validate_desc(d);
   if (rc != MFC_OK) return rc;
-  if (!io || !io->w_packed) return fail(MFC_EINVAL, "conv: null io / weights");
-  if (!io->y_c8 && !io->y_nchw) return fail(MFC_EINVAL, "conv: no output buffer");
-  mfc::ConvParams p;
-  memset(&p, 0, sizeof(p));
-  rc = get_tiling(d, &p.t);
+  mfc::ConvTiling t;
+  rc = get_tiling(d, &t);
   if (rc != MFC_OK) return rc;
-  p.B = d->B; p.Hin = d->Hin; p.Win = d->Win; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
-  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.upsample = d->upsample; p.act = d->act;
-  p.in_off_y = d->in_off_y; p.in_off_x = d->in_off_x; p.out_stride = d->out_stride == 2 ? 2 : 1;
-  p.out_off_y = d->out_off_y; p.out_off_x = d->out_off_x;
-  if (p.out_stride == 2 && (io->residual || io->stats)) return fail(MFC_EINVAL, "conv: transposed-conv parity mode has no residual / statistics");
-  p.nsrc = d->nsrc;
-  int end = 0;
-  for (int i = 0; i < MFC_MAX_SRC; ++i) {
-    if (i < d->nsrc) {
-      if (!d->src[i].ptr) return fail(MFC_EINVAL, "conv: source %d is null", i);
-      if (((uintptr_t)d->src[i].ptr & 15) || (d->src[i].batch_stride & 15)) return fail(MFC_EINVAL, "conv: source %d not 16-byte aligned", i);
-      p.src_ptr[i] = (const uint8_t*)d->src[i].ptr;
-      p.src_aff[i] = d->src[i].affine;
-      p.src_bs[i] = d->src[i].batch_stride;
-      end += d->src[i].nchunks;
-    }
-    p.src_end[i] = end;
-  }
-  p.divP = mfc::make_fastdiv((uint32_t)p.t.P);
-  p.div_nblk = mfc::make_fastdiv((uint32_t)p.t.nblk);
-  p.div_tx = mfc::make_fastdiv((uint32_t)p.t.tiles_x);
-  p.div_ty = mfc::make_fastdiv((uint32_t)p.t.tiles_y);
-  p.idesc = mfc::make_idesc_f16(p.t.NB, d->dtype == MFC_BF16);
-  p.w = (const uint8_t*)io->w_packed;
-  p.scale = io->scale;
-  p.shift = io->shift;
-  p.res = (const uint8_t*)io->residual;
-  p.res_aff = io->res_affine;
-  p.res_bs = io->res_batch_stride;
-  p.y = (uint8_t*)io->y_c8;
-  p.y_bs = io->y_batch_stride;
-  p.y_nchw = io->y_nchw;
-  p.stats = io->stats;
+  return conv_fwd_tiled(d, io, t, stream);
+}
+
+/* Measures the planner's shortlisted tilings of `d` on the device with the caller's real buffers and keeps the fastest for
+ * every later query / pack / fwd of the same geometry.  io->w_packed is ignored: the raw weights are packed into
+ * `scratch_packed` (packed_weight_bytes of mfc_conv2d_query) once per weight layout.  io->stats, when given, must hold
+ * [B][148][nb*nblk][2] floats (any candidate's grid fits).  Synchronises the stream.  Idempotent per geometry. */
+int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* w_oihw, int Cin_w, const int* chan_map,
+                        void* scratch_packed, int reps, void* stream) {
+  MFC_REQUIRE_ARCH();
+  int rc = validate_desc(d);
+  if (rc != MFC_OK) return rc;
+  if (!io || !w_oihw || !scratch_packed || reps < 1) return fail(MFC_EINVAL, "conv_autotune: bad argument");
+  const PlanKey key = plan_key(d);
   {
-    static const int dbg = getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0;
-    p.debug = dbg;
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    if (g_tuned.count(key)) return MFC_OK;
   }
-  if (p.t.tma) {
-    rc = encode_source_maps(d, &p);
-    if (rc != MFC_OK) return rc;
+  std::vector<mfc::ConvTiling> cands;
+  mfc::conv_shortlist(*d, 3, cands);
+  if (cands.empty()) return fail(MFC_EINVAL, "conv: no tiling fits shared memory / TMEM for this shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return fail(MFC_ECUDA, "conv_autotune: cudaEventCreate failed");
+  MfcConvIO tio = *io;
+  tio.w_packed = scratch_packed;
+  float best_ms = 1e30f;
+  int best_i = -1;
+  for (int layout = 0; layout < 2 && rc == MFC_OK; ++layout) {
+    bool packed = false;
+    for (size_t i = 0; i < cands.size() && rc == MFC_OK; ++i) {
+      const mfc::ConvTiling& t = cands[i];
+      if (t.slide != layout) continue;
+      if (!packed) {
+        cudaError_t e = mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,
+                                                 t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, scratch_packed,
+                                                 d->dtype == MFC_BF16, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "conv_autotune: pack");
+        packed = true;
+      }
+      if (rc == MFC_OK) rc = conv_fwd_tiled(d, &tio, t, stream);  // warm-up (instruction cache, L2 state)
+      cudaEventRecord(e0, st);
+      for (int r = 0; r < reps && rc == MFC_OK; ++r) rc = conv_fwd_tiled(d, &tio, t, stream);
+      cudaEventRecord(e1, st);
+      if (rc != MFC_OK) break;
+      cudaError_t e = cudaEventSynchronize(e1);
+      if (e != cudaSuccess) {
+        rc = cuda_fail(e, "conv_autotune: sync");
+        break;
+      }
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < best_ms) {
+        best_ms = ms;
+        best_i = (int)i;
+      }
+    }
   }
-  if (p.stats && p.t.NB * p.t.nblk > 256) return fail(MFC_EINVAL, "conv: GroupNorm statistics need Cout <= 256");
-  if (((uintptr_t)p.w & 15) || ((uintptr_t)p.y & 15) || ((uintptr_t)p.res & 15) || (p.y_bs & 15) || (p.res_bs & 15))
-    return fail(MFC_EINVAL, "conv: weights / output / residual not 16-byte aligned");
-  MFC_LAUNCH(mfc::launch_conv(p, d->dtype == MFC_BF16, (cudaStream_t)stream), "conv2d_fwd");
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc != MFC_OK) return rc;
+  if (best_i < 0) return fail(MFC_EINVAL, "conv_autotune: no candidate ran");
+  {
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    g_plans[key] = cands[best_i];
+    g_tuned.insert(key);
+  }
+  return MFC_OK;
 }
 
 int mfc_gn_finalize(const float* stats, int B, int stats_per_image, int cpad, int C, int groups, long long pixels, const float* gamma,

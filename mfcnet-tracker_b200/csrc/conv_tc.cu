@@ -25,6 +25,9 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cstring>
+#include <utility>
+#include <vector>
 
 namespace mfc {
 
@@ -110,24 +113,35 @@ __device__ __forceinline__ void affine_silu_slot(uint32_t saddr, const float (&s
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// (scale, shift) of the 8 channels of one plane, fetched ahead of use (the L2 round trip of these 64 bytes would
+// otherwise sit in front of every plane's pass)
+struct AffRegs {
+  float2 a[8];
+};
+__device__ __forceinline__ void load_aff(AffRegs& r, const float* __restrict__ aff) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.a[i] = __ldg(reinterpret_cast<const float2*>(aff) + i);
+}
+
 template <bool BF16, int NT>
-__device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* plane, const float* __restrict__ aff, int iy_base,
-                                                int ix_base, int tid) {
+__device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* plane, const AffRegs& ar, int iy_base, int ix_base,
+                                                int tid) {
   const int s = p.stride;
   const int P = p.t.P;
   const int items = p.t.rows_sub * P;
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float2 a = __ldg(reinterpret_cast<const float2*>(aff) + i);
-    sc[i] = 0.5f * a.x;  // silu(y) = h + h*tanh(h) with h = y/2: the halving is folded into the affine
-    sh[i] = 0.5f * a.y;
+    sc[i] = 0.5f * ar.a[i].x;  // silu(y) = h + h*tanh(h) with h = y/2: the halving is folded into the affine
+    sh[i] = 0.5f * ar.a[i].y;
   }
   if (s == 1 && p.upsample == 1) {
     // Four slots per iteration: all four LDS.128 are issued before the first value is needed and the stores come
     // last, so one thread keeps four independent load -> FMA -> MUFU -> FMA -> pack chains in flight (the six
     // producer warps alone cannot hide those latencies by multithreading).
-    const uint32_t H = (uint32_t)p.Hin, W = (uint32_t)p.Win;
+    const uint32_t H = (uint32_t)p.Hin;
+    // columns past the tile's own halo (slide mode pads the row pitch to 128) are never read for a valid output
+    const uint32_t W = (uint32_t)min(p.Win, ix_base + p.t.TW + (p.kw - 1));
     const uint32_t base = smem_u32(plane);
     constexpr int U = 4;
     for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
@@ -250,16 +264,29 @@ __device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* ab
 }
 
 // phase 2 of one (item, K stage)
+// `first` holds the affine of the stage's first plane (prefetch_stage_aff, issued before the wait for the stage's data);
+// the affine of plane q+1 is fetched while plane q is processed.
 template <bool BF16, int NT>
-__device__ __forceinline__ void transform_stage(const ConvParams& p, uint8_t* abuf, int b, int ks, int iy_base, int ix_base, int tid) {
+__device__ __forceinline__ void transform_stage(const ConvParams& p, uint8_t* abuf, int b, int ks, int iy_base, int ix_base, int tid,
+                                                const AffRegs& first) {
   const int ksteps_per_stage = p.t.CBc / 2;
   const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
-  for (int q = 0; q < 2 * nks; ++q) {
-    const int k = ks * p.t.CBc + q;
-    if (k >= p.t.cin_chunks) break;
-    const SrcRef r = locate_plane(p, b, k);
-    if (r.aff) transform_plane<BF16, NT>(p, abuf + (size_t)q * p.t.plane_bytes, r.aff, iy_base, ix_base, tid);
+  const int nq = min(2 * nks, p.t.cin_chunks - ks * p.t.CBc);
+  AffRegs cur = first;
+  for (int q = 0; q < nq; ++q) {
+    const bool has = locate_plane(p, b, ks * p.t.CBc + q).aff != nullptr;
+    AffRegs nxt = cur;
+    if (q + 1 < nq) {
+      const SrcRef rn = locate_plane(p, b, ks * p.t.CBc + q + 1);
+      if (rn.aff) load_aff(nxt, rn.aff);
+    }
+    if (has) transform_plane<BF16, NT>(p, abuf + (size_t)q * p.t.plane_bytes, cur, iy_base, ix_base, tid);
+    cur = nxt;
   }
+}
+__device__ __forceinline__ void prefetch_stage_aff(const ConvParams& p, int b, int ks, AffRegs& first) {
+  const SrcRef r = locate_plane(p, b, ks * p.t.CBc);
+  if (r.aff) load_aff(first, r.aff);
 }
 
 __device__ __forceinline__ void cp_async_wait_dyn(int n) {
@@ -704,15 +731,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     for (int j = 0; j < D; ++j) issue_next();
     while (wt < total_items) {
       if (D == 0) issue_next();
+      const ItemCoord c = decode_item(p, wt);
+      AffRegs aff0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) aff0.a[i] = make_float2(0.0f, 0.0f);
+      if (!(p.debug & 1)) prefetch_stage_aff(p, c.b, kst, aff0);  // in flight while we wait for the stage's data
       if (tma) {
         if (!(p.debug & 1)) mbar_wait_t(&bar_tma[slot_t], phase_t, timed, wait_a);  // the box loads of the hand-off stage have landed
       } else {
         cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // this thread's copies of the hand-off stage have landed
       }
-      const ItemCoord c = decode_item(p, wt);
       if (!(p.debug & 1))
         transform_stage<BF16, kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, c.b, kst,
-                                            c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x, ptid);
+                                            c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x, ptid, aff0);
       fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[slot_t]);
@@ -985,7 +1016,8 @@ int conv_nb(int cout, int* nblk) {
   return nb;
 }
 
-bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
+// Enumerates every feasible tiling of `d` with its modelled cost (SM cycles for the whole layer).
+static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, ConvTiling>>& all) {
   const int s = d.stride;
   const int hy = (d.kh - 1) / s, hx = (d.kw - 1) / s;
   int cin_chunks = 0;
@@ -1009,9 +1041,6 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
   const uint32_t off_bres = (off_stats + (cpad <= 256 ? (uint32_t)kEpiWarps * cpad * 8 : 0u) + 127) & ~127u;
   static const int force_slide = getenv("MFC_CONV_SLIDE") ? atoi(getenv("MFC_CONV_SLIDE")) : -1;  // measurement: 0 never, 1 always
   const bool slide_ok = s == 1 && d.kh > 1 && nblk == 1 && d.kh * NB <= 256 && d.out_stride != 2 && force_slide != 0;
-  double best_cost = 1e300;
-  bool found = false;
-
   // evaluates one tile shape; slide = sliding-accumulate mode (P must be 128: one MMA run per input row)
   auto consider = [&](int TH, int TW, int nx, bool slide) -> bool {  // false: TH too large for this TW (stop growing it)
     const int P = slide ? 128 : TW + hx;
@@ -1059,9 +1088,14 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
       //              dependent accumulate chain costs 167 per MMA divided by the accumulators in rotation
       //   epilogue : ~400 per item + ~475 per (run, 16-column) step of a warp
       const double load_items = (double)cin_chunks * s * s * rows_sub * P;
-      // with TMA the raw copy costs the producer warps nothing (one elected thread issues one box load per plane,
-      // ~0.4 cycles per slot of data-path time); only the in-place affine+SiLU pass is per-slot thread work
-      const double L = tma ? 300.0 * kstages + load_items * (any_aff ? 1.2 : 0.4) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.1)
+      // TMA: the raw copy costs the producer warps nothing, but the data path delivers ~13 bytes/clk per SM when all
+      // SMs pull (measured: 74 KB stages landing in 5.6k cycles); the in-place affine+SiLU pass is SFU-bound at ~1 cycle
+      // per slot on six warps.  The two overlap only when the ring is deep enough to keep a load in flight during a
+      // pass (the next load is issued after a hand-off, so a 2-deep ring exposes the whole load latency).
+      const double xf_items = (double)cin_chunks * rows_sub * std::min(P, TW + hx);
+      const double t_tma = 500.0 * kstages + load_items * 1.2 + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 1.2);
+      const double t_xf = any_aff ? 500.0 * kstages + xf_items * 1.0 : 0.0;
+      const double L = tma ? (nstages >= 3 ? std::max(t_tma, t_xf) : t_tma + t_xf)
                            : 600.0 * kstages + load_items * (any_aff ? 3.0 : 2.0) + (resident ? 0.0 : (double)(w_bytes_nblk / 16) * 0.5);
       double M;
       if (slide) {
@@ -1094,9 +1128,9 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
         per_item = L + std::max(M, E) + (nacc == 2 ? 0.0 : std::min(M, E));
       }
       const double cost = (rounds - 1.0) * per_item + (L + M + E) + (resident ? (double)(w_bytes_nblk / 16) * 0.3 : 0.0);
-      if (cost < best_cost) {
-        best_cost = cost;
-        found = true;
+      {
+        ConvTiling best;
+        memset(&best, 0, sizeof(best));
         best.TH = TH; best.TW = TW; best.P = P; best.R = R; best.rows_sub = rows_sub; best.slots_sub = slots_sub;
         best.CBc = CBc; best.kstages = kstages; best.nstages = nstages; best.nacc = nacc; best.kacc = kacc; best.pair = pair ? 1 : 0;
         best.entries = entries; best.b_resident = resident ? 1 : 0; best.tma = tma ? 1 : 0;
@@ -1108,6 +1142,7 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
         best.smem_bytes = smem; best.tmem_cols = tmem; best.acc_cols = (uint32_t)(R * NB * kacc);
         best.off_scale = off_scale; best.off_stats = off_stats; best.off_bres = off_bres; best.off_stage = (uint32_t)off_stage;
         best.grid = G;
+        all.emplace_back(cost, best);
       }
     }
     return true;
@@ -1131,7 +1166,34 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
         if (!consider(TH, TW, nx, true)) break;
     }
   }
-  return found;
+}
+
+bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
+  std::vector<std::pair<double, ConvTiling>> all;
+  conv_enumerate(d, all);
+  if (all.empty()) return false;
+  size_t bi = 0;
+  for (size_t i = 1; i < all.size(); ++i)
+    if (all[i].first < all[bi].first) bi = i;
+  best = all[bi].second;
+  return true;
+}
+
+// Candidates worth MEASURING (mfc_conv2d_autotune): the model's best few in every (weight layout, ring depth class)
+// bucket, so that a systematic error of the model in one dimension cannot hide the real optimum.
+void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling>& out) {
+  std::vector<std::pair<double, ConvTiling>> all;
+  conv_enumerate(d, all);
+  std::sort(all.begin(), all.end(), [](const std::pair<double, ConvTiling>& a, const std::pair<double, ConvTiling>& b) { return a.first < b.first; });
+  int taken[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  for (const auto& c : all) {
+    const ConvTiling& t = c.second;
+    const int depth = t.nstages >= 3 ? 2 : t.nstages - 1;
+    int& n = taken[t.slide ? 1 : 0][depth];
+    if (n >= per_bucket) continue;
+    ++n;
+    out.push_back(t);
+  }
 }
 
 template <bool BF16, int MODE, bool NB16>

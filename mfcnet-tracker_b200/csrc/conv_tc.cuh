@@ -1,5 +1,7 @@
 // conv_tc.cuh -- parameters shared by the tcgen05 implicit-GEMM convolution kernel and its host planner.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "../../include/mfcnet_b200.h"
 
@@ -83,5 +85,6 @@ struct ConvParams {
 // host planner
 int conv_nb(int cout, int* nblk);
 bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& out);
+void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling>& out);
 
 }  // namespace mfc

@@ -26,6 +26,15 @@ def default_dtype():
     return os.environ.get("MFC_B200_DTYPE", "fp16")
 
 
+def autotune_enabled():
+    """MFC_CONV_TUNE=0 disables the plan-time measurement of conv tilings (the cost model's choice is used)."""
+    return os.environ.get("MFC_CONV_TUNE", "1") != "0"
+
+
+def autotune_reps():
+    return max(1, int(os.environ.get("MFC_CONV_TUNE_REPS", "3")))
+
+
 def require_cuda(t, what):
     if not t.is_cuda and not abi.plan_only():
         raise RuntimeError("%s: mfcnet_tracker_b200 runs on a B200 only; got a %s tensor (there is no CPU fallback)"
@@ -492,7 +501,6 @@ class Builder:
         at the given offsets).  Returns (Act|None, stats|None, info, io)."""
         Cout = w_oihw.shape[0]
         d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity)
-        info = self.prog.query(d)
         layout = []
         off = 0
         for i, s in enumerate(srcs):
@@ -503,10 +511,54 @@ class Builder:
         cmap = None if identity else chan_map_for(layout)
         if shift is None and bias is not None:
             shift = bias
+        if autotune_enabled() and self.device.type == "cuda" and not abi.plan_only():
+            self._autotune(d, srcs, w_oihw, cmap, scale is not None, shift is not None, residual, want_stats, out_c8, out_nchw, y_c8)
+        info = self.prog.query(d)
         packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift)
         out, stats, io = self.prog.conv(d, info, srcs, packed, residual=residual, want_stats=want_stats, out_c8=out_c8,
                                         out_nchw=out_nchw, arena=self.arena, y_c8=y_c8, name=key)
         return out, stats, info, io
+
+    def _autotune(self, d, srcs, w_oihw, cmap, has_scale, has_shift, residual, want_stats, out_c8, out_nchw, y_c8):
+        """Plan-time measurement of the candidate tilings of this conv on the device, with buffers of the real sizes and
+        the real epilogue mode (mfc_conv2d_autotune keeps the fastest; temporaries are released afterwards)."""
+        lib = self.prog.lib
+        info = self.prog.query(d)
+        dev = self.device
+        cpad = info.nb * info.nblk
+        io = abi.MfcConvIO()
+        keep = []
+
+        def tmp(shape, dtype, fill=None):
+            t = torch.empty(shape, dtype=dtype, device=dev) if fill is None else torch.full(shape, fill, dtype=dtype, device=dev)
+            keep.append(t)
+            return t
+
+        os_ = 2 if d.out_stride == 2 else 1
+        if has_scale:
+            io.scale = tmp((cpad,), torch.float32, 1.0).data_ptr()
+        if has_shift:
+            io.shift = tmp((cpad,), torch.float32, 0.0).data_ptr()
+        if residual is not None:
+            io.residual = residual.t.data_ptr()
+            io.res_affine = abi.ptr(residual.affine)
+            io.res_batch_stride = residual.bstride
+        if out_c8:
+            y = y_c8 if y_c8 is not None else tmp((d.B, (d.Cout + 7) // 8, d.Hout * os_, d.Wout * os_, 8), self.tdtype)
+            io.y_c8 = y.data_ptr()
+            io.y_batch_stride = y.stride(0) * y.element_size()
+        if out_nchw is not None:
+            io.y_nchw = out_nchw.data_ptr()
+        if want_stats:
+            io.stats = tmp((d.B, 148, cpad, 2), torch.float32).data_ptr()
+        w = w_oihw.detach().contiguous().float()
+        cm = torch.tensor(cmap, dtype=torch.int32, device=dev) if cmap is not None else None
+        scratch = tmp((int(info.packed_weight_bytes),), torch.uint8)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        abi.check(lib.mfc_conv2d_autotune(C.byref(d), C.byref(io), w.data_ptr(), w.shape[1], abi.ptr(cm), scratch.data_ptr(),
+                                          autotune_reps(), stream))
+        torch.cuda.current_stream(dev).synchronize()
+        del keep
 
     def group_norm_affine(self, stats, info, gamma, beta, C_, groups, pixels, eps=1e-5):
         """Finalise GroupNorm statistics into the pending affine of the producing conv's output."""
