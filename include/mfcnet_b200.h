@@ -133,9 +133,11 @@ typedef struct MfcConvDesc {
    * is read as 1) and zero offsets = an ordinary conv. */
   int in_off_y, in_off_x;
   int out_stride, out_off_y, out_off_x;
-  int reserved;
+  int reserved;            /* flags: MFC_CONV_HAS_RESIDUAL when mfc_conv2d_fwd will be given io->residual (the plan then
+                              reserves the shared-memory prefetch rings for it)                                        */
   MfcSrc src[MFC_MAX_SRC];
 } MfcConvDesc;
+#define MFC_CONV_HAS_RESIDUAL 1
 
 int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info);
 

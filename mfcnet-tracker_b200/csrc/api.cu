@@ -62,7 +62,7 @@ int arch_ok() {
 inline bool dtype_ok(int dt) { return dt == MFC_F16 || dt == MFC_BF16; }
 
 // ---- conv planner cache ---------------------------------------------------------------------
-using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int>;
+using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int, int>;
 std::mutex g_plan_mu;
 std::map<PlanKey, mfc::ConvTiling> g_plans;
 
@@ -105,7 +105,8 @@ PlanKey plan_key(const MfcConvDesc* d) {
     chunks += d->src[i].nchunks;
     aff |= d->src[i].affine != nullptr;
   }
-  return PlanKey{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks, aff};
+  return PlanKey{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks, aff,
+                 d->reserved & MFC_CONV_HAS_RESIDUAL};
 }
 
 int get_tiling(const MfcConvDesc* d, mfc::ConvTiling* out) {
@@ -179,6 +180,8 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.upsample = d->upsample; p.act = d->act;
   p.in_off_y = d->in_off_y; p.in_off_x = d->in_off_x; p.out_stride = d->out_stride == 2 ? 2 : 1;
   p.out_off_y = d->out_off_y; p.out_off_x = d->out_off_x;
+  if ((io->residual != nullptr) != ((d->reserved & MFC_CONV_HAS_RESIDUAL) != 0))
+    return fail(MFC_EINVAL, "conv: io->residual and the descriptor's MFC_CONV_HAS_RESIDUAL flag disagree");
   if (p.out_stride == 2 && (io->residual || io->stats)) return fail(MFC_EINVAL, "conv: transposed-conv parity mode has no residual / statistics");
   p.nsrc = d->nsrc;
   int end = 0;

@@ -372,6 +372,65 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   return v;
 }
 
+struct ItemCoord {
+  int b, oy0, ox0, nbk, tile_lin;
+};
+__device__ __forceinline__ ItemCoord decode_item(const ConvParams& p, int w) {
+  ItemCoord c;
+  uint32_t tile = fdiv((uint32_t)w, p.div_nblk);
+  c.nbk = w - (int)tile * p.t.nblk;
+  c.tile_lin = (int)tile;
+  uint32_t t2 = fdiv(tile, p.div_tx);
+  const int tx = (int)(tile - t2 * (uint32_t)p.t.tiles_x);
+  const uint32_t bb = fdiv(t2, p.div_ty);
+  const int ty = (int)(t2 - bb * (uint32_t)p.t.tiles_y);
+  c.b = (int)bb;
+  c.oy0 = ty * p.t.TH;
+  c.ox0 = tx * p.t.TW;
+  return c;
+}
+
+// Residual prefetch ring of one epilogue warp.  The residual tile of a step (32 lanes x two 16-byte planes = 1 KB) is
+// copied global -> shared with cp.async kResDepth steps ahead of its use -- across work items, the addresses do not
+// depend on the MMAs -- so that 4 KB per warp (32 KB per SM) of residual reads are always in flight; a one-step register
+// prefetch (1 KB per warp) left these layers bound by load latency.  Every lane reads back only what it copied itself,
+// so cp.async.wait_group is the only synchronisation.
+struct ResPrefetch {
+  uint32_t ring;   // shared address of this warp's ring: [kResDepth][2 planes][32 lanes] x 16 bytes
+  int w, r, j;     // prefetch cursor: work item, run, first output channel of the step
+  uint32_t head;   // steps issued (ring slot = count % kResDepth)
+  uint32_t tail;   // steps consumed
+};
+__device__ __forceinline__ void res_prefetch_step(const ConvParams& p, ResPrefetch& rp, int total_items, int lq, int half, int lane,
+                                                  int NB) {
+  if (rp.w < total_items) {
+    const ItemCoord c = decode_item(p, rp.w);
+    const PixRef q = run_pixel(p, rp.r, lq, lane, c.oy0, c.ox0);
+    const int cc_out = (p.Cout + 7) >> 3;
+    const size_t HWo = (size_t)p.Hout * p.Wout * p.out_stride * p.out_stride;
+    const uint8_t* res_b = p.res + (size_t)c.b * p.res_bs;
+    const int ch0 = (c.nbk * NB + rp.j) >> 3;
+    const uint32_t dst = rp.ring + ((rp.head % kResDepth) * 64u + (uint32_t)lane) * 16u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const bool ok = q.valid && ch0 + h < cc_out;
+      const uint8_t* src = ok ? res_b + ((size_t)(ch0 + h) * HWo + q.pix) * 16 : p.res;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)h * 512u), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    rp.j += 16;
+    if (rp.j >= NB) {
+      rp.j = 0;
+      rp.r += 2;
+      if (rp.r >= p.t.R) {
+        rp.r = half;
+        rp.w += gridDim.x;
+      }
+    }
+  }
+  cp_async_commit();  // one group per step, empty or not: keeps wait_group(kResDepth-1) exact
+  ++rp.head;
+}
+
 // Epilogue of one work item: TMEM accumulators -> scale/shift -> residual -> ReLU -> GroupNorm partial
 // sums -> C8 / NCHW stores.  Called by 8 warps: `lq` = TMEM lane quarter of the warp (hardware: warp id % 4),
 // `half` = which of the two interleaved run sets (r = half, half+2, ...) the warp owns.
@@ -383,7 +442,8 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
 template <bool BF16, int MODE, bool NB16>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem_acc, uint32_t s_scale_addr, float* my_stats,
                                               float (&d1)[16], float (&d2)[16], const float (&sc)[16], const float (&sh)[16], int b,
-                                              int oy0, int ox0, int nbk, int lq, int half, int lane, bool res_aff_smem) {
+                                              int oy0, int ox0, int nbk, int lq, int half, int lane, bool res_aff_smem, ResPrefetch& rp,
+                                              int total_items) {
   constexpr bool kRes = MODE == EPI_RES || MODE == EPI_GENERIC;
   constexpr bool kStats = MODE == EPI_STATS || MODE == EPI_GENERIC;
   constexpr bool kNchw = MODE == EPI_NCHW || MODE == EPI_GENERIC;
@@ -395,26 +455,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   const bool has_stats = kStats && p.stats != nullptr;
   const bool has_nchw = kNchw && p.y_nchw != nullptr;
   const bool has_c8 = (MODE != EPI_NCHW && MODE != EPI_GENERIC) || p.y != nullptr;
-  const uint8_t* res_b = has_res ? p.res + (size_t)b * p.res_bs : nullptr;
   uint8_t* y_b = has_c8 ? p.y + (size_t)b * p.y_bs : nullptr;
   const uint32_t tm_lane = tmem_acc + ((uint32_t)(lq * 32) << 16);
   int r = half, j = 0;
   if (r >= p.t.R) return;
   uint32_t acc[16];
   tmem_ld16(tm_lane + (uint32_t)(r * NB + j), acc);
-  uint4 rv_next[2];
-  rv_next[0] = rv_next[1] = make_uint4(0, 0, 0, 0);
-  auto fetch_res = [&](int rr, int jj) {
-    // residual of step (rr, jj): issued one step ahead so that its latency hides behind the current step
-    const PixRef q = run_pixel(p, rr, lq, lane, oy0, ox0);
-    const int co0 = nbk * NB + jj;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ch = (co0 >> 3) + h;
-      rv_next[h] = (q.valid && ch < cc_out) ? ldg_nc16(res_b + ((size_t)ch * HWo + q.pix) * 16) : make_uint4(0, 0, 0, 0);
-    }
-  };
-  if (has_res) fetch_res(r, j);
   while (true) {
     const PixRef q = run_pixel(p, r, lq, lane, oy0, ox0);
     const bool valid = q.valid;
@@ -427,10 +473,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     }
     const bool more = r2 < p.t.R;
     uint4 rv[2];
-    if (kRes) {
-      rv[0] = rv_next[0];
-      rv[1] = rv_next[1];
-      if (has_res && more) fetch_res(r2, j2);
+    if (kRes && has_res && !(p.debug & 16)) {
+      cp_async_wait_group<kResDepth - 1>();  // the oldest step in the ring (this one) has landed
+      const uint32_t src = rp.ring + ((rp.tail % kResDepth) * 64u + (uint32_t)lane) * 16u;
+      rv[0] = lds16_u32(src);
+      rv[1] = lds16_u32(src + 512u);
+      ++rp.tail;
     }
     tmem_ld_wait();
     if (p.t.slide) tmem_st16_zero(tm_lane + (uint32_t)(r * NB + j));  // slide mode accumulates into zeroed columns
@@ -466,7 +514,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
         if (ch < cc_out) {
           float rf[8];
           unpack8<BF16>(rv[h], rf);
-          if (p.res_aff) {
+          if (p.res_aff && !(p.debug & 64)) {
             if (res_aff_smem) {
               // (s/2, t/2) of this sample's channels parked in the warp's smem slot: silu(y) = h + h*tanh(h), h = y/2
               const uint32_t sa = smem_u32(my_stats) + (uint32_t)(co0 + h * 8) * 8u;
@@ -521,7 +569,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
         }
       }
     }
-    if (valid) {
+    if (valid && !(p.debug & 32)) {
       if (has_c8) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -543,6 +591,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
         }
       }
     }
+    if (kRes && has_res && !(p.debug & 16)) res_prefetch_step(p, rp, total_items, lq, half, lane, NB);  // refills the ring slot just consumed
     if (!more) break;
     r = r2;
     j = j2;
@@ -589,24 +638,6 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   acc += clock64() - t0;
-}
-
-struct ItemCoord {
-  int b, oy0, ox0, nbk, tile_lin;
-};
-__device__ __forceinline__ ItemCoord decode_item(const ConvParams& p, int w) {
-  ItemCoord c;
-  uint32_t tile = fdiv((uint32_t)w, p.div_nblk);
-  c.nbk = w - (int)tile * p.t.nblk;
-  c.tile_lin = (int)tile;
-  uint32_t t2 = fdiv(tile, p.div_tx);
-  const int tx = (int)(tile - t2 * (uint32_t)p.t.tiles_x);
-  const uint32_t bb = fdiv(t2, p.div_ty);
-  const int ty = (int)(t2 - bb * (uint32_t)p.t.tiles_y);
-  c.b = (int)bb;
-  c.oy0 = ty * p.t.TH;
-  c.ox0 = tx * p.t.TW;
-  return c;
 }
 
 template <bool BF16, int MODE, bool NB16>
@@ -902,6 +933,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     }
     int cur_b = -1, aff_b = -1;
     const bool res_aff_smem = (MODE == EPI_RES || MODE == EPI_GENERIC) && p.res != nullptr && p.res_aff != nullptr && !has_stats && cpad <= 256;
+    ResPrefetch rp;
+    rp.ring = smem_u32(smem + p.t.off_resring) + (uint32_t)warp * (kResDepth * 1024u);
+    rp.w = blockIdx.x;
+    rp.r = half;
+    rp.j = 0;
+    rp.head = rp.tail = 0;
+    if ((MODE == EPI_RES || MODE == EPI_GENERIC) && p.res != nullptr && half < p.t.R) {
+      for (int i = 0; i < kResDepth; ++i) res_prefetch_step(p, rp, total_items, lq, half, lane, NB);
+    }
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
       const ItemCoord c = decode_item(p, w);
       if (has_stats && c.b != cur_b) {
@@ -925,7 +965,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
       if (!(p.debug & 2))
         epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
-                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem);
+                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem, rp, total_items);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc_i]);
@@ -1038,7 +1078,9 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
   const uint32_t cpad = (uint32_t)(NB * nblk);
   const uint32_t off_scale = 256;
   const uint32_t off_stats = off_scale + cpad * 8;
-  const uint32_t off_bres = (off_stats + (cpad <= 256 ? (uint32_t)kEpiWarps * cpad * 8 : 0u) + 127) & ~127u;
+  const bool has_res = (d.reserved & MFC_CONV_HAS_RESIDUAL) != 0;
+  const uint32_t off_resring = (off_stats + (cpad <= 256 ? (uint32_t)kEpiWarps * cpad * 8 : 0u) + 127) & ~127u;
+  const uint32_t off_bres = off_resring + (has_res ? (uint32_t)kEpiWarps * kResDepth * 1024u : 0u);
   static const int force_slide = getenv("MFC_CONV_SLIDE") ? atoi(getenv("MFC_CONV_SLIDE")) : -1;  // measurement: 0 never, 1 always
   const bool slide_ok = s == 1 && d.kh > 1 && nblk == 1 && d.kh * NB <= 256 && d.out_stride != 2 && force_slide != 0;
   // evaluates one tile shape; slide = sliding-accumulate mode (P must be 128: one MMA run per input row)
@@ -1140,7 +1182,7 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
         best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;
         best.stage_bytes = (uint32_t)stage_bytes;
         best.smem_bytes = smem; best.tmem_cols = tmem; best.acc_cols = (uint32_t)(R * NB * kacc);
-        best.off_scale = off_scale; best.off_stats = off_stats; best.off_bres = off_bres; best.off_stage = (uint32_t)off_stage;
+        best.off_scale = off_scale; best.off_stats = off_stats; best.off_resring = off_resring; best.off_bres = off_bres; best.off_stage = (uint32_t)off_stage;
         best.grid = G;
         all.emplace_back(cost, best);
       }

@@ -17,6 +17,7 @@ constexpr int kProdWarps = 6;                      // 16 warps = 512 threads: 12
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kConvThreads = (kEpiWarps + kMmaWarps + kProdWarps) * 32;
 constexpr int kMaxStages = 8;
+constexpr int kResDepth = 4;                       // residual prefetch ring depth (steps) of an epilogue warp
 
 struct ConvTiling {
   int TH, TW;        // output tile
@@ -52,6 +53,7 @@ struct ConvTiling {
   uint32_t smem_bytes;
   uint32_t tmem_cols;      // allocated (power of two >= 32)
   uint32_t acc_cols;       // kacc * R * NB, columns of one accumulator buffer
+  uint32_t off_resring;    // residual prefetch rings of the epilogue warps (only with MFC_CONV_HAS_RESIDUAL)
   uint32_t off_scale, off_stats, off_bres, off_stage;  // smem carve-up (bytes from the 128B-aligned base)
   int grid;                // persistent CTAs
 };

@@ -501,6 +501,8 @@ class Builder:
         at the given offsets).  Returns (Act|None, stats|None, info, io)."""
         Cout = w_oihw.shape[0]
         d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity)
+        if residual is not None:
+            d.reserved |= abi.MFC_CONV_HAS_RESIDUAL
         layout = []
         off = 0
         for i, s in enumerate(srcs):
