@@ -175,10 +175,11 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream);
 /* Plan-time autotuning: measures the planner's shortlisted tilings (tile shape, K staging, weight layout) of `d` on the
  * device with the caller's real buffers and keeps the fastest for every later mfc_conv2d_query / _pack_weights / _fwd of
  * the same geometry.  io->w_packed is ignored; the raw OIHW weights are packed into `scratch_packed`
- * (packed_weight_bytes of mfc_conv2d_query) once per weight layout.  io->stats, when given, must hold
+ * (`scratch_bytes`: twice the packed_weight_bytes of mfc_conv2d_query covers every candidate; candidates that do not fit are
+ * skipped) once per weight image.  io->stats, when given, must hold
  * [B][148][nb*nblk][2] floats.  Synchronises `stream`.  Idempotent per geometry; call it BEFORE mfc_conv2d_query. */
 int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* w_oihw, int Cin_w, const int* chan_map,
-                        void* scratch_packed, int reps, void* stream);
+                        void* scratch_packed, long long scratch_bytes, int reps, void* stream);
 
 /* GroupNorm statistics -> per-(sample,channel) affine.  Replaces nn.GroupNorm
  * (models/resunet.py:72,77) split in two: partial sums come from the producing conv's
@@ -404,6 +405,14 @@ int mfc_run_list(const MfcCmd* cmds, int n, void* stream);
  * `stream` around every command; synchronises the stream and writes each command's device time
  * in milliseconds to ms_out[n].  This is the one entry point that creates events and blocks. */
 int mfc_run_list_timed(const MfcCmd* cmds, int n, void* stream, float* ms_out);
+
+/* CUDA-graph replay of a command list whose pointers are all static: capture once (on a private stream; kernels are not
+ * executed), then one mfc_graph_launch per step on the caller's stream.  The graph holds copies of all kernel arguments;
+ * the buffers they point to must stay alive and in place. */
+int mfc_graph_capture(const MfcCmd* cmds, int n, void** graph_out);
+int mfc_graph_launch(void* graph, void* stream);
+int mfc_graph_destroy(void* graph);
+
 
 #ifdef __cplusplus
 }

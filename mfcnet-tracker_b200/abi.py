@@ -111,7 +111,7 @@ _SIGNATURES = {
     "mfc_conv2d_query": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvInfo)], c_int),
     "mfc_conv2d_pack_weights": ([C.POINTER(MfcConvDesc), c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "mfc_conv2d_fwd": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p], c_int),
-    "mfc_conv2d_autotune": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p], c_int),
+    "mfc_conv2d_autotune": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p], c_int),
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
     "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p], c_int),
     "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),
@@ -129,6 +129,9 @@ _SIGNATURES = {
     "mfc_trace_contours": ([c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "mfc_run_list": ([C.POINTER(MfcCmd), c_int, c_void_p], c_int),
     "mfc_run_list_timed": ([C.POINTER(MfcCmd), c_int, c_void_p, C.POINTER(c_float)], c_int),
+    "mfc_graph_capture": ([C.POINTER(MfcCmd), c_int, C.POINTER(c_void_p)], c_int),
+    "mfc_graph_launch": ([c_void_p, c_void_p], c_int),
+    "mfc_graph_destroy": ([c_void_p], c_int),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -324,7 +324,7 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
  * `scratch_packed` (packed_weight_bytes of mfc_conv2d_query) once per weight layout.  io->stats, when given, must hold
  * [B][148][nb*nblk][2] floats (any candidate's grid fits).  Synchronises the stream.  Idempotent per geometry. */
 int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* w_oihw, int Cin_w, const int* chan_map,
-                        void* scratch_packed, int reps, void* stream) {
+                        void* scratch_packed, long long scratch_bytes, int reps, void* stream) {
   MFC_REQUIRE_ARCH();
   int rc = validate_desc(d);
   if (rc != MFC_OK) return rc;
@@ -344,11 +344,16 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
   tio.w_packed = scratch_packed;
   float best_ms = 1e30f;
   int best_i = -1;
-  for (int layout = 0; layout < 2 && rc == MFC_OK; ++layout) {
+  // candidates are measured grouped by weight image (layout, N-block width): one packing per group
+  std::vector<char> done(cands.size(), 0);
+  for (size_t g0 = 0; g0 < cands.size() && rc == MFC_OK; ++g0) {
+    if (done[g0]) continue;
     bool packed = false;
-    for (size_t i = 0; i < cands.size() && rc == MFC_OK; ++i) {
+    for (size_t i = g0; i < cands.size() && rc == MFC_OK; ++i) {
       const mfc::ConvTiling& t = cands[i];
-      if (t.slide != layout) continue;
+      if (done[i] || t.slide != cands[g0].slide || t.NB != cands[g0].NB) continue;
+      done[i] = 1;
+      if ((long long)t.nblk * t.ksteps * t.entries * 2 * t.nrows_b * 16 > scratch_bytes) continue;
       if (!packed) {
         cudaError_t e = mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,
                                                  t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, scratch_packed,
@@ -357,6 +362,10 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
         packed = true;
       }
       if (rc == MFC_OK) rc = conv_fwd_tiled(d, &tio, t, stream);  // warm-up (instruction cache, L2 state)
+      if (rc == MFC_EINVAL) {  // this candidate does not support the requested epilogue (e.g. statistics with a padded Cout > 256)
+        rc = MFC_OK;
+        continue;
+      }
       cudaEventRecord(e0, st);
       for (int r = 0; r < reps && rc == MFC_OK; ++r) rc = conv_fwd_tiled(d, &tio, t, stream);
       cudaEventRecord(e1, st);
@@ -565,6 +574,50 @@ int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
     }
   }
   return MFC_OK;
+}
+
+// ---- CUDA graphs ---------------------------------------------------------------------------------
+// A command list whose pointers are all static (the streaming runner's per-slot programs) is captured once and replayed
+// with ONE cudaGraphLaunch per frame: the ~350 launches of an HRNet frame are latency-bound when issued one by one from
+// the host.  Capture happens on a private stream (the caller's stream may be the legacy default stream, which cannot be
+// captured); programmatic-dependent-launch attributes become programmatic edges of the graph.
+int mfc_graph_capture(const MfcCmd* cmds, int n, void** graph_out) {
+  MFC_REQUIRE_ARCH();
+  if (!cmds || n < 1 || !graph_out) return fail(MFC_EINVAL, "graph_capture: bad argument");
+  *graph_out = nullptr;
+  cudaStream_t cs;
+  cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return cuda_fail(e, "graph_capture: cudaStreamCreate");
+  e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(cs);
+    return cuda_fail(e, "graph_capture: cudaStreamBeginCapture");
+  }
+  const int rc = mfc_run_list(cmds, n, cs);
+  cudaGraph_t g = nullptr;
+  e = cudaStreamEndCapture(cs, &g);
+  cudaStreamDestroy(cs);
+  if (rc != MFC_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  if (e != cudaSuccess || !g) return cuda_fail(e, "graph_capture: cudaStreamEndCapture");
+  cudaGraphExec_t ex = nullptr;
+  e = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return cuda_fail(e, "graph_capture: cudaGraphInstantiate");
+  *graph_out = (void*)ex;
+  return MFC_OK;
+}
+
+int mfc_graph_launch(void* graph, void* stream) {
+  if (!graph) return fail(MFC_EINVAL, "graph_launch: null graph");
+  MFC_LAUNCH(cudaGraphLaunch((cudaGraphExec_t)graph, (cudaStream_t)stream), "graph_launch");
+}
+
+int mfc_graph_destroy(void* graph) {
+  if (!graph) return MFC_OK;
+  MFC_LAUNCH(cudaGraphExecDestroy((cudaGraphExec_t)graph), "graph_destroy");
 }
 
 int mfc_run_list_timed(const MfcCmd* cmds, int n, void* stream, float* ms_out) {

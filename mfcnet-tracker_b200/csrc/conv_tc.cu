@@ -1073,8 +1073,20 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
   // hardware zero fill outside the image); box extents are limited to 256 per dimension
   const bool tma = s == 1 && d.upsample == 1;
   const int ksteps = ceil_div(cin_chunks, 2);
-  int nblk;
-  const int NB = conv_nb(d.Cout, &nblk);
+  // N-block width: by default as wide as possible (<= 128).  Layers with few pixels (the low-resolution HRNet / bottleneck
+  // stages) produce fewer work items than there are SMs; narrower N-blocks multiply the items and divide the weights each
+  // CTA has to stream, so they are offered as candidates there (the autotuner measures them).
+  int nblk0;
+  const int NB0 = conv_nb(d.Cout, &nblk0);
+  int nb_opts[3] = {NB0, 0, 0};
+  int n_opts = 1;
+  if ((long long)d.B * d.Hout * d.Wout < 128LL * 4 * kSmCount) {
+    if (NB0 > 64) nb_opts[n_opts++] = 64;
+    if (NB0 > 32) nb_opts[n_opts++] = 32;
+  }
+  for (int oi_nb = 0; oi_nb < n_opts; ++oi_nb) {
+  const int NB = nb_opts[oi_nb];
+  const int nblk = ceil_div(d.Cout, NB);
   const uint32_t cpad = (uint32_t)(NB * nblk);
   const uint32_t off_scale = 256;
   const uint32_t off_stats = off_scale + cpad * 8;
@@ -1208,6 +1220,7 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
         if (!consider(TH, TW, nx, true)) break;
     }
   }
+  }  // N-block options
 }
 
 bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
@@ -1227,11 +1240,16 @@ void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling
   std::vector<std::pair<double, ConvTiling>> all;
   conv_enumerate(d, all);
   std::sort(all.begin(), all.end(), [](const std::pair<double, ConvTiling>& a, const std::pair<double, ConvTiling>& b) { return a.first < b.first; });
-  int taken[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  int taken[2][3][3] = {};
+  int nb_seen[3] = {0, 0, 0};
   for (const auto& c : all) {
     const ConvTiling& t = c.second;
     const int depth = t.nstages >= 3 ? 2 : t.nstages - 1;
-    int& n = taken[t.slide ? 1 : 0][depth];
+    int nbi = 0;
+    while (nbi < 3 && nb_seen[nbi] != 0 && nb_seen[nbi] != t.NB) ++nbi;
+    if (nbi == 3) continue;
+    nb_seen[nbi] = t.NB;
+    int& n = taken[t.slide ? 1 : 0][depth][nbi];
     if (n >= per_bucket) continue;
     ++n;
     out.push_back(t);

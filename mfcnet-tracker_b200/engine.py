@@ -175,6 +175,15 @@ class Program:
             stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
         abi.check(self.lib.mfc_run_list(self._array, len(self.cmds), stream))
 
+    def capture(self):
+        """Capture this program into a CUDA graph (all of its pointers must be static from now on)."""
+        if self._array is None:
+            self.finalize()
+        g = C.c_void_p()
+        with device_guard(self.device):
+            abi.check(self.lib.mfc_graph_capture(self._array, len(self.cmds), C.byref(g)))
+        return Graph(self.lib, g, self)
+
     def run_timed(self, stream=None):
         """Measurement only: runs the list with CUDA events around every command and returns
         the per-command meta dicts with an added 'ms' (device milliseconds).  Synchronises."""
@@ -398,6 +407,25 @@ class Program:
         self._push(abi.OP_WARP, args, meta={"kind": "flow_warp", "name": "", "flops": 0, "bytes": nbytes})
 
 
+class Graph:
+    """An instantiated CUDA graph of one Program (keeps the program, hence every buffer it points to, alive)."""
+
+    def __init__(self, lib, handle, prog):
+        self.lib, self.handle, self.prog = lib, handle, prog
+
+    def launch(self, stream=None):
+        if stream is None:
+            stream = torch.cuda.current_stream(self.prog.device).cuda_stream
+        abi.check(self.lib.mfc_graph_launch(self.handle, stream))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.mfc_graph_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class PackedConv:
     __slots__ = ("w", "scale", "shift")
 
@@ -527,7 +555,7 @@ class Builder:
         lib = self.prog.lib
         info = self.prog.query(d)
         dev = self.device
-        cpad = info.nb * info.nblk
+        cpad = d.Cout + 256      # upper bound over the N-block widths the tuner may try
         io = abi.MfcConvIO()
         keep = []
 
@@ -555,10 +583,10 @@ class Builder:
             io.stats = tmp((d.B, 148, cpad, 2), torch.float32).data_ptr()
         w = w_oihw.detach().contiguous().float()
         cm = torch.tensor(cmap, dtype=torch.int32, device=dev) if cmap is not None else None
-        scratch = tmp((int(info.packed_weight_bytes),), torch.uint8)
+        scratch = tmp((2 * int(info.packed_weight_bytes) + 4096,), torch.uint8)
         stream = torch.cuda.current_stream(dev).cuda_stream
         abi.check(lib.mfc_conv2d_autotune(C.byref(d), C.byref(io), w.data_ptr(), w.shape[1], abi.ptr(cm), scratch.data_ptr(),
-                                          autotune_reps(), stream))
+                                          scratch.numel(), autotune_reps(), stream))
         torch.cuda.current_stream(dev).synchronize()
         del keep
 

@@ -11,6 +11,8 @@ channel concat is a rotation of pointers, not a copy.
 ``shard_frames`` splits a video of F frames into contiguous clips, one per GPU, each preceded by a
 K-1-frame halo that only fills the ring (no collective on the inference path).
 """
+import os
+
 import torch
 
 from . import engine
@@ -55,65 +57,82 @@ class StreamingMFCNet:
         self.ring = torch.zeros((K, (N + 7) // 8, H, W, 8), dtype=tdtype, device=dev)   # slot s holds frame t with t % K == s
         self.x_c8 = torch.empty((1, (cin + 7) // 8, H, W, 8), dtype=tdtype, device=dev)
         self.out = torch.empty((1, N, H, W), dtype=torch.float32, device=dev)
-        ph = torch.zeros((1, cin, H, W), dtype=torch.float32, device=dev)
+        # static fp32 input buffers: every program reads these (the caller's tensors are copied in per step), so that all
+        # pointers of a step are fixed and the step can be replayed as one CUDA graph
+        self.in_frame = torch.zeros((1, cin, H, W), dtype=torch.float32, device=dev)
+        self.in_flow = [torch.zeros((1, 2, H, W), dtype=torch.float32, device=dev) for _ in range(K - 1)] if m.optflow_inputs else None
+        self.in_depth = [torch.zeros((1, 1, H, W), dtype=torch.float32, device=dev) for _ in range(K)] if m.depth_inputs else None
         arena_sfc, arena_fus = engine.Arena(dev), engine.Arena(dev)
         self.sfc, self.fus = [], []
         for s in range(K):
             arena_sfc.reset()
             b = engine.Builder(dev, self.dt, packer, arena_sfc)
-            ext = Ext("frame", ph)
+            ext = Ext("frame", self.in_frame)
             for c0 in range(0, cin, 8):
                 b.prog.gather([(ext, c) for c in range(c0, min(c0 + 8, cin))], self.x_c8[:, c0 // 8], 1, H, W)
             m.base_model.record(b, Act(self.x_c8, cin), maps_c8=self.ring[s:s + 1])
             b.prog.finalize()
             self.sfc.append(b.prog)
-        phf = torch.zeros((1, 2, H, W), dtype=torch.float32, device=dev)
-        phd = torch.zeros((1, 1, H, W), dtype=torch.float32, device=dev)
         for s in range(K):  # s = slot of the current frame; frame i earlier lives in slot (s - i) % K
             arena_fus.reset()
             b = engine.Builder(dev, self.dt, packer, arena_fus)
             maps = [Act(self.ring[(s - i) % K:(s - i) % K + 1], N) for i in range(K)]
-            flows = [Ext(("flow", i), phf) for i in range(K - 1)] if m.optflow_inputs else None
-            depths = [Ext(("depth", i), phd) for i in range(K)] if m.depth_inputs else None
-            io = m.multiframe_net.record(b, maps, flows, depths, self.out)
+            flows = [Ext(("flow", i), self.in_flow[i]) for i in range(K - 1)] if m.optflow_inputs else None
+            depths = [Ext(("depth", i), self.in_depth[i]) for i in range(K)] if m.depth_inputs else None
+            m.multiframe_net.record(b, maps, flows, depths, self.out)
             b.prog.finalize()
-            self.fus.append((b.prog, io))
-        self.launches_per_frame = self.sfc[0].n_kernels + self.fus[0][0].n_kernels
+            self.fus.append(b.prog)
+        self.launches_per_frame = self.sfc[0].n_kernels + self.fus[0].n_kernels
+        self.use_graphs = os.environ.get("MFC_STREAM_GRAPH", "1") != "0" and dev.type == "cuda"
+        self.graphs = [None] * K      # slot -> CUDA graph of (SFC of the new frame + fusion head), captured after one eager run
+        self._ran_eager = [False] * K
         self._keep = (packer, arena_sfc, arena_fus)
 
     def reset(self):
         self.t = 0
+
+    def _load(self, dst, src):
+        dst.copy_(src, non_blocking=True)   # fp32 cast + layout fix-up + staging in one copy on the current stream
 
     def encode(self, frame):
         """Run the SFC network on one frame into its ring slot (used alone for the shard halo)."""
         if engine.params_fingerprint(self.model) != self._fingerprint:
             self._build()
         s = self.t % self.K
-        f = frame.contiguous().float()
-        self.sfc[s].rebind({"frame": f})
         with engine.device_guard(self.device):
+            self._load(self.in_frame, frame)
             self.sfc[s].run()
-        engine.record_stream(f)
         self.t += 1
         return s
 
     def step(self, frame, flows=None, depths=None, out=None):
-        s = self.encode(frame)
-        if self.t < self.K:
+        if self.t < self.K - 1:
+            self.encode(frame)
             return None
-        prog, io = self.fus[s]
-        tensors = {}
-        if self.model.optflow_inputs:
-            tensors.update({("flow", i): flows[i].contiguous().float() for i in range(self.K - 1)})
-        if self.model.depth_inputs:
-            tensors.update({("depth", i): depths[i].contiguous().float() for i in range(self.K)})
-        prog.rebind(tensors)
-        y = out if out is not None else torch.empty_like(self.out)
-        io.y_nchw = y.data_ptr()
+        if engine.params_fingerprint(self.model) != self._fingerprint:
+            self._build()
+        s = self.t % self.K
         with engine.device_guard(self.device):
-            prog.run()
-        for t in tensors.values():
-            engine.record_stream(t)
+            self._load(self.in_frame, frame)
+            if self.model.optflow_inputs:
+                for i in range(self.K - 1):
+                    self._load(self.in_flow[i], flows[i])
+            if self.model.depth_inputs:
+                for i in range(self.K):
+                    self._load(self.in_depth[i], depths[i])
+            if self.use_graphs and self.graphs[s] is None and self._ran_eager[s]:
+                both = engine.Program(self.device, self.dt)
+                both.extend(self.sfc[s])
+                both.extend(self.fus[s])
+                self.graphs[s] = both.capture()
+            if self.graphs[s] is not None:
+                self.graphs[s].launch()      # one launch: the whole frame (SFC + fusion head)
+            else:
+                self.sfc[s].run()
+                self.fus[s].run()
+                self._ran_eager[s] = True
+            y = self.out.clone() if out is None else out.copy_(self.out)
+        self.t += 1
         return y
 
 
