@@ -344,7 +344,7 @@ __device__ __forceinline__ float reduce_scatter16(float (&a)[16], int lane) {
 
 // ---- epilogue -----------------------------------------------------------------------------------------
 struct PixRef {
-  size_t pix;
+  uint32_t pix;  // pixel index inside one output plane (an image has < 2^28 pixels: 32-bit address arithmetic)
   bool valid;
 };
 __device__ __forceinline__ PixRef run_pixel(const ConvParams& p, int r, int lq, int lane, int oy0, int ox0) {
@@ -354,7 +354,7 @@ __device__ __forceinline__ PixRef run_pixel(const ConvParams& p, int r, int lq, 
   const int oy = oy0 + row, ox = ox0 + col;
   PixRef q;
   q.valid = row < p.t.TH && col < p.t.TW && oy < p.Hout && ox < p.Wout;
-  q.pix = (size_t)(oy * p.out_stride + p.out_off_y) * (size_t)(p.Wout * p.out_stride) + (size_t)(ox * p.out_stride + p.out_off_x);
+  q.pix = (uint32_t)(oy * p.out_stride + p.out_off_y) * (uint32_t)(p.Wout * p.out_stride) + (uint32_t)(ox * p.out_stride + p.out_off_x);
   return q;
 }
 
@@ -400,30 +400,49 @@ struct ResPrefetch {
   int w, r, j;     // prefetch cursor: work item, run, first output channel of the step
   uint32_t head;   // steps issued (ring slot = count % kResDepth)
   uint32_t tail;   // steps consumed
+  int cw;          // work item whose coordinates are cached in c (-1: none)
+  ItemCoord c;
 };
 __device__ __forceinline__ void res_prefetch_step(const ConvParams& p, ResPrefetch& rp, int total_items, int lq, int half, int lane,
                                                   int NB) {
   if (rp.w < total_items) {
-    const ItemCoord c = decode_item(p, rp.w);
-    const PixRef q = run_pixel(p, rp.r, lq, lane, c.oy0, c.ox0);
+    if (rp.cw != rp.w) {
+      rp.c = decode_item(p, rp.w);
+      rp.cw = rp.w;
+    }
+    const PixRef q = run_pixel(p, rp.r, lq, lane, rp.c.oy0, rp.c.ox0);
     const int cc_out = (p.Cout + 7) >> 3;
-    const size_t HWo = (size_t)p.Hout * p.Wout * p.out_stride * p.out_stride;
-    const uint8_t* res_b = p.res + (size_t)c.b * p.res_bs;
-    const int ch0 = (c.nbk * NB + rp.j) >> 3;
+    const uint32_t HWo = (uint32_t)(p.Hout * p.Wout * p.out_stride * p.out_stride);
+    const uint8_t* res_b = p.res + (size_t)rp.c.b * p.res_bs;
+    const int ch0 = (rp.c.nbk * NB + rp.j) >> 3;
     const uint32_t dst = rp.ring + ((rp.head % kResDepth) * 64u + (uint32_t)lane) * 16u;
+    const uint32_t off0 = (uint32_t)ch0 * HWo + q.pix;  // 16-byte slots from the sample's base: < 2^32
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const bool ok = q.valid && ch0 + h < cc_out;
-      const uint8_t* src = ok ? res_b + ((size_t)(ch0 + h) * HWo + q.pix) * 16 : p.res;
+      const uint8_t* src = ok ? res_b + (size_t)(off0 + (uint32_t)h * HWo) * 16 : p.res;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)h * 512u), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
-    rp.j += 16;
-    if (rp.j >= NB) {
-      rp.j = 0;
-      rp.r += 2;
+    // same sub-step order as epilogue_tile: NB == 16 walks the run pairs (r, r+1) of this warp, otherwise the 16-channel
+    // groups of the runs half, half+2, ...
+    if (NB == 16) {
+      if ((rp.r & 1) == 0 && rp.r + 1 < p.t.R)
+        rp.r += 1;
+      else
+        rp.r += (rp.r & 1) ? 3 : 4;
       if (rp.r >= p.t.R) {
-        rp.r = half;
+        rp.r = 2 * half;
         rp.w += gridDim.x;
+      }
+    } else {
+      rp.j += 16;
+      if (rp.j >= NB) {
+        rp.j = 0;
+        rp.r += 2;
+        if (rp.r >= p.t.R) {
+          rp.r = half;
+          rp.w += gridDim.x;
+        }
       }
     }
   }
@@ -450,96 +469,97 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   const int NB = NB16 ? 16 : p.t.NB;
   const int cpad = NB * p.t.nblk;
   const int cc_out = (p.Cout + 7) >> 3;
-  const size_t HWo = (size_t)p.Hout * p.Wout * p.out_stride * p.out_stride;
+  const uint32_t HWo = (uint32_t)(p.Hout * p.Wout * p.out_stride * p.out_stride);
   const bool has_res = kRes && p.res != nullptr;
+  const bool res_aff = has_res && p.res_aff != nullptr;
+  const bool relu = p.act == 1;
   const bool has_stats = kStats && p.stats != nullptr;
   const bool has_nchw = kNchw && p.y_nchw != nullptr;
   const bool has_c8 = (MODE != EPI_NCHW && MODE != EPI_GENERIC) || p.y != nullptr;
   uint8_t* y_b = has_c8 ? p.y + (size_t)b * p.y_bs : nullptr;
   const uint32_t tm_lane = tmem_acc + ((uint32_t)(lq * 32) << 16);
-  int r = half, j = 0;
-  if (r >= p.t.R) return;
-  uint32_t acc[16];
-  tmem_ld16(tm_lane + (uint32_t)(r * NB + j), acc);
-  while (true) {
-    const PixRef q = run_pixel(p, r, lq, lane, oy0, ox0);
-    const bool valid = q.valid;
-    const size_t pix = q.pix;
-    const int co0 = nbk * NB + j;
-    int r2 = r, j2 = j + 16;
-    if (NB16 || j2 >= NB) {
-      j2 = 0;
-      r2 = r + 2;
-    }
-    const bool more = r2 < p.t.R;
-    uint4 rv[2];
-    if (kRes && has_res && !(p.debug & 16)) {
-      cp_async_wait_group<kResDepth - 1>();  // the oldest step in the ring (this one) has landed
-      const uint32_t src = rp.ring + ((rp.tail % kResDepth) * 64u + (uint32_t)lane) * 16u;
-      rv[0] = lds16_u32(src);
-      rv[1] = lds16_u32(src + 512u);
-      ++rp.tail;
-    }
-    tmem_ld_wait();
-    if (p.t.slide) tmem_st16_zero(tm_lane + (uint32_t)(r * NB + j));  // slide mode accumulates into zeroed columns
-    for (int a = 1; a < p.t.kacc; ++a) {  // K-split accumulator sets: add the partial sums
-      uint32_t part[16];
-      tmem_ld16(tm_lane + (uint32_t)((a * p.t.R + r) * NB + j), part);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
-    }
-    float f[16];
+  const int R = p.t.R;
+  // One step = 32 accumulator columns = two 16-channel sub-steps behind ONE tcgen05.ld + wait (the wait costs > 100 cycles
+  // whatever the amount of data): with NB == 16 the two sub-steps are the adjacent runs (r, r+1) -- this warp owns the run
+  // pairs half, half+2, ... -- otherwise they are the channels j..j+15 and j+16..j+31 of run r (runs half, half+2, ...).
+  int r = NB16 ? 2 * half : half, j = 0;
+  if (r >= R) return;
+  uint32_t acc[32];
+  auto load_step = [&](int rr, int jj) -> bool {
+    const bool two = NB16 ? (rr + 1 < R) : (jj + 16 < NB);
+    const uint32_t col = tm_lane + (uint32_t)(rr * NB + jj);
+    if (two)
+      tmem_ld32(col, acc);
+    else
+      tmem_ld16_lo(col, acc);
+    return two;
+  };
+  // scale / shift of one sub-step: accumulators -> fp32 values
+  auto scale_shift = [&](const uint32_t* a16, int co0, float (&f)[16]) {
     // with the 32 GroupNorm accumulators live (STATS) the scale/shift registers would push the loop over the
     // register budget: read them from smem there (8 broadcast LDS.128 per step)
-    if constexpr (NB16 && MODE != EPI_STATS && MODE != EPI_GENERIC) {
+    if constexpr (NB16 && (MODE == EPI_PLAIN || MODE == EPI_NCHW)) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(acc[i]), sc[i], sh[i]);
+      for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(a16[i]), sc[i], sh[i]);
     } else {
       const uint32_t sa = s_scale_addr + (uint32_t)co0 * 4, sb = sa + (uint32_t)cpad * 4;
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
         const float4 a = lds_f4(sa + i * 4), c = lds_f4(sb + i * 4);
-        f[i + 0] = fmaf(__uint_as_float(acc[i + 0]), a.x, c.x);
-        f[i + 1] = fmaf(__uint_as_float(acc[i + 1]), a.y, c.y);
-        f[i + 2] = fmaf(__uint_as_float(acc[i + 2]), a.z, c.z);
-        f[i + 3] = fmaf(__uint_as_float(acc[i + 3]), a.w, c.w);
+        f[i + 0] = fmaf(__uint_as_float(a16[i + 0]), a.x, c.x);
+        f[i + 1] = fmaf(__uint_as_float(a16[i + 1]), a.y, c.y);
+        f[i + 2] = fmaf(__uint_as_float(a16[i + 2]), a.z, c.z);
+        f[i + 3] = fmaf(__uint_as_float(a16[i + 3]), a.w, c.w);
       }
     }
-    if (more) tmem_ld16(tm_lane + (uint32_t)(r2 * NB + j2), acc);  // in flight during the rest of this step
-    if (kRes && has_res && valid) {
+  };
+  // everything after scale/shift for one sub-step: residual -> ReLU -> GroupNorm sums -> stores
+  auto finish = [&](float (&f)[16], int rr, int co0) {
+    const PixRef q = run_pixel(p, rr, lq, lane, oy0, ox0);
+    const bool valid = q.valid;
+    const uint32_t pix = q.pix;
+    if (kRes && has_res) {
+      cp_async_wait_group<kResDepth - 1>();  // the oldest sub-step in the ring (this one) has landed
+      const uint32_t src = rp.ring + ((rp.tail % kResDepth) * 64u + (uint32_t)lane) * 16u;
+      uint4 rv[2];
+      rv[0] = lds16_u32(src);
+      rv[1] = lds16_u32(src + 512u);
+      ++rp.tail;
+      if (valid) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ch = (co0 >> 3) + h;
-        if (ch < cc_out) {
-          float rf[8];
-          unpack8<BF16>(rv[h], rf);
-          if (p.res_aff && !(p.debug & 64)) {
-            if (res_aff_smem) {
-              // (s/2, t/2) of this sample's channels parked in the warp's smem slot: silu(y) = h + h*tanh(h), h = y/2
-              const uint32_t sa = smem_u32(my_stats) + (uint32_t)(co0 + h * 8) * 8u;
+        for (int h = 0; h < 2; ++h) {
+          const int ch = (co0 >> 3) + h;
+          if (ch < cc_out) {
+            float rf[8];
+            unpack8<BF16>(rv[h], rf);
+            if (res_aff) {
+              if (res_aff_smem) {
+                // (s/2, t/2) of this sample's channels parked in the warp's smem slot: silu(y) = h + h*tanh(h), h = y/2
+                const uint32_t sa = smem_u32(my_stats) + (uint32_t)(co0 + h * 8) * 8u;
 #pragma unroll
-              for (int i = 0; i < 8; i += 2) {
-                const float4 a = lds_f4(sa + i * 8);
-                const float h0 = fmaf(rf[i], a.x, a.y), h1 = fmaf(rf[i + 1], a.z, a.w);
-                rf[i] = fmaf(h0, tanh_fast(h0), h0);
-                rf[i + 1] = fmaf(h1, tanh_fast(h1), h1);
-              }
-            } else {
-              const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
+                for (int i = 0; i < 8; i += 2) {
+                  const float4 a = lds_f4(sa + i * 8);
+                  const float h0 = fmaf(rf[i], a.x, a.y), h1 = fmaf(rf[i + 1], a.z, a.w);
+                  rf[i] = fmaf(h0, tanh_fast(h0), h0);
+                  rf[i + 1] = fmaf(h1, tanh_fast(h1), h1);
+                }
+              } else {
+                const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float2 a = __ldg(ra + i);
-                rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
+                for (int i = 0; i < 8; ++i) {
+                  float2 a = __ldg(ra + i);
+                  rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
+                }
               }
             }
-          }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[h * 8 + i] += rf[i];
+            for (int i = 0; i < 8; ++i) f[h * 8 + i] += rf[i];
+          }
         }
       }
+      res_prefetch_step(p, rp, total_items, lq, half, lane, NB);  // refills the ring slot just consumed
     }
-    if (p.act == 1) {
+    if (relu) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
     }
@@ -569,17 +589,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
         }
       }
     }
-    if (valid && !(p.debug & 32)) {
+    if (valid) {
       if (has_c8) {
+        const uint32_t off0 = (uint32_t)(co0 >> 3) * HWo + pix;  // 16-byte slots from the sample's base: < 2^32
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int ch = (co0 >> 3) + h;
-          if (ch < cc_out) {
+          if ((co0 >> 3) + h < cc_out) {
             float g[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[i] = f[h * 8 + i];
             uint4 ov = pack8<BF16>(g);
-            *reinterpret_cast<uint4*>(y_b + ((size_t)ch * HWo + pix) * 16) = ov;
+            *reinterpret_cast<uint4*>(y_b + (size_t)(off0 + (uint32_t)h * HWo) * 16) = ov;
           }
         }
       }
@@ -587,14 +607,79 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int co = co0 + i;
-          if (co < p.Cout) p.y_nchw[((size_t)b * p.Cout + co) * HWo + pix] = f[i];
+          if (co < p.Cout) p.y_nchw[((size_t)b * p.Cout + co) * (size_t)HWo + pix] = f[i];
         }
       }
     }
-    if (kRes && has_res && !(p.debug & 16)) res_prefetch_step(p, rp, total_items, lq, half, lane, NB);  // refills the ring slot just consumed
+  };
+
+  bool two = load_step(r, j);
+  while (true) {
+    int r2, j2;
+    if (NB16) {
+      r2 = r + 4;
+      j2 = 0;
+    } else {
+      r2 = r;
+      j2 = j + 32;
+      if (j2 >= NB) {
+        j2 = 0;
+        r2 = r + 2;
+      }
+    }
+    const bool more = r2 < R;
+    tmem_ld_wait();
+    if (p.t.slide) {  // slide mode accumulates into zeroed columns
+      if (two)
+        tmem_st32_zero(tm_lane + (uint32_t)(r * NB + j));
+      else
+        tmem_st16_zero(tm_lane + (uint32_t)(r * NB + j));
+    }
+    for (int a = 1; a < p.t.kacc; ++a) {  // K-split accumulator sets: add the partial sums
+      uint32_t part[16];
+      tmem_ld16(tm_lane + (uint32_t)((a * R + r) * NB + j), part);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
+      if (two) {
+        // NB16: run r+1 of set a; otherwise channels j+16.. of run r -- both are the next 16 columns
+        tmem_ld16(tm_lane + (uint32_t)((a * R + r) * NB + j + 16), part);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[16 + i] = __float_as_uint(__uint_as_float(acc[16 + i]) + __uint_as_float(part[i]));
+      }
+    }
+    const int co_a = nbk * NB + j;
+    const int co_b = NB16 ? co_a : co_a + 16;
+    const int r_a = r, r_b = NB16 ? r + 1 : r;
+    if constexpr (MODE == EPI_PLAIN || MODE == EPI_NCHW) {
+      // registers allow it: convert both sub-steps, then put the next step's load in flight during the stores of this one
+      float fa[16], fb[16];
+      scale_shift(acc, co_a, fa);
+      if (two) scale_shift(acc + 16, co_b, fb);
+      const bool two_now = two;
+      if (more) {
+        r = r2;
+        j = j2;
+        two = load_step(r, j);
+      }
+      finish(fa, r_a, co_a);
+      if (two_now) finish(fb, r_b, co_b);
+    } else {
+      float f[16];
+      scale_shift(acc, co_a, f);
+      finish(f, r_a, co_a);
+      if (two) {
+        scale_shift(acc + 16, co_b, f);
+        finish(f, r_b, co_b);
+      }
+      if (more) {
+        r = r2;
+        j = j2;
+        two = load_step(r, j);
+      }
+    }
     if (!more) break;
-    r = r2;
-    j = j2;
   }
   if (p.t.slide) tmem_st_wait();
 }
@@ -936,10 +1021,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     ResPrefetch rp;
     rp.ring = smem_u32(smem + p.t.off_resring) + (uint32_t)warp * (kResDepth * 1024u);
     rp.w = blockIdx.x;
-    rp.r = half;
+    rp.r = NB16 ? 2 * half : half;
     rp.j = 0;
     rp.head = rp.tail = 0;
-    if ((MODE == EPI_RES || MODE == EPI_GENERIC) && p.res != nullptr && half < p.t.R) {
+    rp.cw = -1;
+    if ((MODE == EPI_RES || MODE == EPI_GENERIC) && p.res != nullptr && rp.r < p.t.R) {
       for (int i = 0; i < kResDepth; ++i) res_prefetch_step(p, rp, total_items, lq, half, lane, NB);
     }
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
