@@ -289,6 +289,29 @@ int mfc_segmentation_loss(const float* logits, const long long* target, const fl
                           int B, int N, long long pixels, float w_nll, float w_jaccard,
                           void* workspace, float* out, void* stream);
 
+/* The additive statistics of the loss over one rank's shard: sums[2 + 3(N-1)] doubles = (sum w[t](-logp[t]), sum w[t], then
+ * per class c >= 1: I_c, S_c, T_c of src/loss.py:45-63).  Data-parallel ranks add their records (one 14-double all-reduce)
+ * and every rank evaluates the loss of the GLOBAL batch -- what nn.DataParallel's gather-to-GPU0 computes
+ * (src/engine.py:56-66).  `workspace`: mfc_segmentation_loss_workspace bytes. */
+int mfc_segmentation_loss_sums(const float* logits, const long long* target, const float* class_weights, int B, int N, long long pixels,
+                               void* workspace, double* sums, void* stream);
+int mfc_segmentation_loss_from_sums(const double* sums, int N, float w_nll, float w_jaccard, float* out /*[3]*/, void* stream);
+
+/* Backward of the loss (the `loss.backward()` of src/engine.py:70 down to the model output):
+ * dlogits[B][N][pixels] = scale * d total / d logits of this rank's shard.  `sums` holds n_records records of loss
+ * statistics that are added first (1 = the record of mfc_segmentation_loss_sums, possibly all-reduced over ranks; 0 = `sums`
+ * is the workspace mfc_segmentation_loss just filled for the same logits).  `coef`: 64 floats of device scratch. */
+int mfc_segmentation_loss_bwd(const float* logits, const long long* target, const float* class_weights, int B, int N, long long pixels,
+                              float w_nll, float w_jaccard, float scale, const void* sums, int n_records, float* coef, float* dlogits,
+                              void* stream);
+
+/* One torch.optim.Adam step (amsgrad off; scripts/train_multiframe_detection.py:128-151 builds two parameter groups =
+ * two calls with different lr) on a flat fp32 bucket.  `step` is the 1-based step count; grad_scale multiplies the
+ * gradient first (the 1/world_size of the data-parallel average after the NCCL sum). */
+int mfc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+
 /* ------------------------------------------------------------------------------------
  * UnFlow correlation cost volume (models/unflow_correlation.py:10-105,282-337).
  * first/second: fp32 NCHW contiguous; out: fp32 [B][D*D][H][W], D = 2*(max_disp/stride2)+1,

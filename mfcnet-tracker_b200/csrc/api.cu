@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of libmfcnet_b200.so (include/mfcnet_b200.h): argument validation, the conv
 // planner cache, and dispatch into the kernel launchers.  No allocation, no synchronisation.
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -480,6 +481,50 @@ int mfc_segmentation_loss(const float* logits, const long long* target, const fl
   MFC_LAUNCH(mfc::launch_segmentation_loss(logits, target, class_weights, B, N, pixels, w_nll, w_jaccard, (double*)workspace, out,
                                            (cudaStream_t)stream),
              "segmentation_loss");
+}
+
+/* The additive statistics of the loss over this rank's shard: sums[2 + 3(N-1)] doubles = (sum w[t](-logp[t]), sum w[t],
+ * then per class c>=1: I_c, S_c, T_c).  Data-parallel ranks add their records (one tiny all-reduce) and every rank then
+ * evaluates the loss of the GLOBAL batch -- what nn.DataParallel's gather-to-GPU0 computes (src/engine.py:56-66). */
+int mfc_segmentation_loss_sums(const float* logits, const long long* target, const float* class_weights, int B, int N, long long pixels,
+                               void* workspace, double* sums, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!logits || !target || !workspace || !sums || B < 1 || N < 2 || N > 16 || pixels < 1)
+    return fail(MFC_EINVAL, "segmentation_loss_sums: bad argument");
+  MFC_LAUNCH(mfc::launch_segmentation_loss_sums(logits, target, class_weights, B, N, pixels, (double*)workspace, sums, (cudaStream_t)stream),
+             "segmentation_loss_sums");
+}
+
+int mfc_segmentation_loss_from_sums(const double* sums, int N, float w_nll, float w_jaccard, float* out, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!sums || !out || N < 2 || N > 16) return fail(MFC_EINVAL, "segmentation_loss_from_sums: bad argument");
+  MFC_LAUNCH(mfc::launch_segmentation_loss_from_sums(sums, N, w_nll, w_jaccard, out, (cudaStream_t)stream), "segmentation_loss_from_sums");
+}
+
+/* Backward: dlogits = scale * d total / d logits of this rank's shard, where `sums` holds n_records records of loss
+ * statistics that are added first (1 = the reduced record of mfc_segmentation_loss_sums, possibly all-reduced over ranks;
+ * 0 = `sums` is the workspace mfc_segmentation_loss just filled for the same logits).  `coef` is 64 floats of scratch. */
+int mfc_segmentation_loss_bwd(const float* logits, const long long* target, const float* class_weights, int B, int N, long long pixels,
+                              float w_nll, float w_jaccard, float scale, const void* sums, int n_records, float* coef, float* dlogits,
+                              void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!logits || !target || !sums || !coef || !dlogits || B < 1 || N < 2 || N > 16 || pixels < 1 || n_records < 0)
+    return fail(MFC_EINVAL, "segmentation_loss_bwd: bad argument");
+  MFC_LAUNCH(mfc::launch_segmentation_loss_bwd(logits, target, class_weights, B, N, pixels, w_nll, w_jaccard, scale, (const double*)sums,
+                                               n_records, coef, dlogits, (cudaStream_t)stream),
+             "segmentation_loss_bwd");
+}
+
+/* One torch.optim.Adam step (amsgrad off) on a flat fp32 bucket; `step` is the 1-based step count, grad_scale multiplies the
+ * gradient first (the 1/world_size of the data-parallel average). */
+int mfc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail(MFC_EINVAL, "adam_step: bad argument");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  MFC_LAUNCH(mfc::launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2),
+                              grad_scale, (cudaStream_t)stream),
+             "adam_step");
 }
 
 // ---- correlation -------------------------------------------------------------------------------

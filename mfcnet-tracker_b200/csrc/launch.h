@@ -44,6 +44,16 @@ int loss_blocks(int B, long long pixels);
 cudaError_t launch_segmentation_loss(const float* logits, const long long* target, const float* cw, int B, int N, long long pixels,
                                      float w_nll, float w_jacc, double* partials, float* out, cudaStream_t st);
 
+// train_ops.cu
+cudaError_t launch_segmentation_loss_bwd(const float* logits, const long long* target, const float* cw, int B, int N, long long pixels,
+                                         float w_nll, float w_jacc, float scale, const double* partials, int n_partials, float* coef,
+                                         float* dlogits, cudaStream_t st);
+cudaError_t launch_segmentation_loss_sums(const float* logits, const long long* target, const float* cw, int B, int N, long long pixels,
+                                          double* partials, double* sums, cudaStream_t st);
+cudaError_t launch_segmentation_loss_from_sums(const double* sums, int N, float w_nll, float w_jacc, float* out, cudaStream_t st);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+                        float bc1, float bc2_sqrt, float grad_scale, cudaStream_t st);
+
 // correlation.cu
 cudaError_t launch_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp,
                                int stride2, int exact_order, cudaStream_t st);

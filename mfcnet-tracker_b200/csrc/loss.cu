@@ -103,6 +103,15 @@ __global__ void loss_final_kernel(const double* __restrict__ partials, int nbloc
   out[2] = (float)jac;
 }
 
+// per-block partial sums -> one record of (2 + 3(N-1)) doubles, added in block order (deterministic)
+__global__ void loss_reduce_kernel(const double* __restrict__ partials, int nblocks, int nacc, double* __restrict__ sums) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nacc) return;
+  double a = 0.0;
+  for (int b = 0; b < nblocks; ++b) a += partials[(size_t)b * nacc + k];
+  sums[k] = a;
+}
+
 int loss_blocks(int B, long long pixels) {
   long long b = ((long long)B * pixels + kLossThreads - 1) / kLossThreads;
   const long long cap = (long long)kSmCount * 4;
@@ -115,6 +124,19 @@ cudaError_t launch_segmentation_loss(const float* logits, const long long* targe
   cudaError_t e = launch_pdl(loss_partial_kernel, dim3(blocks), dim3(kLossThreads), 0, st, logits, target, cw, B, N, pixels, partials);
   if (e != cudaSuccess) return e;
   return launch_pdl(loss_final_kernel, dim3(1), dim3(32), 0, st, (const double*)partials, blocks, N, w_nll, w_jacc, out);
+}
+
+cudaError_t launch_segmentation_loss_sums(const float* logits, const long long* target, const float* cw, int B, int N, long long pixels,
+                                          double* partials, double* sums, cudaStream_t st) {
+  const int blocks = loss_blocks(B, pixels);
+  cudaError_t e = launch_pdl(loss_partial_kernel, dim3(blocks), dim3(kLossThreads), 0, st, logits, target, cw, B, N, pixels, partials);
+  if (e != cudaSuccess) return e;
+  loss_reduce_kernel<<<1, 64, 0, st>>>(partials, blocks, 2 + 3 * (N - 1), sums);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_segmentation_loss_from_sums(const double* sums, int N, float w_nll, float w_jacc, float* out, cudaStream_t st) {
+  return launch_pdl(loss_final_kernel, dim3(1), dim3(32), 0, st, sums, 1, N, w_nll, w_jacc, out);
 }
 
 }  // namespace mfc
