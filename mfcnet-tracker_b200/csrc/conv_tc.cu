@@ -138,11 +138,14 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
   if (s == 1 && p.upsample == 1) {
     // Four slots per iteration: all four LDS.128 are issued before the first value is needed and the stores come
     // last, so one thread keeps four independent load -> FMA -> MUFU -> FMA -> pack chains in flight (the six
-    // producer warps alone cannot hide those latencies by multithreading).
+    // producer warps alone cannot hide those latencies by multithreading).  The slots are dealt out flat (consecutive
+    // lanes = consecutive slots): a row-per-warp walk was measured slower, it idles lanes whenever the row pitch is not
+    // a multiple of 32 and the SFU cost of a warp instruction does not depend on the number of active lanes.
     const uint32_t H = (uint32_t)p.Hin;
     // columns past the tile's own halo (slide mode pads the row pitch to 128) are never read for a valid output
     const uint32_t W = (uint32_t)min(p.Win, ix_base + p.t.TW + (p.kw - 1));
     const uint32_t base = smem_u32(plane);
+    const FastDiv divP = p.divP;
     constexpr int U = 4;
     for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
       uint4 v[U];
@@ -150,7 +153,7 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int idx = idx0 + u * NT;
-        const int r = (int)fdiv((uint32_t)idx, p.divP);
+        const int r = (int)fdiv((uint32_t)idx, divP);
         const int c = idx - r * P;
         ok[u] = idx < items && (uint32_t)(iy_base + r) < H && (uint32_t)(ix_base + c) < W;  // padding stays zero
         if (ok[u]) v[u] = lds16_u32(base + (uint32_t)idx * 16u);
@@ -470,12 +473,35 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   const int cpad = NB * p.t.nblk;
   const int cc_out = (p.Cout + 7) >> 3;
   const uint32_t HWo = (uint32_t)(p.Hout * p.Wout * p.out_stride * p.out_stride);
-  const bool has_res = kRes && p.res != nullptr;
+  // launch_conv_t picks the mode from exactly these pointers: in the specialised modes they are compile-time facts
+  const bool has_res = MODE == EPI_RES ? true : (MODE == EPI_GENERIC && p.res != nullptr);
   const bool res_aff = has_res && p.res_aff != nullptr;
   const bool relu = p.act == 1;
-  const bool has_stats = kStats && p.stats != nullptr;
-  const bool has_nchw = kNchw && p.y_nchw != nullptr;
+  const bool has_stats = MODE == EPI_STATS ? true : (MODE == EPI_GENERIC && p.stats != nullptr);
+  const bool has_nchw = MODE == EPI_NCHW ? true : (MODE == EPI_GENERIC && p.y_nchw != nullptr);
   const bool has_c8 = (MODE != EPI_NCHW && MODE != EPI_GENERIC) || p.y != nullptr;
+  // tile geometry in registers: the per-sub-step pixel arithmetic must not go back to the parameter bank
+  const int tP = p.t.P, tTH = p.t.TH, tTW = p.t.TW, Hout = p.Hout, Wout = p.Wout;
+  const uint32_t row_pitch = (uint32_t)(p.Wout * p.out_stride);
+  const int ostr = p.out_stride, ooy = p.out_off_y, oox = p.out_off_x;
+  const FastDiv divP = p.divP;
+  const bool slide = p.t.slide != 0;
+  auto pixel_of = [&](int rr) -> PixRef {
+    const int sl = rr * 128 + lq * 32 + lane;
+    int row, col;
+    if (slide) {  // P == 128: a run is one output row
+      row = rr;
+      col = lq * 32 + lane;
+    } else {
+      row = (int)fdiv((uint32_t)sl, divP);
+      col = sl - row * tP;
+    }
+    const int oy = oy0 + row, ox = ox0 + col;
+    PixRef q;
+    q.valid = row < tTH && col < tTW && oy < Hout && ox < Wout;
+    q.pix = (uint32_t)(oy * ostr + ooy) * row_pitch + (uint32_t)(ox * ostr + oox);
+    return q;
+  };
   uint8_t* y_b = has_c8 ? p.y + (size_t)b * p.y_bs : nullptr;
   const uint32_t tm_lane = tmem_acc + ((uint32_t)(lq * 32) << 16);
   const int R = p.t.R;
@@ -515,7 +541,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   };
   // everything after scale/shift for one sub-step: residual -> ReLU -> GroupNorm sums -> stores
   auto finish = [&](float (&f)[16], int rr, int co0) {
-    const PixRef q = run_pixel(p, rr, lq, lane, oy0, ox0);
+    const PixRef q = pixel_of(rr);
     const bool valid = q.valid;
     const uint32_t pix = q.pix;
     if (kRes && has_res) {
@@ -629,7 +655,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     }
     const bool more = r2 < R;
     tmem_ld_wait();
-    if (p.t.slide) {  // slide mode accumulates into zeroed columns
+    if (slide) {  // slide mode accumulates into zeroed columns
       if (two)
         tmem_st32_zero(tm_lane + (uint32_t)(r * NB + j));
       else
@@ -681,7 +707,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     }
     if (!more) break;
   }
-  if (p.t.slide) tmem_st_wait();
+  if (slide) tmem_st_wait();
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
@@ -741,6 +767,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   uint8_t* b_res = smem + p.t.off_bres;
   uint8_t* stage0 = smem + p.t.off_stage;
 
+  const long long t_entry = clock64();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NB = p.t.NB;
   const int taps = p.t.entries;  // MMA entries (= B-operand blocks) per K step
@@ -792,6 +819,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long t_alloc = clock64();
   if (p.t.slide) {  // every MMA of this mode accumulates: start from zeroed accumulators (the epilogue re-zeroes what it drains)
     if (warp < 4) {
       for (uint32_t c = 0; c < p.t.tmem_cols; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
@@ -801,6 +829,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
   }
+  const long long t_prewait = clock64();
   pdl_wait();  // from here on the previous kernel's outputs (activations, GroupNorm affines) are read
   const long long t_setup = clock64();
   const bool timed = (p.debug & 8) != 0;
@@ -1061,8 +1090,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
   // ---- teardown
   if ((p.debug & 8) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kMmaWarp0 || warp == kProdWarp0))
-    printf("mfc conv timing: warp %d role loop %lld cycles, waiting for input %lld, for back-pressure %lld (items/cta %d)\n", warp,
-           clock64() - t_setup, wait_a, wait_b, (total_items + (int)gridDim.x - 1) / (int)gridDim.x);
+    printf("mfc conv timing: warp %d role loop %lld cycles, waiting for input %lld, for back-pressure %lld (items/cta %d); setup: "
+           "smem+alloc %lld, zeroing %lld, pdl wait %lld\n", warp, clock64() - t_setup, wait_a, wait_b,
+           (total_items + (int)gridDim.x - 1) / (int)gridDim.x, t_alloc - t_entry, t_prewait - t_alloc, t_setup - t_prewait);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -1355,7 +1385,9 @@ static cudaError_t launch_conv_inst(const ConvParams& p, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p.t.grid);
   cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = p.t.smem_bytes;
+  // always the full 227 KB: one CTA per SM anyway, and consecutive launches with different shared-memory needs would make
+  // the SMs switch their L1 / shared-memory carve-out between kernels (a drain that serialises back-to-back launches)
+  cfg.dynamicSmemBytes = (static_cast<int>(getenv("MFC_CONV_SMEM_EXACT") != nullptr)) ? p.t.smem_bytes : (size_t)kSmemPerCtaMax;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

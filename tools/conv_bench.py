@@ -32,6 +32,10 @@ CASES = [
     dict(name="B24 128->128 k3 aff+stats", B=24, H=60, W=80, cins=[128], Cout=128, k=3, stats=True, aff=True),
     dict(name="B24 64->64 k3 aff+stats", B=24, H=120, W=160, cins=[64], Cout=64, k=3, stats=True, aff=True),
     dict(name="B24 32->32 k3 aff+stats", B=24, H=240, W=320, cins=[32], Cout=32, k=3, stats=True, aff=True),
+    # latency-bound shapes of the batch-1 streaming paths
+    dict(name="B1 hrnet 48->48 k3 relu 120x160", B=1, H=120, W=160, cins=[48], Cout=48, k=3, act=1),
+    dict(name="B1 hrnet 192->192 k3 relu 30x40", B=1, H=30, W=40, cins=[192], Cout=192, k=3, act=1),
+    dict(name="B1 16->16 k3 aff+stats 480x640", B=1, H=480, W=640, cins=[16], Cout=16, k=3, stats=True, aff=True),
 ]
 
 
@@ -68,6 +72,24 @@ def run(case, iters):
     out, st, info, io = bld.conv("c", acts, w, k, bias=torch.zeros(Cout, device=dev), pad=k // 2, upsample=ups, act=act,
                                  residual=res, want_stats=bool(c.get("stats")), out_nchw=out_nchw, out_c8=out_nchw is None)
     prog = bld.prog
+    if "--graph" in sys.argv:      # 20 back-to-back launches of the layer as ONE CUDA-graph launch: no host work in between
+        for _ in range(3):
+            prog.run()
+        rep = engine.Program(dev, dt)
+        for _ in range(20):
+            rep.extend(prog)
+        g = rep.capture()
+        g.launch()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            g.launch()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1000.0 / (iters * 20)
+        print(json.dumps({"case": name + " (graph x20)", "us": round(us, 2)}), flush=True)
+        return {"case": name, "us": us}
     for _ in range(3):
         prog.run()
     torch.cuda.synchronize()
@@ -87,7 +109,7 @@ def run(case, iters):
 
 
 def main():
-    args = sys.argv[1:]
+    args = [a for a in sys.argv[1:] if a != "--graph"]
     iters = 20
     if "--iters" in args:
         i = args.index("--iters")
