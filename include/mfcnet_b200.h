@@ -415,9 +415,16 @@ typedef struct MfcHeatmapArgs {   /* mfc_heatmap_head as a list command (Ternaus
   int B, N;
 } MfcHeatmapArgs;
 
+/* `lane`: 0 = the caller's stream; 1..3 = side streams owned by the library, for commands that are independent of the
+ * other lanes (the parallel branches of an HRNet module: each conv there fills only part of the SMs).  MFC_OP_FORK makes
+ * the side lanes wait for everything issued so far on lane 0, MFC_OP_JOIN makes lane 0 wait for the side lanes; a list must
+ * JOIN before it ends.  Under mfc_graph_capture the lanes become parallel branches of the graph. */
+#define MFC_OP_FORK 100
+#define MFC_OP_JOIN 101
+#define MFC_MAX_LANES 4
 typedef struct MfcCmd {
   int op;
-  int reserved;
+  int lane;
   const void* a;
   const void* b;
 } MfcCmd;

@@ -565,12 +565,65 @@ int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* o
 }
 
 // ---- command list ------------------------------------------------------------------------------
-int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
+namespace {
+// side streams / events of the calling thread, per device (created on first use, never destroyed)
+struct LanePool {
+  bool ready = false;
+  cudaStream_t s[MFC_MAX_LANES - 1];
+  cudaEvent_t ev_main, ev[MFC_MAX_LANES - 1];
+};
+LanePool* lane_pool() {
+  thread_local LanePool pools[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  LanePool& p = pools[dev];
+  if (!p.ready) {
+    for (int i = 0; i < MFC_MAX_LANES - 1; ++i) {
+      if (cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&p.ev_main, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    p.ready = true;
+  }
+  return &p;
+}
+int run_list_impl(const MfcCmd* cmds, int n, void* stream, bool use_lanes);
+}  // namespace
+
+int mfc_run_list(const MfcCmd* cmds, int n, void* stream) { return run_list_impl(cmds, n, stream, true); }
+
+namespace {
+int run_list_impl(const MfcCmd* cmds, int n, void* main_stream, bool use_lanes) {
   if (!cmds || n < 0) return fail(MFC_EINVAL, "run_list: bad argument");
+  LanePool* pool = nullptr;
   for (int i = 0; i < n; ++i) {
     const MfcCmd& c = cmds[i];
     int rc = MFC_OK;
+    void* stream = main_stream;
+    if (use_lanes && (c.lane != 0 || c.op == MFC_OP_FORK || c.op == MFC_OP_JOIN)) {
+      if (c.lane < 0 || c.lane >= MFC_MAX_LANES) return fail(MFC_EINVAL, "run_list: lane %d out of range at %d", c.lane, i);
+      if (!pool) pool = lane_pool();
+      if (!pool) return fail(MFC_ECUDA, "run_list: cannot create the side streams");
+      if (c.lane > 0) stream = (void*)pool->s[c.lane - 1];
+    }
     switch (c.op) {
+      case MFC_OP_FORK:
+        if (use_lanes) {
+          cudaError_t e = cudaEventRecord(pool->ev_main, (cudaStream_t)main_stream);
+          for (int l = 0; l < MFC_MAX_LANES - 1 && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(pool->s[l], pool->ev_main, 0);
+          if (e != cudaSuccess) rc = cuda_fail(e, "run_list: fork");
+        }
+        break;
+      case MFC_OP_JOIN:
+        if (use_lanes) {
+          cudaError_t e = cudaSuccess;
+          for (int l = 0; l < MFC_MAX_LANES - 1 && e == cudaSuccess; ++l) {
+            e = cudaEventRecord(pool->ev[l], pool->s[l]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)main_stream, pool->ev[l], 0);
+          }
+          if (e != cudaSuccess) rc = cuda_fail(e, "run_list: join");
+        }
+        break;
       case MFC_OP_CONV:
         rc = mfc_conv2d_fwd((const MfcConvDesc*)c.a, (const MfcConvIO*)c.b, stream);
         break;
@@ -620,6 +673,7 @@ int mfc_run_list(const MfcCmd* cmds, int n, void* stream) {
   }
   return MFC_OK;
 }
+}  // namespace
 
 // ---- CUDA graphs ---------------------------------------------------------------------------------
 // A command list whose pointers are all static (the streaming runner's per-slot programs) is captured once and replayed
@@ -674,7 +728,7 @@ int mfc_run_list_timed(const MfcCmd* cmds, int n, void* stream, float* ms_out) {
   int rc = MFC_OK;
   cudaEventRecord(ev[0], st);
   for (int i = 0; i < n && rc == MFC_OK; ++i) {
-    rc = mfc_run_list(cmds + i, 1, stream);
+    rc = run_list_impl(cmds + i, 1, stream, false);  // serial on the caller's stream: per-command times
     cudaEventRecord(ev[i + 1], st);
   }
   cudaError_t e = cudaEventSynchronize(ev[n]);

@@ -145,7 +145,8 @@ class Program:
         self.device = canonical_device(device)
         self.dtype_name = dtype_name
         self.tdtype, self.cdtype = _DTYPES[dtype_name]
-        self.cmds = []       # (op, struct_a, struct_b)
+        self.cmds = []       # (op, struct_a, struct_b, lane)
+        self.lane = 0        # lane (stream) the next recorded commands run on; see fork() / join()
         self.keep = []       # tensors referenced by raw pointer
         self._array = None
         self.n_kernels = 0   # kernel launches one run() issues
@@ -154,19 +155,33 @@ class Program:
 
     # ---- low-level recording -----------------------------------------------------------------
     def _push(self, op, a, b=None, launches=1, meta=None):
-        self.cmds.append((op, a, b))
+        self.cmds.append((op, a, b, self.lane))
         self.meta.append(meta or {"kind": "op%d" % op, "name": "", "bytes": 0, "flops": 0})
         self._array = None
         self.n_kernels += launches
 
     def finalize(self):
         arr = (abi.MfcCmd * len(self.cmds))()
-        for i, (op, a, b) in enumerate(self.cmds):
+        for i, (op, a, b, lane) in enumerate(self.cmds):
             arr[i].op = op
-            arr[i].a = C.cast(C.pointer(a), C.c_void_p)
+            arr[i].lane = lane
+            arr[i].a = C.cast(C.pointer(a), C.c_void_p) if a is not None else None
             arr[i].b = C.cast(C.pointer(b), C.c_void_p) if b is not None else None
         self._array = arr
         return self
+
+    @property
+    def has_lanes(self):
+        return any(c[3] != 0 for c in self.cmds)
+
+    def fork(self):
+        """Commands recorded on lanes 1..3 after this point run concurrently with lane 0 (and with each other); they see
+        everything recorded before the fork.  Every fork needs a join()."""
+        self._push(abi.OP_FORK, None, launches=0, meta={"kind": "fork", "name": "", "bytes": 0, "flops": 0})
+
+    def join(self):
+        self.lane = 0
+        self._push(abi.OP_JOIN, None, launches=0, meta={"kind": "join", "name": "", "bytes": 0, "flops": 0})
 
     def run(self, stream=None):
         if self._array is None:

@@ -19,10 +19,12 @@ libmfcnet_b200.so:
     summed by ``fuse_sum`` together with BN + ReLU, then the 720->N 1x1 conv and the final x4
     bilinear upsampling of the logits.
 """
+import os
+
 import torch
 from torch import nn
 
-from . import engine
+from . import abi, engine
 from .engine import Act, Ext
 
 BN_MOMENTUM = 0.1
@@ -159,14 +161,24 @@ class HighResolutionNet(nn.Module):
         return self._cb(bld, name + ".conv2", blk.conv2, blk.bn2, [h], 1, residual=res)
 
     def _module(self, bld, name, mod, xs):
+        # The branches of a module are independent until the fuse step and each of their convs fills only part of the GPU
+        # (72..120 work items at batch 1): they are recorded on separate lanes = concurrent streams / parallel graph branches.
+        lanes = mod.num_branches > 1 and mod.num_branches <= abi.MFC_MAX_LANES and os.environ.get("MFC_LANES", "1") != "0"
         ys = []
+        if lanes:
+            bld.prog.fork()
         for i in range(mod.num_branches):
+            bld.prog.lane = i if lanes else 0
             x = xs[i]
             for k, blk in enumerate(mod.branches[i]):
                 x = self._block(bld, "%s.branches.%d.%d" % (name, i, k), blk, x)
             ys.append(x)
+        if lanes:
+            bld.prog.join()
+            bld.prog.fork()
         outs = []
         for i in range(mod.num_branches):
+            bld.prog.lane = i if lanes else 0      # the fuse step of output i only reads the branch results
             terms = []
             for j in range(mod.num_branches):
                 if j == i:
@@ -175,6 +187,8 @@ class HighResolutionNet(nn.Module):
                     terms.append(self._seq(bld, "%s.fuse_layers.%d.%d" % (name, i, j), mod.fuse_layers[i][j], ys[j]))
             o = bld.arena.alloc(tuple(ys[i].t.shape), bld.tdtype)
             outs.append(bld.prog.fuse_sum(terms, o, ys[i].C, act=1))
+        if lanes:
+            bld.prog.join()
         return outs
 
     def record(self, bld, x_act, logits_nchw=None, maps_c8=None):

@@ -83,7 +83,10 @@ class StreamingMFCNet:
             b.prog.finalize()
             self.fus.append(b.prog)
         self.launches_per_frame = self.sfc[0].n_kernels + self.fus[0].n_kernels
-        self.use_graphs = os.environ.get("MFC_STREAM_GRAPH", "1") != "0" and dev.type == "cuda"
+        # measured on B200: replaying a graph with parallel branches (HRNet's lanes) is slower than issuing the lanes on real
+        # streams (109 vs 206 frames/s for HRNetMulti-Large K=5), single-lane programs are the same or slightly faster as a graph
+        self.use_graphs = (os.environ.get("MFC_STREAM_GRAPH", "1") != "0" and dev.type == "cuda"
+                           and not any(p.has_lanes for p in self.sfc + self.fus))
         self.graphs = [None] * K      # slot -> CUDA graph of (SFC of the new frame + fusion head), captured after one eager run
         self._ran_eager = [False] * K
         self._keep = (packer, arena_sfc, arena_fus)
