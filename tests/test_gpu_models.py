@@ -219,3 +219,45 @@ def test_weight_update_invalidates_plan(M):
         net.output_layer.bias.add_(1.0)
         y1 = net(x)
     assert torch.allclose(y1, y0 + 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("family", ["resunet", "hrnet"])
+def test_streaming_runner_matches_window_forward(M, family):
+    """StreamingMFCNet (feature ring, static inputs, CUDA-graph replay for single-lane programs / concurrent lanes for HRNet)
+    against the wrapper's own batch forward on the same K-frame windows."""
+    torch.manual_seed(3)
+    N, K, H, W = 5, 3, 64, 96
+    cls = M.ResUNetMultiLarge if family == "resunet" else M.HRNetMultiLarge
+    net = cls(N, K, pretrained=False, loadpath=None, optflow_inputs=True, depth_inputs=True).cuda().eval()
+    if family == "hrnet":     # random-init HRNet logits are O(1e3): scale the head as the fixtures do
+        with torch.no_grad():
+            net.base_model.last_layer[3].weight.mul_(1e-3)
+            net.base_model.last_layer[3].bias.mul_(1e-3)
+    run = M.StreamingMFCNet(net, H, W)
+    T = 3 * K + 2             # long enough to replay every ring slot's graph at least once
+    frames = [torch.randn(1, 3, H, W, device="cuda") for _ in range(T)]
+    flows = [[2 * torch.randn(1, 2, H, W, device="cuda") for _ in range(K - 1)] for _ in range(T)]
+    depths = [[torch.rand(1, 1, H, W, device="cuda") for _ in range(K)] for _ in range(T)]
+    worst = 0.0
+    with torch.no_grad():
+        for t in range(T):
+            y = run.step(frames[t], flows[t], depths[t])
+            if t < K - 1:
+                assert y is None
+                continue
+            ref = net([frames[t - i] for i in range(K)], optflow=flows[t], depth=depths[t])
+            worst = max(worst, float((y - ref).abs().max()))
+    # same kernels, same fp16 storage; only the batch composition of the SFC pass (hence the autotuned tiling) differs
+    assert worst <= 5e-3, worst
+
+
+def test_conv_formulations_agree_in_a_fresh_process():
+    """tools/conv_diag.py (36 single-conv cases against torch fp32) with the sliding-accumulate formulation forced on, in
+    its own process: the planner switch is read once per process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MFC_CONV_SLIDE="1", MFC_CONV_TUNE="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "conv_diag.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "0 bad" in r.stdout.strip().splitlines()[-1], r.stdout[-2000:]

@@ -183,3 +183,23 @@ def test_product_never_imports_oracle():
             with open(os.path.join(pkg, fn)) as f:
                 src = f.read()
             assert "oracle" not in src.replace("torch_oracle", "oracle") or fn == "" , fn
+
+
+def test_hrnet_program_lanes_are_balanced(M):
+    """The HRNet plan records module branches on lanes 0..3 between FORK / JOIN pairs; every list ends joined on lane 0."""
+    net = M.HighResolutionNet(num_classes=5).eval()
+    net(torch.zeros(1, 3, 64, 96))                    # plan-only forward
+    prog = net._plans[(1, 64, 96)][0]
+    depth, lanes = 0, set()
+    for op, _, _, lane in prog.cmds:
+        assert 0 <= lane < M.abi.MFC_MAX_LANES
+        lanes.add(lane)
+        if op == M.abi.OP_FORK:
+            depth += 1
+        elif op == M.abi.OP_JOIN:
+            depth -= 1
+            assert lane == 0
+        else:
+            assert lane == 0 or depth == 1
+        assert depth in (0, 1)
+    assert depth == 0 and prog.cmds[-1][3] == 0 and len(lanes) > 1
