@@ -336,7 +336,7 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
     if (g_tuned.count(key)) return MFC_OK;
   }
   std::vector<mfc::ConvTiling> cands;
-  mfc::conv_shortlist(*d, 3, cands);
+  mfc::conv_shortlist(*d, getenv("MFC_CONV_TUNE_WIDTH") ? atoi(getenv("MFC_CONV_TUNE_WIDTH")) : 3, cands);
   if (cands.empty()) return fail(MFC_EINVAL, "conv: no tiling fits shared memory / TMEM for this shape");
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t e0, e1;
@@ -534,6 +534,22 @@ int mfc_correlation_fwd(const float* first, const float* second, float* out, int
   if (!first || !second || !out || B < 1 || C < 1 || H < 1 || W < 1) return fail(MFC_EINVAL, "correlation: bad argument");
   if (stride2 != 1 && stride2 != 2) return fail(MFC_EINVAL, "correlation: stride2 %d unsupported (1 or 2)", stride2);
   if (max_disp < 0 || max_disp > 32 || max_disp % stride2) return fail(MFC_EINVAL, "correlation: max_disp %d unsupported", max_disp);
+  if (!exact_order && mfc::correlation_tma_supported(C, H, W, max_disp, stride2) && !(((uintptr_t)first | (uintptr_t)second | (uintptr_t)out) & 15) &&
+      encode_tiled_fn()) {
+    // both operands as (W, H, C, B) fp32 tensors; boxes = the CTA tile (+ halo for `second`), zero fill outside the image
+    CUtensorMap m1, m2;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    cuuint32_t b1[4], b2[4], es[4] = {1, 1, 1, 1};
+    mfc::correlation_tma_boxes(H, W, b1, b2);
+    EncodeTiledFn enc = encode_tiled_fn();
+    CUresult r1 = enc(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(first), dims, strides, b1, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&m2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(second), dims, strides, b2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS)
+      MFC_LAUNCH(mfc::launch_correlation_tma(m1, m2, out, B, C, H, W, (cudaStream_t)stream), "correlation (tma)");
+  }
   MFC_LAUNCH(mfc::launch_correlation(first, second, out, B, C, H, W, max_disp, stride2, exact_order, (cudaStream_t)stream), "correlation");
 }
 
