@@ -540,15 +540,15 @@ int mfc_correlation_fwd(const float* first, const float* second, float* out, int
     CUtensorMap m1, m2;
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
-    cuuint32_t b1[4], b2[4], es[4] = {1, 1, 1, 1};
-    mfc::correlation_tma_boxes(H, W, b1, b2);
+    cuuint32_t b1[4], b2[4], es[4];
+    mfc::correlation_tma_boxes(H, W, stride2, b1, b2, es);
     EncodeTiledFn enc = encode_tiled_fn();
     CUresult r1 = enc(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(first), dims, strides, b1, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CUresult r2 = enc(&m2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(second), dims, strides, b2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS)
-      MFC_LAUNCH(mfc::launch_correlation_tma(m1, m2, out, B, C, H, W, (cudaStream_t)stream), "correlation (tma)");
+      MFC_LAUNCH(mfc::launch_correlation_tma(m1, m2, out, B, C, H, W, stride2, (cudaStream_t)stream), "correlation (tma)");
   }
   MFC_LAUNCH(mfc::launch_correlation(first, second, out, B, C, H, W, max_disp, stride2, exact_order, (cudaStream_t)stream), "correlation");
 }

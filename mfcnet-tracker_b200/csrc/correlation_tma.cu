@@ -144,8 +144,96 @@ __global__ void __launch_bounds__(CtCfg<TXG, TY, NST>::Threads, (CtCfg<TXG, TY, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stride-2 variant (the reference's own operating point: max displacement 20, stride 2, D = 21, 441 output channels).
+// Vertical displacements are even, so an output row only meets rows of `second` with its own parity: a CTA works on ONE row
+// parity and its TMA boxes traverse H with stride 2 (elementStrides; TMA has no traversal stride on the innermost dimension,
+// so columns stay interleaved).  A thread owns 4 ADJACENT image pixels x 21 dx for one (row, dy): its 44-float window of
+// `second` (11 LDS.128) serves both column parities -- pixel a, displacement d reads window[a + 2d] -- so no loaded value is
+// wasted: 12 LDS.128 per 84 FMAs, float4 stores.  Tile = TY2 rows (parity space) x 32 columns; threads = 8 x TY2 x 21.
+constexpr int kC2R = 10, kC2D = 21, kC2TXG = 8, kC2TX = 32, kC2TY = 2, kC2CK = 8, kC2NST = 2;
+constexpr int kC2F2Rows = kC2TY + 2 * kC2R, kC2F2Cols = kC2TX + 4 * kC2R;     // 22 x 72 (columns in image space)
+constexpr int kC2Threads = kC2TXG * kC2TY * kC2D;                             // 336
+constexpr int kC2F1Stage = kC2CK * kC2TY * kC2TX, kC2F2Stage = kC2CK * kC2F2Rows * kC2F2Cols;
+constexpr int kC2F1Bytes = (kC2F1Stage * 4 + 127) / 128 * 128;
+constexpr int kC2StageBytes = kC2F1Bytes + (kC2F2Stage * 4 + 127) / 128 * 128;
+constexpr int kC2Smem = kC2NST * kC2StageBytes + 1024;
+
+__global__ void __launch_bounds__(kC2Threads, 1) correlation_tma_s2_kernel(const __grid_constant__ CUtensorMap map1,
+                                                                           const __grid_constant__ CUtensorMap map2,
+                                                                           float* __restrict__ out, int B, int C, int H, int W,
+                                                                           int tiles_x, int tiles_y) {
+  extern __shared__ uint8_t ct_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ct_smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[kC2NST];
+  int bid = blockIdx.x;
+  const int py = bid & 1; bid >>= 1;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int b = bid / tiles_y;
+  const int x0 = tx * kC2TX, yp0 = ty * kC2TY;          // columns in image space, rows in parity space (y = 2 yp + py)
+  const int t = threadIdx.x;
+  const int g = t % kC2TXG, k = t / kC2TXG;
+  const int j = k / kC2D, iy = k - j * kC2D;             // output row of the tile, vertical displacement index (dy = 2 (iy - R))
+  const int r_s = j + iy;                                // row of the staged `second` tile (tile row 0 = parity row yp0 - R)
+  if (t == 0) {
+    for (int i = 0; i < kC2NST; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int nst = (C + kC2CK - 1) / kC2CK;
+  auto issue = [&](int st) {
+    uint8_t* buf = smem + (size_t)(st % kC2NST) * kC2StageBytes;
+    mbar_arrive_expect_tx(&full[st % kC2NST], (uint32_t)((kC2F1Stage + kC2F2Stage) * 4));
+    tma_load_4d(buf, &map1, &full[st % kC2NST], x0, 2 * yp0 + py, st * kC2CK, b);
+    tma_load_4d(buf + kC2F1Bytes, &map2, &full[st % kC2NST], x0 - 2 * kC2R, 2 * (yp0 - kC2R) + py, st * kC2CK, b);
+  };
+  if (t == 0)
+    for (int i = 0; i < kC2NST - 1 && i < nst; ++i) issue(i);
+  float acc[4][kC2D];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int d = 0; d < kC2D; ++d) acc[a][d] = 0.0f;
+  for (int st = 0; st < nst; ++st) {
+    if (t == 0 && st + kC2NST - 1 < nst) issue(st + kC2NST - 1);
+    mbar_wait(&full[st % kC2NST], (uint32_t)((st / kC2NST) & 1));
+    const uint32_t s1 = smem_u32(smem) + (uint32_t)(st % kC2NST) * (uint32_t)kC2StageBytes + (uint32_t)(j * kC2TX + 4 * g) * 4u;
+    const uint32_t s2 = smem_u32(smem) + (uint32_t)(st % kC2NST) * (uint32_t)kC2StageBytes + (uint32_t)kC2F1Bytes +
+                        (uint32_t)(r_s * kC2F2Cols + 4 * g) * 4u;
+    for (int cc = 0; cc < kC2CK; ++cc) {
+      const uint32_t q2 = s2 + (uint32_t)(cc * (kC2F2Rows * kC2F2Cols)) * 4u;
+      const float4 a4 = lds_f4s(s1 + (uint32_t)(cc * (kC2TY * kC2TX)) * 4u);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      float w[44];
+#pragma unroll
+      for (int i = 0; i < 11; ++i) {
+        const float4 v = lds_f4s(q2 + 16u * i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int d = 0; d < kC2D; ++d) acc[a][d] = fmaf(av[a], w[a + 2 * d], acc[a][d]);
+    }
+    __syncthreads();
+  }
+  const float cf = (float)C;
+  const int y = 2 * (yp0 + j) + py;
+  const int x = x0 + 4 * g;
+  if (y < H && x < W) {
+    const size_t HW = (size_t)H * W;
+    float* o = out + ((size_t)b * kC2D * kC2D + (size_t)iy * kC2D) * HW + (size_t)y * W + x;
+#pragma unroll
+    for (int d = 0; d < kC2D; ++d)
+      *reinterpret_cast<float4*>(o + (size_t)d * HW) =
+          make_float4(__fdiv_rn(acc[0][d], cf), __fdiv_rn(acc[1][d], cf), __fdiv_rn(acc[2][d], cf), __fdiv_rn(acc[3][d], cf));
+  }
+}
+
 bool correlation_tma_supported(int C, int H, int W, int max_disp, int stride2) {
-  return stride2 == 1 && max_disp == kCtR && (W % 4) == 0 && C >= 1 && H >= 1;
+  if ((W % 4) != 0 || C < 1 || H < 1) return false;
+  return (stride2 == 1 && max_disp == kCtR) || (stride2 == 2 && max_disp == 2 * kC2R);
 }
 
 // Tile shape.  Measured on B200 (B=8, C=64, 120x160, md 4): 32 x 4 tiles (160 threads, 3 CTAs per SM, no spills) 70.6 us,
@@ -180,7 +268,22 @@ static cudaError_t ct_launch(const CUtensorMap& map1, const CUtensorMap& map2, f
 }
 
 cudaError_t launch_correlation_tma(const CUtensorMap& map1, const CUtensorMap& map2, float* out, int B, int C, int H, int W,
-                                   cudaStream_t st) {
+                                   int stride2, cudaStream_t st) {
+  if (stride2 == 2) {
+    static int configured_for = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_for != dev) {
+      cudaError_t e = cudaFuncSetAttribute(correlation_tma_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2Smem);
+      if (e != cudaSuccess) return e;
+      configured_for = dev;
+    }
+    const int Hp = (H + 1) / 2;   // rows of one parity class (class 0; class 1 is not larger)
+    const int tiles_x = (W + kC2TX - 1) / kC2TX, tiles_y = (Hp + kC2TY - 1) / kC2TY;
+    correlation_tma_s2_kernel<<<(unsigned)(B * tiles_x * tiles_y * 2), kC2Threads, kC2Smem, st>>>(map1, map2, out, B, C, H, W, tiles_x,
+                                                                                                  tiles_y);
+    return cudaGetLastError();
+  }
   switch (ct_pick_tx(W)) {
     case 32:
       if (ct_ty(H) == 16) return ct_launch<8, 16, 3>(map1, map2, out, B, C, H, W, st);
@@ -191,7 +294,15 @@ cudaError_t launch_correlation_tma(const CUtensorMap& map1, const CUtensorMap& m
   }
 }
 
-void correlation_tma_boxes(int H, int W, unsigned* box1, unsigned* box2) {
+void correlation_tma_boxes(int H, int W, int stride2, unsigned* box1, unsigned* box2, unsigned* estride) {
+  estride[0] = 1;
+  estride[1] = (unsigned)stride2;
+  estride[2] = estride[3] = 1;
+  if (stride2 == 2) {   // the row extent is in tensor elements: twice the number of (stride-2) rows taken
+    box1[0] = kC2TX; box1[1] = 2 * kC2TY; box1[2] = kC2CK; box1[3] = 1;
+    box2[0] = kC2F2Cols; box2[1] = 2 * kC2F2Rows; box2[2] = kC2CK; box2[3] = 1;
+    return;
+  }
   const int tx = ct_pick_tx(W), ty = tx == 128 ? 4 : (tx == 32 ? ct_ty(H) : 8);
   box1[0] = tx; box1[1] = ty; box1[2] = kCtCK; box1[3] = 1;
   box2[0] = tx + 2 * kCtR; box2[1] = ty + 2 * kCtR; box2[2] = kCtCK; box2[3] = 1;

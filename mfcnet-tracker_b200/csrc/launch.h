@@ -60,9 +60,9 @@ cudaError_t launch_correlation(const float* first, const float* second, float* o
 
 // correlation_tma.cu (stride-1, max displacement 4: TMA-fed register-tiled kernel)
 bool correlation_tma_supported(int C, int H, int W, int max_disp, int stride2);
-void correlation_tma_boxes(int H, int W, unsigned* box1, unsigned* box2);
+void correlation_tma_boxes(int H, int W, int stride2, unsigned* box1, unsigned* box2, unsigned* estride);
 cudaError_t launch_correlation_tma(const CUtensorMap& map1, const CUtensorMap& map2, float* out, int B, int C, int H, int W,
-                                   cudaStream_t st);
+                                   int stride2, cudaStream_t st);
 
 // localize.cu
 cudaError_t launch_gaussian_blur(const float* heat, float* tmp, float* out, int B, int H, int W, const double* w, int radius,
