@@ -158,8 +158,9 @@ int encode_source_maps(const MfcConvDesc* d, mfc::ConvParams* p) {
     cuuint64_t dims[5] = {8, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->src[i].nchunks, (cuuint64_t)d->B};
     cuuint64_t strides[4] = {16, (cuuint64_t)d->Win * 16, plane,
                              d->B > 1 ? (cuuint64_t)d->src[i].batch_stride : plane * (cuuint64_t)d->src[i].nchunks};
-    cuuint32_t box[5] = {8, (cuuint32_t)p->t.P, (cuuint32_t)p->t.rows_sub, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint32_t st = (cuuint32_t)d->stride;  // stride 2: box extents in tensor elements, every second one is taken
+    cuuint32_t box[5] = {8, (cuuint32_t)p->t.P * st, (cuuint32_t)p->t.rows_sub * st, 1, 1};
+    cuuint32_t estr[5] = {1, st, st, 1, 1};
     CUresult r = enc(&p->tmap[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(d->src[i].ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

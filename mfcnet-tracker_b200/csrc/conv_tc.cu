@@ -246,7 +246,8 @@ __device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* ab
   const int ksteps_per_stage = p.t.CBc / 2;
   const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
   const int nplanes = p.t.pair ? 1 : 2 * nks;
-  const uint32_t box_bytes = (uint32_t)(p.t.rows_sub * p.t.P) * 16u;
+  const int nsub = p.stride * p.stride;
+  const uint32_t box_bytes = (uint32_t)(p.t.rows_sub * p.t.P) * 16u * (uint32_t)nsub;
   const uint32_t w_bytes = p.t.b_resident ? 0u : (uint32_t)(nks * p.t.entries * 2 * p.t.nrows_b) * 16u;
   mbar_arrive_expect_tx(bar, (uint32_t)nplanes * box_bytes + w_bytes);
   if (w_bytes) {
@@ -262,7 +263,13 @@ __device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* ab
       while (k >= p.src_end[si]) ++si;
       k -= si ? p.src_end[si - 1] : 0;
     }
-    tma_load_5d(abuf + (size_t)q * p.t.plane_bytes, &p.tmap[si], bar, 0, ix_base, iy_base, k, b);
+    uint8_t* plane = abuf + (size_t)q * p.t.plane_bytes;
+    if (nsub == 1) {
+      tma_load_5d(plane, &p.tmap[si], bar, 0, ix_base, iy_base, k, b);
+    } else {  // stride 2: sub-plane (py, px) = the pixels (iy_base + 2r + py, ix_base + 2c + px), box traversal stride 2
+      for (int sub = 0; sub < 4; ++sub)
+        tma_load_5d(plane + (size_t)sub * p.t.slots_sub * 16, &p.tmap[si], bar, 0, ix_base + (sub & 1), iy_base + (sub >> 1), k, b);
+    }
   }
 }
 
@@ -1187,7 +1194,8 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
   const bool pair = cin_chunks == 1 && s == 1 && d.upsample == 1 && d.kw > 1;
   // stride-1, no-upsample convs stage their halo tiles with TMA box loads (one instruction per 8-channel plane,
   // hardware zero fill outside the image); box extents are limited to 256 per dimension
-  const bool tma = s == 1 && d.upsample == 1;
+  // (stride-2 convs: four box loads per plane with a traversal stride of 2 on W and H de-interleave the parity sub-planes)
+  const bool tma = d.upsample == 1;
   const int ksteps = ceil_div(cin_chunks, 2);
   // N-block width: by default as wide as possible (<= 128).  Layers with few pixels (the low-resolution HRNet / bottleneck
   // stages) produce fewer work items than there are SMs; narrower N-blocks multiply the items and divide the weights each
@@ -1227,10 +1235,11 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
     const int nacc = (2 * R * NB * kacc <= 512) ? 2 : 1;
     const uint32_t tmem = pow2_at_least((uint32_t)(nacc * R * NB * kacc), 32);
     const int rows_sub = TH + hy;
-    const int slots_sub = slide ? rows_sub * P + hx + 1 : std::max(R * 128 + hy * P + hx, rows_sub * P);
+    int slots_sub = slide ? rows_sub * P + hx + 1 : std::max(R * 128 + hy * P + hx, rows_sub * P);
+    if (s == 2) slots_sub = (slots_sub + 7) & ~7;  // every parity sub-plane is a TMA destination: 128-byte aligned
     const uint32_t plane_bytes = ((uint32_t)(s * s) * slots_sub * 16 + 127u) & ~127u;  // TMA destinations: 128-byte aligned
     if (plane_bytes > 200000u) return false;
-    if (tma && (P > 256 || rows_sub > 256)) return true;
+    if (tma && (P * s > 256 || rows_sub * s > 256)) return true;
     const int tiles_x = nx, tiles_y = ceil_div(d.Hout, TH);
     const long long items = (long long)d.B * tiles_x * tiles_y * nblk;
     // K staging options: all channels in one stage, or 16/32/64/128-channel stages
