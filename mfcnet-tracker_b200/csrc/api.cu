@@ -160,6 +160,10 @@ int encode_source_maps(const MfcConvDesc* d, mfc::ConvParams* p) {
                              d->B > 1 ? (cuuint64_t)d->src[i].batch_stride : plane * (cuuint64_t)d->src[i].nchunks};
     const cuuint32_t st = (cuuint32_t)d->stride;  // stride 2: box extents in tensor elements, every second one is taken
     cuuint32_t box[5] = {8, (cuuint32_t)p->t.P * st, (cuuint32_t)p->t.rows_sub * st, 1, 1};
+    if (d->upsample == 2) {  // the low-resolution tile; the producer warps expand it x2 in shared memory
+      box[1] = (cuuint32_t)p->t.P_lo;
+      box[2] = (cuuint32_t)p->t.rows_lo;
+    }
     cuuint32_t estr[5] = {1, st, st, 1, 1};
     CUresult r = enc(&p->tmap[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(d->src[i].ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

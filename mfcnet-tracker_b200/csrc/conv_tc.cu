@@ -247,7 +247,8 @@ __device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* ab
   const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
   const int nplanes = p.t.pair ? 1 : 2 * nks;
   const int nsub = p.stride * p.stride;
-  const uint32_t box_bytes = (uint32_t)(p.t.rows_sub * p.t.P) * 16u * (uint32_t)nsub;
+  const bool ups = p.upsample == 2;
+  const uint32_t box_bytes = ups ? (uint32_t)(p.t.rows_lo * p.t.P_lo) * 16u : (uint32_t)(p.t.rows_sub * p.t.P) * 16u * (uint32_t)nsub;
   const uint32_t w_bytes = p.t.b_resident ? 0u : (uint32_t)(nks * p.t.entries * 2 * p.t.nrows_b) * 16u;
   mbar_arrive_expect_tx(bar, (uint32_t)nplanes * box_bytes + w_bytes);
   if (w_bytes) {
@@ -264,11 +265,45 @@ __device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* ab
       k -= si ? p.src_end[si - 1] : 0;
     }
     uint8_t* plane = abuf + (size_t)q * p.t.plane_bytes;
-    if (nsub == 1) {
+    if (ups) {  // the low-resolution pixels the upsampled tile maps to: (iy >> 1, ix >> 1), arithmetic shifts (padding rows/columns -> -1)
+      tma_load_5d(abuf + p.t.off_lo + (size_t)q * p.t.lo_plane_bytes, &p.tmap[si], bar, 0, ix_base >> 1, iy_base >> 1, k, b);
+    } else if (nsub == 1) {
       tma_load_5d(plane, &p.tmap[si], bar, 0, ix_base, iy_base, k, b);
     } else {  // stride 2: sub-plane (py, px) = the pixels (iy_base + 2r + py, ix_base + 2c + px), box traversal stride 2
       for (int sub = 0; sub < 4; ++sub)
         tma_load_5d(plane + (size_t)sub * p.t.slots_sub * 16, &p.tmap[si], bar, 0, ix_base + (sub & 1), iy_base + (sub >> 1), k, b);
+    }
+  }
+}
+
+// nearest x2 with TMA: plane[r][c] = box[((iy_base + r) >> 1) - (iy_base >> 1)][((ix_base + c) >> 1) - (ix_base >> 1)]; slots outside the
+// upsampled image map to box entries outside the low-resolution image, which TMA filled with zeros.  Same flat slot-to-thread
+// mapping as the affine pass, so a thread later transforms exactly the slots it expanded itself.
+template <int NT>
+__device__ __forceinline__ void expand_stage(const ConvParams& p, uint8_t* abuf, int ks, int iy_base, int ix_base, int tid) {
+  const int ksteps_per_stage = p.t.CBc / 2;
+  const int nks = min(ksteps_per_stage, p.t.ksteps - ks * ksteps_per_stage);
+  const int P = p.t.P, items = p.t.rows_sub * P, P_lo = p.t.P_lo;
+  const int ly0 = iy_base >> 1, lx0 = ix_base >> 1;
+  const FastDiv divP = p.divP;
+  constexpr int U = 4;
+  for (int q = 0; q < 2 * nks; ++q) {
+    const uint32_t dst = smem_u32(abuf) + (uint32_t)q * p.t.plane_bytes;
+    const uint32_t src = smem_u32(abuf) + p.t.off_lo + (uint32_t)q * p.t.lo_plane_bytes;
+    for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = idx0 + u * NT;
+        if (idx < items) {
+          const int r = (int)fdiv((uint32_t)idx, divP);
+          const int c = idx - r * P;
+          v[u] = lds16_u32(src + (uint32_t)((((iy_base + r) >> 1) - ly0) * P_lo + (((ix_base + c) >> 1) - lx0)) * 16u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (idx0 + u * NT < items) sts16_u32(dst + (uint32_t)(idx0 + u * NT) * 16u, v[u]);
     }
   }
 }
@@ -893,9 +928,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       } else {
         cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // this thread's copies of the hand-off stage have landed
       }
-      if (!(p.debug & 1))
+      if (!(p.debug & 1)) {
+        if (tma && p.upsample == 2)
+          expand_stage<kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, kst, c.oy0 * p.stride - p.pad + p.in_off_y,
+                                     c.ox0 * p.stride - p.pad + p.in_off_x, ptid);
         transform_stage<BF16, kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, c.b, kst,
                                             c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x, ptid, aff0);
+      }
       fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[slot_t]);
@@ -1195,7 +1234,8 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
   // stride-1, no-upsample convs stage their halo tiles with TMA box loads (one instruction per 8-channel plane,
   // hardware zero fill outside the image); box extents are limited to 256 per dimension
   // (stride-2 convs: four box loads per plane with a traversal stride of 2 on W and H de-interleave the parity sub-planes)
-  const bool tma = d.upsample == 1;
+  const bool tma = d.upsample == 1 || (d.upsample == 2 && s == 1);
+  const bool ups_tma = d.upsample == 2 && tma;  // the low-resolution tile comes in by TMA and is expanded x2 in shared memory
   const int ksteps = ceil_div(cin_chunks, 2);
   // N-block width: by default as wide as possible (<= 128).  Layers with few pixels (the low-resolution HRNet / bottleneck
   // stages) produce fewer work items than there are SMs; narrower N-blocks multiply the items and divide the weights each
@@ -1251,7 +1291,10 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
       const bool resident = kstages == 1 && nblk == 1;
       const uint32_t a_stage = (uint32_t)CBc * plane_bytes;
       const uint64_t b_stage = (uint64_t)(CBc / 2) * entries * 2 * nrows_b * 16;
-      const uint64_t stage_bytes = ((uint64_t)a_stage + (resident ? 0 : b_stage) + 127) & ~(uint64_t)127;
+      const int P_lo = P / 2 + 2, rows_lo = rows_sub / 2 + 2;
+      const uint32_t lo_plane_bytes = ups_tma ? ((uint32_t)(P_lo * rows_lo) * 16u + 127u) & ~127u : 0u;
+      const uint64_t off_lo = ((uint64_t)a_stage + (resident ? 0 : b_stage) + 127) & ~(uint64_t)127;
+      const uint64_t stage_bytes = (off_lo + (uint64_t)CBc * lo_plane_bytes + 127) & ~(uint64_t)127;
       const uint64_t off_stage = ((uint64_t)off_bres + (resident ? w_bytes_nblk : 0) + 127) & ~(uint64_t)127;
       if (off_stage + stage_bytes + 128 > (uint64_t)kSmemPerCtaMax) continue;
       int nstages = (int)(((uint64_t)kSmemPerCtaMax - 128 - off_stage) / stage_bytes);
@@ -1316,6 +1359,7 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
         best.slide = slide ? 1 : 0; best.nrows_b = nrows_b;
         best.tiles_x = tiles_x; best.tiles_y = tiles_y;
         best.NB = NB; best.nblk = nblk; best.ksteps = ksteps; best.cin_chunks = cin_chunks;
+        best.P_lo = P_lo; best.rows_lo = rows_lo; best.lo_plane_bytes = lo_plane_bytes; best.off_lo = (uint32_t)off_lo;
         best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;
         best.stage_bytes = (uint32_t)stage_bytes;
         best.smem_bytes = smem; best.tmem_cols = tmem; best.acc_cols = (uint32_t)(R * NB * kacc);

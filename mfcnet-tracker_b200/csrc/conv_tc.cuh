@@ -40,6 +40,9 @@ struct ConvTiling {
                      //    accumulator columns of the output rows r-ky, which are adjacent column blocks [row][NB] in TMEM.
                      //    kh x fewer MMAs and A-operand reads than one MMA per tap; accumulators are zeroed by the epilogue.
   int nrows_b;       // rows (N) of one packed B block: NB, or kh*NB in slide mode (N-group g' = kh-1-ky)
+  int P_lo, rows_lo;          // nearest-x2 convs with TMA: extent of the LOW-resolution box staged per plane ...
+  uint32_t lo_plane_bytes;    // ... its size, and where the boxes sit inside a stage (after the planes and the streamed weights);
+  uint32_t off_lo;            //     the producer warps expand them x2 into the planes
   int tma;           // 1: stride-1, no-upsample conv: the halo tile of every plane is ONE TMA box load (zero fill = padding)
   int b_resident;    // 1: the whole packed weight blob is loaded once per CTA; 0: streamed with each stage
   int tiles_x, tiles_y;
