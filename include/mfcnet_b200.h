@@ -312,6 +312,15 @@ int mfc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 
+/* Frame ingest of the video loop (scripts/test_multiframe_segmentation_on_videos_v3.py:234-258), bit-exact with its numpy /
+ * torchvision arithmetic.  `bgr`: B uint8 frames [H][W][3] as cv2 delivers them (device memory, frame_stride_bytes apart),
+ * already at the network's input size.
+ *   mfc_ingest_rgb  : BGR2RGB -> /255 -> (t - mean[c]) / std[c]  -> fp32 [B][3][H][W]   (mean / std: 3 HOST floats each)
+ *   mfc_ingest_depth: OpenCV's fixed-point BGR2GRAY -> /255       -> fp32 [B][1][H][W] */
+int mfc_ingest_rgb(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, const float* mean3_host,
+                   const float* std3_host, void* stream);
+int mfc_ingest_depth(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * UnFlow correlation cost volume (models/unflow_correlation.py:10-105,282-337).
  * first/second: fp32 NCHW contiguous; out: fp32 [B][D*D][H][W], D = 2*(max_disp/stride2)+1,

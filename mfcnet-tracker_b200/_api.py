@@ -5,6 +5,7 @@ from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
 from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxima_and_estimate_centroids, gaussian_blur,
                       heatmap_head, predicted_keypoints)
 from .hrnet import HighResolutionNet
+from .ingest import ingest_depth, ingest_rgb
 from .loss import segmentation_loss
 from .multiframe import (HRNetMultiBasic, HRNetMultiLarge, ResUNetMultiBasic, ResUNetMultiLarge, TernausNetMultiBasic,
                          TernausNetMultiLarge)
@@ -17,7 +18,7 @@ __all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic"
            "FunctionCorrelation", "ModuleCorrelation", "correlation", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
            "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames", "segmentation_loss",
-           "DataParallelTrainer", "autograd_forward", "loss_and_grad"]
+           "DataParallelTrainer", "autograd_forward", "loss_and_grad", "ingest_rgb", "ingest_depth"]
 
 
 def get_tooltip_segmentation_model(args):

@@ -127,6 +127,8 @@ _SIGNATURES = {
     "mfc_segmentation_loss_from_sums": ([c_void_p, c_int, c_float, c_float, c_void_p, c_void_p], c_int),
     "mfc_segmentation_loss_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_float, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "mfc_adam_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p], c_int),
+    "mfc_ingest_rgb": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p], c_int),
+    "mfc_ingest_depth": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_correlation_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_gaussian_blur": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p], c_int),
     "mfc_localmax_mask": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p], c_int),

@@ -532,6 +532,21 @@ int mfc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
              "adam_step");
 }
 
+// ---- frame ingest --------------------------------------------------------------------------------
+int mfc_ingest_rgb(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, const float* mean3_host,
+                   const float* std3_host, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!bgr || !out || !mean3_host || !std3_host || B < 1 || H < 1 || W < 1 || frame_stride_bytes < (long long)H * W * 3)
+    return fail(MFC_EINVAL, "ingest_rgb: bad argument");
+  MFC_LAUNCH(mfc::launch_ingest_rgb(bgr, frame_stride_bytes, out, B, (long long)H * W, mean3_host, std3_host, (cudaStream_t)stream), "ingest_rgb");
+}
+
+int mfc_ingest_depth(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!bgr || !out || B < 1 || H < 1 || W < 1 || frame_stride_bytes < (long long)H * W * 3) return fail(MFC_EINVAL, "ingest_depth: bad argument");
+  MFC_LAUNCH(mfc::launch_ingest_depth(bgr, frame_stride_bytes, out, B, (long long)H * W, (cudaStream_t)stream), "ingest_depth");
+}
+
 // ---- correlation -------------------------------------------------------------------------------
 int mfc_correlation_fwd(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp, int stride2,
                         int exact_order, void* stream) {

@@ -64,6 +64,11 @@ void correlation_tma_boxes(int H, int W, int stride2, unsigned* box1, unsigned* 
 cudaError_t launch_correlation_tma(const CUtensorMap& map1, const CUtensorMap& map2, float* out, int B, int C, int H, int W,
                                    int stride2, cudaStream_t st);
 
+// ingest.cu
+cudaError_t launch_ingest_rgb(const uint8_t* bgr, long long frame_stride, float* out, int B, long long pixels, const float* mean,
+                              const float* stdv, cudaStream_t st);
+cudaError_t launch_ingest_depth(const uint8_t* bgr, long long frame_stride, float* out, int B, long long pixels, cudaStream_t st);
+
 // localize.cu
 cudaError_t launch_gaussian_blur(const float* heat, float* tmp, float* out, int B, int H, int W, const double* w, int radius,
                                  cudaStream_t st);
