@@ -75,12 +75,18 @@ __global__ void class_mask_kernel(const uint8_t* __restrict__ cls, int cls_id, u
 }
 
 // ---- connected components (union-find; the root of a set is its smallest linear index) ----------
+// find with path halving: a non-root's label only ever moves to one of its ancestors (a plain store is enough: any value it
+// can hold is a valid ancestor), roots change only through the atomicMin of uf_union.  Without it the chains of the big
+// background region are hundreds of hops long and every hop is an L2 round trip.
 __device__ __forceinline__ int uf_find(int* lab, int a) {
+  volatile int* v = reinterpret_cast<volatile int*>(lab);
   int r = a;
   while (true) {
-    const int p = reinterpret_cast<volatile int*>(lab)[r];
+    const int p = v[r];
     if (p == r) break;
-    r = p;
+    const int g = v[p];
+    if (g != p) v[r] = g;
+    r = g;
   }
   return r;
 }
@@ -100,10 +106,21 @@ __device__ __forceinline__ void uf_union(int* lab, int a, int b) {
   }
 }
 
-__global__ void ccl_init_kernel(int* __restrict__ lab, int* __restrict__ flag, int n, int* __restrict__ n_out) {
+// Initial label = the first pixel of the pixel's horizontal run inside its 32-pixel warp segment (ballot of the run-start bits),
+// so the horizontal part of every component is already merged up to segment boundaries before the union pass starts.
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lab, int* __restrict__ flag, int n, int W,
+                                int* __restrict__ n_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool start = true;
   if (i < n) {
-    lab[i] = i;
+    const int x = i % W;
+    start = x == 0 || ((mask[i] != 0) != (mask[i - 1] != 0));
+  }
+  const unsigned bits = __ballot_sync(0xffffffffu, start || lane == 0);
+  if (i < n) {
+    const unsigned below = bits & (0xffffffffu >> (31 - lane));   // start bits at or below this lane (bit 0 is always set)
+    lab[i] = i - lane + (31 - __clz(below));
     flag[i] = 0;
   }
   if (i == 0) *n_out = 0;
@@ -182,7 +199,7 @@ cudaError_t launch_trace_contours(const uint8_t* mask, int H, int W, int* labels
   const int n = H * W;
   const int blocks = (n + 255) / 256;
   int* flag = labels + n;
-  ccl_init_kernel<<<blocks, 256, 0, st>>>(labels, flag, n, n_out);
+  ccl_init_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, n, W, n_out);
   ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, labels, H, W);
   ccl_flatten_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W);
   trace_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W, out, max_contours, n_out);

@@ -155,26 +155,102 @@ def determine_local_maxima_and_estimate_centroids(heatmap, argmax_u8, cls_id, ma
     return calc_centroids(loc)
 
 
+class _KeypointWorkspace:
+    """Per-(device, H, W) buffers and constants of `predicted_keypoints`: the gaussian taps and the circular footprint live on
+    the device once, the contour tracer's label / record buffers are reused, and the four contour lists of a frame come back
+    in ONE device-to-host copy (pinned) after ONE synchronisation -- the straightforward composition of the helpers above pays
+    two pageable uploads, four `.item()` syncs and four record downloads per frame."""
+    QUICK = 64          # contour records per mask fetched with the counts; more than that -> one more (full) copy for that mask
+
+    def __init__(self, device, H, W):
+        self.device, self.H, self.W = device, H, W
+        w, self.radius = gaussian_kernel1d(4)
+        self.taps = torch.from_numpy(w).to(device)
+        self.footprint = torch.from_numpy(np.ascontiguousarray(create_circular_mask(10, 10)).astype(np.uint8)).to(device)
+        self.amax = torch.empty((1, H, W), dtype=torch.uint8, device=device)
+        self.masks = torch.empty((4, H, W), dtype=torch.uint8, device=device)      # lb, lt, rb, rt
+        self.heat = torch.empty((2, H, W), dtype=torch.float32, device=device)     # class 4, class 2 probabilities
+        self.tmp = torch.empty_like(self.heat)
+        self.smooth = torch.empty_like(self.heat)
+        self.labels = torch.empty((4, 2 * H * W), dtype=torch.int32, device=device)
+        self.rec = torch.empty((4, MAX_CONTOURS, 6), dtype=torch.float64, device=device)
+        self.n = torch.zeros(4, dtype=torch.int32, device=device)
+        self.pack = torch.empty((4, self.QUICK * 6 + 1), dtype=torch.float64, device=device)   # [count | first QUICK records]
+        self.host = torch.empty((4, self.QUICK * 6 + 1), dtype=torch.float64).pin_memory()
+
+    def run(self, p):
+        lib = abi.load()
+        H, W, dev = self.H, self.W, self.device
+        st = _stream(dev)
+        with torch.cuda.device(dev):
+            abi.check(lib.mfc_argmax_u8(p.data_ptr(), 1, 5, H * W, self.amax.data_ptr(), st))
+            a = self.amax.data_ptr()
+            # bases: class masks (3 = left base, 1 = right base); tips: local maxima of the blurred class-4 / class-2 probability
+            abi.check(lib.mfc_class_mask(a, 3, self.masks[0].data_ptr(), H * W, st))
+            abi.check(lib.mfc_class_mask(a, 1, self.masks[2].data_ptr(), H * W, st))
+            self.heat[0].copy_(p[0, 4])
+            self.heat[1].copy_(p[0, 2])
+            abi.check(lib.mfc_gaussian_blur(self.heat.data_ptr(), self.tmp.data_ptr(), self.smooth.data_ptr(), 2, H, W, self.taps.data_ptr(),
+                                            self.radius, st))
+            for slot, (k, cls) in ((1, (0, 4)), (3, (1, 2))):
+                abi.check(lib.mfc_localmax_mask(self.smooth[k].data_ptr(), a, cls, self.footprint.data_ptr(), 10, 10,
+                                                self.masks[slot].data_ptr(), 1, H, W, st))
+            self.n.zero_()
+            for i in range(4):
+                abi.check(lib.mfc_trace_contours(self.masks[i].data_ptr(), H, W, self.labels[i].data_ptr(), self.rec[i].data_ptr(),
+                                                 MAX_CONTOURS, self.n[i:i + 1].data_ptr(), st))
+            self.pack[:, 0] = self.n.double()
+            self.pack[:, 1:] = self.rec[:, :self.QUICK].reshape(4, -1)
+            self.host.copy_(self.pack, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        out = []
+        for i in range(4):
+            cnt = int(self.host[i, 0])
+            if cnt > MAX_CONTOURS:
+                raise RuntimeError("trace_contours: %d contours exceed the %d-record buffer" % (cnt, MAX_CONTOURS))
+            if cnt <= self.QUICK:
+                raw = self.host[i, 1:1 + cnt * 6].reshape(cnt, 6).numpy()
+            else:
+                raw = self.rec[i, :cnt].cpu().numpy()
+            out.append(contour_records(raw, W))
+        return out
+
+
+_KP_WS = {}
+
+
+def _centroids_from_records(recs):
+    """calc_centroids (utils/localization_utils_v2.py:15-33) on contour records."""
+    cnts = sorted(recs, key=lambda r: r[0], reverse=True)[:2]
+    cX, cY = [], []
+    for area, m00, m10, m01, fx, fy in cnts:
+        if m00 == 0:
+            cX.append(fx)
+            cY.append(fy)
+        else:
+            cX.append(int(m10 / m00))
+            cY.append(int(m01 / m00))
+    return cX, cY
+
+
 def predicted_keypoints(prob):
     """The prediction half of `centroid_error` for 5 classes (utils/localization_utils_v2.py:193-212,
     :247-272): prob (1,5,H,W) device tensor -> c_pred = [rt_x, rt_y, rb_x, rb_y, lt_x, lt_y, lb_x, lb_y]
     with the reference's padding (tips duplicated / NaN-filled to length 2, bases NaN if absent)."""
     if prob.shape[0] != 1 or prob.shape[1] != 5:
         raise ValueError("predicted_keypoints expects a (1,5,H,W) probability map")
-    lib = abi.load()
+    if not prob.is_cuda:
+        raise RuntimeError("predicted_keypoints: CUDA tensors only (no CPU fallback)")
     p = prob.contiguous().float()
     _, _, H, W = p.shape
-    # numpy first-max argmax of the probabilities == heat-map head argmax on log-space inputs;
-    # here the input already is a probability map, so take the first maximum directly.
-    amax = torch.empty((1, H, W), dtype=torch.uint8, device=p.device)
-    with torch.cuda.device(p.device):
-        abi.check(lib.mfc_argmax_u8(p.data_ptr(), 1, 5, H * W, amax.data_ptr(), _stream(p.device)))
-    amax = amax[0]
-    mask = create_circular_mask(10, 10)
-    c_lb_x, c_lb_y = calc_centroids(class_mask(amax, 3))
-    c_lt_x, c_lt_y = determine_local_maxima_and_estimate_centroids(p[0, 4], amax, 4, mask)
-    c_rb_x, c_rb_y = calc_centroids(class_mask(amax, 1))
-    c_rt_x, c_rt_y = determine_local_maxima_and_estimate_centroids(p[0, 2], amax, 2, mask)
+    key = (p.device, H, W)
+    if key not in _KP_WS:
+        _KP_WS[key] = _KeypointWorkspace(p.device, H, W)
+    lb, lt, rb, rt = _KP_WS[key].run(p)
+    c_lb_x, c_lb_y = _centroids_from_records(lb)
+    c_lt_x, c_lt_y = _centroids_from_records(lt)
+    c_rb_x, c_rb_y = _centroids_from_records(rb)
+    c_rt_x, c_rt_y = _centroids_from_records(rt)
 
     def tips(xs, ys):
         if len(xs) == 0:
