@@ -32,12 +32,15 @@ def main():
     with torch.no_grad():
         for name, ctor, B in (("ResUNet-16 SFC", lambda: M.ResUnet_VB(3, 16, out_dim=N), 4),
                               ("HRNet-W48 SFC", lambda: M.HighResolutionNet(N), 4),
-                              ("HRNet-W48 SFC", lambda: M.HighResolutionNet(N), 1)):
+                              ("HRNet-W48 SFC", lambda: M.HighResolutionNet(N), 1),
+                              ("TernausNet16 SFC (762 GFLOP/frame)", lambda: M.TernausNet16(num_classes=N, num_filters=64, pretrained=False), 2)):
             net = ctor().cuda().eval()
             x = torch.randn(B, 3, H, W, device="cuda")
             ms = timeit(lambda: net(x), iters)
             prog = net._plans[(B, H, W)][0]
-            r = {"what": name, "batch": B, "ms": round(ms, 3), "frames_per_s": round(B * 1000.0 / ms, 1), "launches": prog.n_kernels}
+            flops = sum(m.get("flops", 0) for m in prog.meta)
+            r = {"what": name, "batch": B, "ms": round(ms, 3), "frames_per_s": round(B * 1000.0 / ms, 1), "launches": prog.n_kernels,
+                 "conv_TFLOPs": round(flops / ms * 1e-9, 1)}
             print(json.dumps(r), flush=True)
             out.append(r)
             del net
