@@ -138,6 +138,10 @@ typedef struct MfcConvDesc {
   MfcSrc src[MFC_MAX_SRC];
 } MfcConvDesc;
 #define MFC_CONV_HAS_RESIDUAL 1
+/* Walk the work items from the last sample to the first.  Activations of a batch are larger than the 126 MB L2: a conv that
+ * runs in the opposite direction of its producer starts with the part of its input that is still cache-resident ("snake"
+ * order through the layers).  Results are identical up to the grouping of the GroupNorm partial sums. */
+#define MFC_CONV_REVERSE_ORDER 2
 
 int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info);
 

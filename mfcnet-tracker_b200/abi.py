@@ -13,6 +13,7 @@ from . import build as _build
 MFC_F16, MFC_BF16 = 0, 1
 MFC_MAX_SRC = 8
 MFC_CONV_HAS_RESIDUAL = 1
+MFC_CONV_REVERSE_ORDER = 2
 OP_FORK, OP_JOIN, MFC_MAX_LANES = 100, 101, 4
 OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP, OP_FUSE_SUM, OP_RESIZE, OP_MAXPOOL2, OP_HEATMAP = 1, 2, 3, 4, 5, 6, 7, 8, 9
 

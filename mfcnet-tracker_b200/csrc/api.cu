@@ -207,6 +207,8 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.div_tx = mfc::make_fastdiv((uint32_t)p.t.tiles_x);
   p.div_ty = mfc::make_fastdiv((uint32_t)p.t.tiles_y);
   p.idesc = mfc::make_idesc_f16(p.t.NB, d->dtype == MFC_BF16);
+  p.reverse = (d->reserved & MFC_CONV_REVERSE_ORDER) ? 1 : 0;
+  p.total_items = p.B * p.t.tiles_x * p.t.tiles_y * p.t.nblk;
   p.w = (const uint8_t*)io->w_packed;
   p.scale = io->scale;
   p.shift = io->shift;

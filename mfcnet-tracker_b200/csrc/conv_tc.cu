@@ -422,6 +422,7 @@ struct ItemCoord {
 };
 __device__ __forceinline__ ItemCoord decode_item(const ConvParams& p, int w) {
   ItemCoord c;
+  if (p.reverse) w = p.total_items - 1 - w;
   uint32_t tile = fdiv((uint32_t)w, p.div_nblk);
   c.nbk = w - (int)tile * p.t.nblk;
   c.tile_lin = (int)tile;

@@ -84,6 +84,7 @@ struct ConvParams {
   float* y_nchw;
   float* stats;
   alignas(64) CUtensorMap tmap[MFC_MAX_SRC];  // t.tma: source i as the 5-D tensor (8 ch, W, H, chunk, sample)
+  int reverse, total_items;  // reverse: walk the work items from the last sample to the first (see MFC_CONV_REVERSE_ORDER)
   int debug;  // measurement only (MFC_CONV_DEBUG): bit0 skip producer copies, bit1 skip epilogue body, bit2 skip MMAs
 };
 

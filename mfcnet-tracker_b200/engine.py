@@ -31,6 +31,10 @@ def autotune_enabled():
     return os.environ.get("MFC_CONV_TUNE", "1") != "0"
 
 
+def snake_enabled():
+    return os.environ.get("MFC_CONV_SNAKE", "1") != "0"
+
+
 def autotune_reps():
     return max(1, int(os.environ.get("MFC_CONV_TUNE_REPS", "3")))
 
@@ -147,6 +151,7 @@ class Program:
         self.tdtype, self.cdtype = _DTYPES[dtype_name]
         self.cmds = []       # (op, struct_a, struct_b, lane)
         self.lane = 0        # lane (stream) the next recorded commands run on; see fork() / join()
+        self._last_forward = True   # direction in which the previous bulk op walked the batch (snake order, see conv())
         self.keep = []       # tensors referenced by raw pointer
         self._array = None
         self.n_kernels = 0   # kernel launches one run() issues
@@ -155,6 +160,8 @@ class Program:
 
     # ---- low-level recording -----------------------------------------------------------------
     def _push(self, op, a, b=None, launches=1, meta=None):
+        if op != abi.OP_CONV and op != abi.OP_GN_FINALIZE:
+            self._last_forward = True      # every other kernel walks the batch front to back
         self.cmds.append((op, a, b, self.lane))
         self.meta.append(meta or {"kind": "op%d" % op, "name": "", "bytes": 0, "flops": 0})
         self._array = None
@@ -340,6 +347,12 @@ class Program:
         if residual is not None:
             nbytes += B * Cout * d.Hout * d.Wout * 2
         flops = 2 * B * Cout * d.Hout * d.Wout * cin * d.kh * d.kw
+        # snake order: a conv walks the batch in the direction opposite to its producer, so it starts with the part of its
+        # input that is still in the L2 (a batch of activations is larger than the cache)
+        if snake_enabled() and B > 1:
+            if self._last_forward:
+                d.reserved |= abi.MFC_CONV_REVERSE_ORDER
+            self._last_forward = not self._last_forward
         self._push(abi.OP_CONV, d, io, meta={"kind": "conv", "name": name, "bytes": nbytes, "flops": flops,
                                              "shape": "B%d %dx%d %d->%d k%d s%d u%d" % (B, d.Hout, d.Wout, cin, Cout, d.kh, d.stride, d.upsample)})
         return out, stats, io
