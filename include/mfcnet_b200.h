@@ -369,6 +369,25 @@ int mfc_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, long long n, v
 int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours,
                        int* n_out, void* stream);
 
+/* The class map of the video script when --score_detection_threshold > 0
+ * (scripts/test_multiframe_segmentation_on_videos_v3.py:282-287): 0, then classes 1..N-1 painted in
+ * ascending order where prob > thr (float32 comparison, as numpy does against a Python float). */
+int mfc_threshold_classes(const float* prob, int B, int N, long long pixels, float thr, uint8_t* out,
+                          void* stream);
+
+/* out = (cls == cls_id) ? heat : 0   (`left_tip_heatmap[left_tip==0] = 0`, ...videos_v3.py:88). */
+int mfc_mask_heat(const float* heat, const uint8_t* cls, int cls_id, float* out, long long n,
+                  void* stream);
+
+/* refine_tip_segmentation (...videos_v3.py:32-42): out = mask inside the FILLED two largest external
+ * contours (area descending, ties in findContours order) whose contourArea >= area_threshold -- i.e.
+ * the selected components plus whatever is nested in their holes.  Must follow mfc_trace_contours on
+ * the same mask: labels / rec / n_contours are that call's scratch, records and count, untouched.
+ * sel: 2 device ints, receives the raster index of each selected contour's first point or -1. */
+int mfc_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, const double* rec,
+                        int max_contours, const int* n_contours, double area_threshold, int* sel,
+                        uint8_t* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Command list: one C call issues a whole pre-built forward (the per-frame SFC pass is
  * ~60 launches).  Replaces the Python-level op-by-op dispatch of nn.Module.forward

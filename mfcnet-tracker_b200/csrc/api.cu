@@ -602,6 +602,27 @@ int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* o
   MFC_LAUNCH(mfc::launch_trace_contours(mask, H, W, labels, out, max_contours, n_out, (cudaStream_t)stream), "trace_contours");
 }
 
+int mfc_threshold_classes(const float* prob, int B, int N, long long pixels, float thr, uint8_t* out, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!prob || !out || B < 1 || N < 2 || N > 255 || pixels < 1) return fail(MFC_EINVAL, "threshold_classes: bad argument");
+  MFC_LAUNCH(mfc::launch_threshold_classes(prob, B, N, pixels, thr, out, (cudaStream_t)stream), "threshold_classes");
+}
+
+int mfc_mask_heat(const float* heat, const uint8_t* cls, int cls_id, float* out, long long n, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!heat || !cls || !out || n < 1) return fail(MFC_EINVAL, "mask_heat: bad argument");
+  MFC_LAUNCH(mfc::launch_mask_heat(heat, cls, cls_id, out, n, (cudaStream_t)stream), "mask_heat");
+}
+
+int mfc_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, const double* rec, int max_contours, const int* n_contours,
+                        double area_threshold, int* sel, uint8_t* out, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!mask || !labels || !rec || !n_contours || !sel || !out || H < 1 || W < 1 || max_contours < 1)
+    return fail(MFC_EINVAL, "refine_tip_mask: bad argument");
+  MFC_LAUNCH(mfc::launch_refine_tip_mask(mask, H, W, labels, rec, max_contours, n_contours, area_threshold, sel, out, (cudaStream_t)stream),
+             "refine_tip_mask");
+}
+
 // ---- command list ------------------------------------------------------------------------------
 namespace {
 // side streams / events of the calling thread, per device (created on first use, never destroyed)

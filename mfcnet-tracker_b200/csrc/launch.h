@@ -78,4 +78,9 @@ cudaError_t launch_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, lon
 cudaError_t launch_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours, int* n_out,
                                   cudaStream_t st);
 
+cudaError_t launch_threshold_classes(const float* prob, int B, int N, long long pixels, float thr, uint8_t* out, cudaStream_t st);
+cudaError_t launch_mask_heat(const float* heat, const uint8_t* cls, int cls_id, float* out, long long n, cudaStream_t st);
+cudaError_t launch_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, const double* rec, int max_contours,
+                                   const int* n_contours, double area_threshold, int* sel, uint8_t* out, cudaStream_t st);
+
 }  // namespace mfc

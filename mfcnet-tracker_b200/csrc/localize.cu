@@ -172,6 +172,98 @@ __global__ void trace_kernel(const uint8_t* __restrict__ mask, const int* __rest
   }
 }
 
+
+// ---- video-script post-processing (scripts/test_multiframe_segmentation_on_videos_v3.py:32-42, :62-88, :282-287) ----------
+// Class map by score threshold: classes 1..N-1 painted in ascending order where prob > thr, i.e. the highest such class wins.
+__global__ void threshold_classes_kernel(const float* __restrict__ prob, int B, int N, long long HW, float thr,
+                                         uint8_t* __restrict__ out) {
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const float* src = prob + b * N * HW + p;
+    int c = 0;
+    for (int k = 1; k < N; ++k)
+      if (src[(long long)k * HW] > thr) c = k;
+    out[i] = (uint8_t)c;
+  }
+}
+
+// heat[cls != cls_id] = 0  (`left_tip_heatmap[left_tip==0] = 0`, :88)
+__global__ void mask_heat_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ cls, int cls_id, float* __restrict__ out,
+                                 long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = cls[i] == cls_id ? heat[i] : 0.0f;
+}
+
+// The two largest external contours in the order `sorted(contours, key=contourArea, reverse=True)[:2]` gives them: area
+// descending, ties in findContours order (descending raster index of the first point); one below the area threshold is dropped.
+// rec = the records of mfc_trace_contours; sel[k] = raster index of the contour's first pixel (= its component root) or -1.
+__global__ void select_top2_kernel(const double* __restrict__ rec, const int* __restrict__ n_ptr, int max_contours, int W,
+                                   double area_threshold, int* __restrict__ sel) {
+  __shared__ double s_a[256];
+  __shared__ int s_i[256];
+  __shared__ int s_first;
+  const int n = min(*n_ptr, max_contours);
+  for (int pass = 0; pass < 2; ++pass) {
+    double best_a = -1.0;
+    int best_i = -1;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const double a = fabs(rec[(size_t)k * 6]);
+      const int idx = (int)rec[(size_t)k * 6 + 4] * W + (int)rec[(size_t)k * 6 + 3];
+      if (pass == 1 && idx == s_first) continue;
+      if (a > best_a || (a == best_a && idx > best_i)) {
+        best_a = a;
+        best_i = idx;
+      }
+    }
+    s_a[threadIdx.x] = best_a;
+    s_i[threadIdx.x] = best_i;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (threadIdx.x < off) {
+        const double a = s_a[threadIdx.x + off];
+        const int idx = s_i[threadIdx.x + off];
+        if (a > s_a[threadIdx.x] || (a == s_a[threadIdx.x] && idx > s_i[threadIdx.x])) {
+          s_a[threadIdx.x] = a;
+          s_i[threadIdx.x] = idx;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (pass == 0) s_first = s_i[0];
+      sel[pass] = (s_i[0] >= 0 && s_a[0] * 0.5 >= area_threshold) ? s_i[0] : -1;
+    }
+    __syncthreads();
+  }
+}
+
+// mask & (filled selected contours): a foreground pixel survives iff the EXTERNAL component its own component sits in (itself,
+// or the one whose hole it is nested in, any depth) is selected.  lab / flag are the labels mfc_trace_contours left behind:
+// the root of a set is its raster-first pixel; the pixel left of a component's root is background, and that background region
+// reaches the frame (flag) iff the component is external; the pixel above a hole's root belongs to the component around the hole.
+__global__ void refine_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ lab, const int* __restrict__ flag,
+                              const int* __restrict__ sel, int H, int W, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  uint8_t keep = 0;
+  if (mask[i] != 0) {
+    const int s0 = sel[0], s1 = sel[1];
+    int r = lab[i];
+    for (int depth = 0; depth < H; ++depth) {
+      if (r == s0 || r == s1) {
+        keep = mask[i];
+        break;
+      }
+      if (r % W == 0) break;          // external, not selected
+      const int hole = lab[r - 1];
+      if (flag[hole]) break;          // external, not selected
+      r = lab[hole - W];
+    }
+  }
+  out[i] = keep;
+}
+
 static inline int grid_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   const long long cap = (long long)kSmCount * 16;
@@ -203,6 +295,21 @@ cudaError_t launch_trace_contours(const uint8_t* mask, int H, int W, int* labels
   ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, labels, H, W);
   ccl_flatten_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W);
   trace_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W, out, max_contours, n_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_threshold_classes(const float* prob, int B, int N, long long pixels, float thr, uint8_t* out, cudaStream_t st) {
+  threshold_classes_kernel<<<grid_for((long long)B * pixels, 256), 256, 0, st>>>(prob, B, N, pixels, thr, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_mask_heat(const float* heat, const uint8_t* cls, int cls_id, float* out, long long n, cudaStream_t st) {
+  mask_heat_kernel<<<grid_for(n, 256), 256, 0, st>>>(heat, cls, cls_id, out, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, const double* rec, int max_contours,
+                                   const int* n_contours, double area_threshold, int* sel, uint8_t* out, cudaStream_t st) {
+  select_top2_kernel<<<1, 256, 0, st>>>(rec, n_contours, max_contours, W, area_threshold, sel);
+  refine_kernel<<<(H * W + 255) / 256, 256, 0, st>>>(mask, labels, labels + (size_t)H * W, sel, H, W, out);
   return cudaGetLastError();
 }
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import corr, localize_cases, localize_oracle as LO, synth
+from oracle import corr, localize_cases, localize_oracle as LO, synth, track_cases, track_oracle as TO
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -132,6 +132,83 @@ def test_keypoints_bit_exact_on_identical_heatmaps(M):
         got = M.predicted_keypoints(torch.from_numpy(p).cuda())
         want = LO.predicted_keypoints(p)
         assert str(got) == str(want), seed
+
+
+# ---------------------------------------------------------------- video-script tracking
+def _blob_masks():
+    """0/255 masks with rings, blobs nested in holes (two levels), ties in area, small blobs and salt noise."""
+    rng = np.random.default_rng(11)
+    H, W = 96, 128
+    y, x = np.mgrid[:H, :W]
+    out = []
+    for k in range(8):
+        m = np.zeros((H, W), bool)
+        for _ in range(int(rng.integers(1, 6))):
+            cy, cx, r = int(rng.integers(0, H)), int(rng.integers(0, W)), int(rng.integers(2, 22))
+            d2 = (y - cy) ** 2 + (x - cx) ** 2
+            m |= d2 <= r * r
+            if r > 8 and rng.random() < 0.8:
+                m &= ~(d2 <= (r - 3) ** 2)                      # ring
+                if rng.random() < 0.8:
+                    m |= d2 <= (r - 6) ** 2                     # blob in the hole
+                    if r > 14:
+                        m &= ~(d2 <= (r - 9) ** 2)              # ... itself a ring
+                        m |= d2 <= 4                            # ... with a blob inside
+        if k % 2:
+            m ^= rng.random((H, W)) < 0.02
+        out.append(255 * m.astype(np.uint8))
+    out.append(np.zeros((H, W), np.uint8))
+    out.append(np.full((H, W), 255, np.uint8))
+    eq = np.zeros((H, W), np.uint8)                             # three equal-area squares: order decided by the stable sort
+    for cx in (10, 50, 90):
+        eq[20:30, cx:cx + 10] = 255
+    out.append(eq)
+    out.append((255 * (rng.random((H, W)) < 0.5)).astype(np.uint8))
+    return out
+
+
+def test_refine_tip_segmentation_matches_cv2(M):
+    """mask & (filled two largest contours over the area threshold), bit-exact with the cv2 sequence of
+    scripts/test_multiframe_segmentation_on_videos_v3.py:32-42 -- including blobs nested in the holes of a kept contour."""
+    nested_kept = 0
+    for mi, mask in enumerate(_blob_masks()):
+        for thr in (0, 10, 150):
+            want = TO.refine_tip_segmentation(mask, thr)
+            got = M.refine_tip_segmentation(torch.from_numpy(mask).cuda(), thr).cpu().numpy()
+            assert np.array_equal(got, want), (mi, thr)
+        import cv2
+        n_all = cv2.connectedComponents((want > 0).astype(np.uint8), connectivity=8)[0] - 1
+        nested_kept += n_all > 2
+    assert nested_kept > 0      # the cases really contain kept nested components
+
+
+def test_class_map_matches_script(M):
+    for seed, thr in ((0, 0.0), (1, 0.3), (2, 0.5), (3, 0.21)):
+        p = synth.uniform("cm/%d" % seed, (1, 5, 60, 80), seed)
+        p = (p / p.sum(1, keepdims=True)).astype(np.float32)
+        got = M.class_map(torch.from_numpy(p).cuda(), thr).cpu().numpy()[0]
+        assert np.array_equal(got, TO.class_map(p, thr).astype(np.uint8)), seed
+
+
+def test_tool_tracker_rows_bit_exact(M):
+    """The 12 tracked coordinates per frame, over frame sequences: identical to the rows the reference's own functions wrote
+    (tests/golden/track_rows.json) and to the cv2 / scipy oracle on noisy random maps."""
+    with open(os.path.join(ROOT, "tests", "golden", "track_rows.json")) as f:
+        gold = json.load(f)
+    for pname, (a, d, s) in track_cases.PARAMS.items():
+        for name, seq in track_cases.sequences().items():
+            tr = M.ToolTracker(a, d, s)
+            for t, p in enumerate(seq):
+                want = np.array([np.nan if v is None else v for v in gold["%s/%s" % (pname, name)][t]])
+                got = tr.step(torch.from_numpy(p).cuda())
+                assert np.array_equal(got, want, equal_nan=True), (pname, name, t, got, want)
+    for thr in (0.0, 0.3):
+        tr, ref = M.ToolTracker(2, 60, thr), TO.Tracker(2, 60, thr)
+        for seed in range(4):
+            p = synth.uniform("trk/%d" % seed, (1, 5, 120, 160), seed)
+            p[0, 1:] *= 0.9
+            p = (p / p.sum(1, keepdims=True)).astype(np.float32)
+            assert np.array_equal(tr.step(torch.from_numpy(p).cuda()), ref.step(p), equal_nan=True), (thr, seed)
 
 
 # ---------------------------------------------------------------- training loss (forward)
