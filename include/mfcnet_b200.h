@@ -358,14 +358,15 @@ int mfc_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, long long n, v
 /* cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + contourArea + moments on ONE 0/255
  * mask (H x W), restricted to what calc_centroids (utils/localization_utils_v2.py:15-33) needs.
  * For every external contour one record of 6 doubles is appended (in no particular order):
- *   {a00, a10, a01, first_x, first_y, npoints}
- * a00/a10/a01 are the exact integer Green's-theorem sums of the closed border polygon, from
- * which the caller derives, with OpenCV's own formulas,
- *   contourArea = |a00| * 0.5,  m00 = a00 * (+-0.5),  m10 = a10 * (+-1/6),  m01 = a01 * (+-1/6)
- * (sign of a00); (first_x, first_y) is the contour's first point = the component's raster-first
+ *   {a00, a10, a01, first_x, first_y, 0}
+ * a00/a10/a01 are the exact integer Green's-theorem sums of the closed border polygon (positive
+ * orientation), from which the caller derives, with OpenCV's own formulas,
+ *   contourArea = |a00| * 0.5,  m00 = a00 * 0.5,  m10 = a10 * (1/6),  m01 = a01 * (1/6);
+ * (first_x, first_y) is the contour's first point = the component's raster-first
  * pixel, so OpenCV's output order is "descending first_y*W+first_x".  *n_out (device int)
  * receives the TOTAL number of external contours; records beyond max_contours are dropped.
- * labels: int32 scratch [2*H*W]. */
+ * labels: int32 scratch [8*H*W], 16-byte aligned (labels, per-pixel contour codes, 3 int64 sums per
+ * pixel); mfc_refine_tip_mask reads it afterwards. */
 int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours,
                        int* n_out, void* stream);
 

@@ -5,12 +5,13 @@
 //   local maxima    scipy.ndimage.maximum_filter(footprint) == smoothed, AND class blob
 //   contours        8-connected component labelling (union-find, root = raster-first pixel) +
 //                   4-connected background labelling to decide which components are external,
-//                   then one thread per component follows its outer border (localize_core.h)
+//                   then the Green sums of every external contour from 2x2 pixel blocks, one thread
+//                   per block (no border following; localize_core.h keeps the serial Suzuki-Abe
+//                   formulation for the host cross-check in tests/)
 // All of it keeps the 6 MB probability maps on the device: the reference copies them to the host
 // twice per frame and runs single-threaded scipy/OpenCV.
 #include "common.cuh"
 #include "launch.h"
-#include "localize_core.h"
 
 namespace mfc {
 
@@ -90,6 +91,17 @@ __device__ __forceinline__ int uf_find(int* lab, int a) {
   }
   return r;
 }
+// Read-only find for the kernels that run after ccl_flatten_kernel.  Flattening compresses paths while other threads are still
+// walking them, and a late path-halving store can put a (valid, but non-root) ancestor back over a label that was already set
+// to its root -- so a label is only guaranteed to be an ancestor; the root is at most a few hops further.
+__device__ __forceinline__ int uf_root(const int* __restrict__ lab, int a) {
+  int p = lab[a];
+  while (p != a) {
+    a = p;
+    p = lab[a];
+  }
+  return a;
+}
 __device__ __forceinline__ void uf_union(int* lab, int a, int b) {
   while (true) {
     a = uf_find(lab, a);
@@ -108,8 +120,8 @@ __device__ __forceinline__ void uf_union(int* lab, int a, int b) {
 
 // Initial label = the first pixel of the pixel's horizontal run inside its 32-pixel warp segment (ballot of the run-start bits),
 // so the horizontal part of every component is already merged up to segment boundaries before the union pass starts.
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lab, int* __restrict__ flag, int n, int W,
-                                int* __restrict__ n_out) {
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lab, int* __restrict__ flag,
+                                unsigned long long* __restrict__ acc, int n, int W, int* __restrict__ n_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool start = true;
@@ -122,6 +134,7 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restric
     const unsigned below = bits & (0xffffffffu >> (31 - lane));   // start bits at or below this lane (bit 0 is always set)
     lab[i] = i - lane + (31 - __clz(below));
     flag[i] = 0;
+    acc[3 * (size_t)i] = acc[3 * (size_t)i + 1] = acc[3 * (size_t)i + 2] = 0ull;
   }
   if (i == 0) *n_out = 0;
 }
@@ -150,28 +163,103 @@ __global__ void ccl_flatten_kernel(const uint8_t* __restrict__ mask, int* __rest
   if (mask[i] == 0 && (x == 0 || y == 0 || x == W - 1 || y == H - 1)) flag[r] = 1;
 }
 
-// One thread per component root.  A component is external (RETR_EXTERNAL) iff the background
-// pixel left of its raster-first pixel belongs to a background region that reaches the frame.
-__global__ void trace_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ lab, const int* __restrict__ flag, int H, int W,
-                             double* __restrict__ out, int max_contours, int* __restrict__ n_out) {
+// ---- external contours without following borders ------------------------------------------------
+// cv2.findContours(RETR_EXTERNAL) + contourArea + moments need, per external component E, the Green sums of the closed polygon
+// through the pixel centres of its outer border.  That polygon bounds the "filled set" of E (E, its holes and whatever sits in
+// them) shrunk by half a pixel, which is tiled exactly by the 2x2 pixel blocks with four filled corners (a unit square) or
+// three (a half-square triangle); blocks with fewer add nothing.  So, with integer arithmetic throughout,
+//     a00 = 2*area = sum(2 | 1),   a10 = 6*int x dA = sum(6x+3 | x1+x2+x3),   a01 likewise
+// -- a sum over blocks, done by every thread for its own block, instead of one thread walking a border of up to 10^5 pixels.
+//
+// ext code of a pixel (kept in the flag array, which is only ever tested for "== 1" at background roots): 1 = outside every
+// contour, -(E+2) = inside the filled outer contour of the external component whose raster-first pixel is E.
+// A component is external iff the background left of its raster-first pixel reaches the frame; a pixel in a hole belongs to the
+// component around the hole (the pixel above the hole's raster-first pixel), which may itself sit in a hole: walk outwards.
+__device__ __forceinline__ int ext_of(const uint8_t* __restrict__ mask, const int* __restrict__ lab, const int* flag, int W, int i,
+                                      int max_depth) {
+  int r;
+  if (mask[i] != 0) {
+    r = uf_root(lab, i);
+  } else {
+    const int hole = uf_root(lab, i);
+    if (flag[hole] == 1 || hole < W) return -1;
+    r = uf_root(lab, hole - W);
+  }
+  for (int depth = 0; depth < max_depth; ++depth) {
+    if (r % W == 0) return r;
+    const int hole = uf_root(lab, r - 1);
+    if (flag[hole] == 1 || hole < W) return r;
+    r = uf_root(lab, hole - W);
+  }
+  return r;
+}
+
+__global__ void ext_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ lab, int* flag, int H, int W) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
-  if (mask[i] == 0 || lab[i] != i) return;
-  const int x = i % W, y = i / W;
-  if (x > 0 && flag[lab[i - 1]] == 0) return;  // sits in a hole of another component
-  const ContourSums s = trace_outer_border(mask, H, W, x, y, 4LL * H * W + 8);
-  const int slot = atomicAdd(n_out, 1);
-  if (slot < max_contours) {
-    double* o = out + (size_t)slot * 6;
-    o[0] = (double)s.a00;
-    o[1] = (double)s.a10;
-    o[2] = (double)s.a01;
-    o[3] = (double)x;
-    o[4] = (double)y;
-    o[5] = (double)s.npoints;
+  const int e = ext_of(mask, lab, flag, W, i, H + W);
+  flag[i] = e < 0 ? 1 : -(e + 2);
+}
+
+__device__ __forceinline__ int ext_at(const int* __restrict__ code, int H, int W, int x, int y) {
+  if (x < 0 || y < 0 || x >= W || y >= H) return -1;
+  const int c = code[y * W + x];
+  return c == 1 ? -1 : -c - 2;
+}
+
+// one thread per 2x2 block (top-left corner (x,y), x in [-1,W), y in [-1,H)); lanes that add to the same component are summed
+// with match_any / reduce_add first, so a large component costs one atomic per warp, not one per block
+__global__ void block_sums_kernel(const int* __restrict__ code, int H, int W, unsigned long long* __restrict__ acc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = (H + 1) * (W + 1);
+  int E = -1, c00 = 0, c10 = 0, c01 = 0;
+  if (t < total) {
+    const int x = t % (W + 1) - 1, y = t / (W + 1) - 1;
+    const int e0 = ext_at(code, H, W, x, y), e1 = ext_at(code, H, W, x + 1, y);
+    const int e2 = ext_at(code, H, W, x, y + 1), e3 = ext_at(code, H, W, x + 1, y + 1);
+    E = e0 >= 0 ? e0 : (e1 >= 0 ? e1 : (e2 >= 0 ? e2 : e3));
+    if (E >= 0) {
+      const int f0 = e0 == E, f1 = e1 == E, f2 = e2 == E, f3 = e3 == E;
+      const int cnt = f0 + f1 + f2 + f3;
+      if (cnt == 4) {
+        c00 = 2;
+        c10 = 6 * x + 3;
+        c01 = 6 * y + 3;
+      } else if (cnt == 3) {
+        c00 = 1;
+        c10 = f0 * x + f1 * (x + 1) + f2 * x + f3 * (x + 1);
+        c01 = f0 * y + f1 * y + f2 * (y + 1) + f3 * (y + 1);
+      } else {
+        E = -1;
+      }
+    }
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, E);
+  const int s00 = __reduce_add_sync(peers, c00), s10 = __reduce_add_sync(peers, c10), s01 = __reduce_add_sync(peers, c01);
+  if (E >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) {
+    atomicAdd(&acc[3 * (size_t)E + 0], (unsigned long long)s00);
+    atomicAdd(&acc[3 * (size_t)E + 1], (unsigned long long)s10);
+    atomicAdd(&acc[3 * (size_t)E + 2], (unsigned long long)s01);
   }
 }
 
+__global__ void emit_contours_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ lab, const int* __restrict__ code, int H,
+                                     int W, const unsigned long long* __restrict__ acc, double* __restrict__ out, int max_contours,
+                                     int* __restrict__ n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  if (mask[i] == 0 || lab[i] != i || code[i] != -(i + 2)) return;   // not the raster-first pixel of an external component
+  const int slot = atomicAdd(n_out, 1);
+  if (slot < max_contours) {
+    double* o = out + (size_t)slot * 6;
+    o[0] = (double)(long long)acc[3 * (size_t)i + 0];
+    o[1] = (double)(long long)acc[3 * (size_t)i + 1];
+    o[2] = (double)(long long)acc[3 * (size_t)i + 2];
+    o[3] = (double)(i % W);
+    o[4] = (double)(i / W);
+    o[5] = 0.0;
+  }
+}
 
 // ---- video-script post-processing (scripts/test_multiframe_segmentation_on_videos_v3.py:32-42, :62-88, :282-287) ----------
 // Class map by score threshold: classes 1..N-1 painted in ascending order where prob > thr, i.e. the highest such class wins.
@@ -238,30 +326,14 @@ __global__ void select_top2_kernel(const double* __restrict__ rec, const int* __
   }
 }
 
-// mask & (filled selected contours): a foreground pixel survives iff the EXTERNAL component its own component sits in (itself,
-// or the one whose hole it is nested in, any depth) is selected.  lab / flag are the labels mfc_trace_contours left behind:
-// the root of a set is its raster-first pixel; the pixel left of a component's root is background, and that background region
-// reaches the frame (flag) iff the component is external; the pixel above a hole's root belongs to the component around the hole.
-__global__ void refine_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ lab, const int* __restrict__ flag,
-                              const int* __restrict__ sel, int H, int W, uint8_t* __restrict__ out) {
+// mask & (filled selected contours): a foreground pixel survives iff the external component it lies in (itself, or the one in
+// whose hole it is nested, at any depth) is selected -- exactly the ext code mfc_trace_contours left in the flag array.
+__global__ void refine_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ code, const int* __restrict__ sel, int H, int W,
+                              uint8_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
-  uint8_t keep = 0;
-  if (mask[i] != 0) {
-    const int s0 = sel[0], s1 = sel[1];
-    int r = lab[i];
-    for (int depth = 0; depth < H; ++depth) {
-      if (r == s0 || r == s1) {
-        keep = mask[i];
-        break;
-      }
-      if (r % W == 0) break;          // external, not selected
-      const int hole = lab[r - 1];
-      if (flag[hole]) break;          // external, not selected
-      r = lab[hole - W];
-    }
-  }
-  out[i] = keep;
+  const int e = -code[i] - 2;
+  out[i] = (mask[i] != 0 && code[i] != 1 && (e == sel[0] || e == sel[1])) ? mask[i] : (uint8_t)0;
 }
 
 static inline int grid_for(long long n, int threads) {
@@ -291,10 +363,13 @@ cudaError_t launch_trace_contours(const uint8_t* mask, int H, int W, int* labels
   const int n = H * W;
   const int blocks = (n + 255) / 256;
   int* flag = labels + n;
-  ccl_init_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, n, W, n_out);
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(labels + 2 * (size_t)n);   // 3 per pixel, 8-byte aligned (caller: 16)
+  ccl_init_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, acc, n, W, n_out);
   ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, labels, H, W);
   ccl_flatten_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W);
-  trace_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W, out, max_contours, n_out);
+  ext_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W);
+  block_sums_kernel<<<((H + 1) * (W + 1) + 255) / 256, 256, 0, st>>>(flag, H, W, acc);
+  emit_contours_kernel<<<blocks, 256, 0, st>>>(mask, labels, flag, H, W, acc, out, max_contours, n_out);
   return cudaGetLastError();
 }
 
@@ -309,7 +384,7 @@ cudaError_t launch_mask_heat(const float* heat, const uint8_t* cls, int cls_id, 
 cudaError_t launch_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, const double* rec, int max_contours,
                                    const int* n_contours, double area_threshold, int* sel, uint8_t* out, cudaStream_t st) {
   select_top2_kernel<<<1, 256, 0, st>>>(rec, n_contours, max_contours, W, area_threshold, sel);
-  refine_kernel<<<(H * W + 255) / 256, 256, 0, st>>>(mask, labels, labels + (size_t)H * W, sel, H, W, out);
+  refine_kernel<<<(H * W + 255) / 256, 256, 0, st>>>(mask, labels + (size_t)H * W, sel, H, W, out);
   return cudaGetLastError();
 }
 

@@ -99,7 +99,7 @@ def trace_contours(mask_u8):
     lib = abi.load()
     H, W = mask_u8.shape
     dev = mask_u8.device
-    labels = torch.empty(2 * H * W, dtype=torch.int32, device=dev)
+    labels = torch.empty(8 * H * W, dtype=torch.int32, device=dev)
     rec = torch.empty((MAX_CONTOURS, 6), dtype=torch.float64, device=dev)
     n = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
@@ -172,7 +172,7 @@ class _KeypointWorkspace:
         self.heat = torch.empty((2, H, W), dtype=torch.float32, device=device)     # class 4, class 2 probabilities
         self.tmp = torch.empty_like(self.heat)
         self.smooth = torch.empty_like(self.heat)
-        self.labels = torch.empty((4, 2 * H * W), dtype=torch.int32, device=device)
+        self.labels = torch.empty((4, 8 * H * W), dtype=torch.int32, device=device)
         self.rec = torch.empty((4, MAX_CONTOURS, 6), dtype=torch.float64, device=device)
         self.n = torch.zeros(4, dtype=torch.int32, device=device)
         self.pack = torch.empty((4, self.QUICK * 6 + 1), dtype=torch.float64, device=device)   # [count | first QUICK records]

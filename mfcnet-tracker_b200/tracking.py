@@ -47,7 +47,7 @@ def refine_tip_segmentation(mask_u8, area_threshold):
     m = mask_u8.contiguous()
     H, W = m.shape
     dev = m.device
-    labels = torch.empty(2 * H * W, dtype=torch.int32, device=dev)
+    labels = torch.empty(8 * H * W, dtype=torch.int32, device=dev)
     rec = torch.empty((MAX_CONTOURS, 6), dtype=torch.float64, device=dev)
     n = torch.zeros(1, dtype=torch.int32, device=dev)
     sel = torch.empty(2, dtype=torch.int32, device=dev)
@@ -92,7 +92,7 @@ class _TrackWorkspace:
         self.heat = torch.empty((2, H, W), dtype=torch.float32, device=device)
         self.tmp = torch.empty_like(self.heat)
         self.smooth = torch.empty_like(self.heat)
-        self.labels = torch.empty((2 * H * W,), dtype=torch.int32, device=device)
+        self.labels = torch.empty((8 * H * W,), dtype=torch.int32, device=device)
         self.rec = torch.empty((4, MAX_CONTOURS, 6), dtype=torch.float64, device=device)       # base L, maxima L, base R, maxima R
         self.rec_tip = torch.empty((MAX_CONTOURS, 6), dtype=torch.float64, device=device)
         self.n = torch.zeros(6, dtype=torch.int32, device=device)                               # + the two raw tip masks

@@ -182,6 +182,21 @@ def test_refine_tip_segmentation_matches_cv2(M):
     assert nested_kept > 0      # the cases really contain kept nested components
 
 
+def test_contour_labels_under_contention(M):
+    """Full-resolution masks near the percolation threshold (components and holes with long union-find chains, heavy
+    contention in the label kernels): contour records and the refined mask must still equal cv2's, run after run."""
+    from mfcnet_tracker_b200 import heatmap as HM
+    rng = np.random.default_rng(3)
+    for dens in (0.4, 0.55, 0.62):
+        mask = (255 * (rng.random((480, 640)) < dens)).astype(np.uint8)
+        want_rec = [tuple(r) for r in LO.contour_records(mask)]
+        want_ref = TO.refine_tip_segmentation(mask, 10)
+        dm = torch.from_numpy(mask).cuda()
+        for rep in range(4):
+            assert HM.trace_contours(dm) == want_rec, (dens, rep)
+            assert np.array_equal(M.refine_tip_segmentation(dm, 10).cpu().numpy(), want_ref), (dens, rep)
+
+
 def test_class_map_matches_script(M):
     for seed, thr in ((0, 0.0), (1, 0.3), (2, 0.5), (3, 0.21)):
         p = synth.uniform("cm/%d" % seed, (1, 5, 60, 80), seed)
