@@ -370,6 +370,14 @@ int mfc_class_mask(const uint8_t* cls, int cls_id, uint8_t* mask, long long n, v
 int mfc_trace_contours(const uint8_t* mask, int H, int W, int* labels, double* out, int max_contours,
                        int* n_out, void* stream);
 
+/* The two largest contours of a mfc_trace_contours record list, in the order
+ * `sorted(contours, key=cv2.contourArea, reverse=True)[:2]` gives them (area descending, ties in
+ * findContours order) -- all calc_centroids / calc_base_centroid ever use
+ * (utils/localization_utils_v2.py:17, ...videos_v3.py:47).  top: 2 records of 6 doubles,
+ * {a00, a10, a01, first_x, first_y, present (1 / 0)}. */
+int mfc_top_contours(const double* rec, const int* n_contours, int max_contours, int W, double* top,
+                     void* stream);
+
 /* The class map of the video script when --score_detection_threshold > 0
  * (scripts/test_multiframe_segmentation_on_videos_v3.py:282-287): 0, then classes 1..N-1 painted in
  * ascending order where prob > thr (float32 comparison, as numpy does against a Python float). */

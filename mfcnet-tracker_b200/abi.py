@@ -138,6 +138,7 @@ _SIGNATURES = {
     "mfc_threshold_classes": ([c_void_p, c_int, c_int, c_ll, C.c_float, c_void_p, c_void_p], c_int),
     "mfc_mask_heat": ([c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p], c_int),
     "mfc_refine_tip_mask": ([c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, C.c_double, c_void_p, c_void_p, c_void_p], c_int),
+    "mfc_top_contours": ([c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
     "mfc_run_list": ([C.POINTER(MfcCmd), c_int, c_void_p], c_int),
     "mfc_run_list_timed": ([C.POINTER(MfcCmd), c_int, c_void_p, C.POINTER(c_float)], c_int),
     "mfc_graph_capture": ([C.POINTER(MfcCmd), c_int, C.POINTER(c_void_p)], c_int),

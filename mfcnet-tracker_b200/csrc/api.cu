@@ -623,6 +623,12 @@ int mfc_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, co
              "refine_tip_mask");
 }
 
+int mfc_top_contours(const double* rec, const int* n_contours, int max_contours, int W, double* top, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!rec || !n_contours || !top || max_contours < 1 || W < 1) return fail(MFC_EINVAL, "top_contours: bad argument");
+  MFC_LAUNCH(mfc::launch_top_contours(rec, n_contours, max_contours, W, top, (cudaStream_t)stream), "top_contours");
+}
+
 // ---- command list ------------------------------------------------------------------------------
 namespace {
 // side streams / events of the calling thread, per device (created on first use, never destroyed)

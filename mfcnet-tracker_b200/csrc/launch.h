@@ -83,4 +83,6 @@ cudaError_t launch_mask_heat(const float* heat, const uint8_t* cls, int cls_id, 
 cudaError_t launch_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, const double* rec, int max_contours,
                                    const int* n_contours, double area_threshold, int* sel, uint8_t* out, cudaStream_t st);
 
+cudaError_t launch_top_contours(const double* rec, const int* n_contours, int max_contours, int W, double* top, cudaStream_t st);
+
 }  // namespace mfc

@@ -287,14 +287,15 @@ __global__ void mask_heat_kernel(const float* __restrict__ heat, const uint8_t* 
 // descending, ties in findContours order (descending raster index of the first point); one below the area threshold is dropped.
 // rec = the records of mfc_trace_contours; sel[k] = raster index of the contour's first pixel (= its component root) or -1.
 __global__ void select_top2_kernel(const double* __restrict__ rec, const int* __restrict__ n_ptr, int max_contours, int W,
-                                   double area_threshold, int* __restrict__ sel) {
+                                   double area_threshold, int* __restrict__ sel, double* __restrict__ top) {
   __shared__ double s_a[256];
   __shared__ int s_i[256];
+  __shared__ int s_k[256];
   __shared__ int s_first;
   const int n = min(*n_ptr, max_contours);
   for (int pass = 0; pass < 2; ++pass) {
     double best_a = -1.0;
-    int best_i = -1;
+    int best_i = -1, best_k = -1;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
       const double a = fabs(rec[(size_t)k * 6]);
       const int idx = (int)rec[(size_t)k * 6 + 4] * W + (int)rec[(size_t)k * 6 + 3];
@@ -302,10 +303,12 @@ __global__ void select_top2_kernel(const double* __restrict__ rec, const int* __
       if (a > best_a || (a == best_a && idx > best_i)) {
         best_a = a;
         best_i = idx;
+        best_k = k;
       }
     }
     s_a[threadIdx.x] = best_a;
     s_i[threadIdx.x] = best_i;
+    s_k[threadIdx.x] = best_k;
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
       if (threadIdx.x < off) {
@@ -314,13 +317,18 @@ __global__ void select_top2_kernel(const double* __restrict__ rec, const int* __
         if (a > s_a[threadIdx.x] || (a == s_a[threadIdx.x] && idx > s_i[threadIdx.x])) {
           s_a[threadIdx.x] = a;
           s_i[threadIdx.x] = idx;
+          s_k[threadIdx.x] = s_k[threadIdx.x + off];
         }
       }
       __syncthreads();
     }
     if (threadIdx.x == 0) {
       if (pass == 0) s_first = s_i[0];
-      sel[pass] = (s_i[0] >= 0 && s_a[0] * 0.5 >= area_threshold) ? s_i[0] : -1;
+      if (sel) sel[pass] = (s_i[0] >= 0 && s_a[0] * 0.5 >= area_threshold) ? s_i[0] : -1;
+      if (top) {
+        for (int f = 0; f < 5; ++f) top[pass * 6 + f] = s_k[0] >= 0 ? rec[(size_t)s_k[0] * 6 + f] : 0.0;
+        top[pass * 6 + 5] = s_k[0] >= 0 ? 1.0 : 0.0;
+      }
     }
     __syncthreads();
   }
@@ -383,8 +391,13 @@ cudaError_t launch_mask_heat(const float* heat, const uint8_t* cls, int cls_id, 
 }
 cudaError_t launch_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, const double* rec, int max_contours,
                                    const int* n_contours, double area_threshold, int* sel, uint8_t* out, cudaStream_t st) {
-  select_top2_kernel<<<1, 256, 0, st>>>(rec, n_contours, max_contours, W, area_threshold, sel);
+  select_top2_kernel<<<1, 256, 0, st>>>(rec, n_contours, max_contours, W, area_threshold, sel, nullptr);
   refine_kernel<<<(H * W + 255) / 256, 256, 0, st>>>(mask, labels + (size_t)H * W, sel, H, W, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_top_contours(const double* rec, const int* n_contours, int max_contours, int W, double* top, cudaStream_t st) {
+  select_top2_kernel<<<1, 256, 0, st>>>(rec, n_contours, max_contours, W, 0.0, nullptr, top);
   return cudaGetLastError();
 }
 

@@ -131,6 +131,25 @@ def contour_records(raw, W):
     return out
 
 
+def top_subset(raw, W, k=2):
+    """The raw records of the k largest contours in `sorted(contours, key=contourArea, reverse=True)` order (area descending,
+    ties in findContours order = descending raster index of the first point).  Every consumer of a frame's records keeps at most
+    two contours, so the per-record Python work is bounded even when a noisy mask has tens of thousands of them."""
+    if len(raw) <= k:
+        return raw
+    area = np.abs(raw[:, 0] * 0.5)
+    idx = raw[:, 4] * W + raw[:, 3]
+    return raw[np.lexsort((-idx, -area))[:k]]
+
+
+def top_records_from_pack(row, W):
+    """[count | 2 x {a00,a10,a01,fx,fy,present}] as written by mfc_top_contours -> records of the (at most two) largest contours."""
+    if int(row[0]) > MAX_CONTOURS:
+        raise RuntimeError("trace_contours: %d contours exceed the %d-record buffer" % (int(row[0]), MAX_CONTOURS))
+    raw = row[1:13].reshape(2, 6)
+    return contour_records(raw[raw[:, 5] == 1.0], W)
+
+
 def calc_centroids(mask_u8):
     """utils/localization_utils_v2.py:15-33 on a device mask: up to two largest external contours
     (stable sort by contourArea, descending), centroid int(m10/m00), int(m01/m00) or the first
@@ -160,7 +179,6 @@ class _KeypointWorkspace:
     the device once, the contour tracer's label / record buffers are reused, and the four contour lists of a frame come back
     in ONE device-to-host copy (pinned) after ONE synchronisation -- the straightforward composition of the helpers above pays
     two pageable uploads, four `.item()` syncs and four record downloads per frame."""
-    QUICK = 64          # contour records per mask fetched with the counts; more than that -> one more (full) copy for that mask
 
     def __init__(self, device, H, W):
         self.device, self.H, self.W = device, H, W
@@ -175,8 +193,8 @@ class _KeypointWorkspace:
         self.labels = torch.empty((4, 8 * H * W), dtype=torch.int32, device=device)
         self.rec = torch.empty((4, MAX_CONTOURS, 6), dtype=torch.float64, device=device)
         self.n = torch.zeros(4, dtype=torch.int32, device=device)
-        self.pack = torch.empty((4, self.QUICK * 6 + 1), dtype=torch.float64, device=device)   # [count | first QUICK records]
-        self.host = torch.empty((4, self.QUICK * 6 + 1), dtype=torch.float64).pin_memory()
+        self.pack = torch.empty((4, 13), dtype=torch.float64, device=device)   # [count | the two largest records (mfc_top_contours)]
+        self.host = torch.empty((4, 13), dtype=torch.float64).pin_memory()
 
     def run(self, p):
         lib = abi.load()
@@ -199,21 +217,11 @@ class _KeypointWorkspace:
             for i in range(4):
                 abi.check(lib.mfc_trace_contours(self.masks[i].data_ptr(), H, W, self.labels[i].data_ptr(), self.rec[i].data_ptr(),
                                                  MAX_CONTOURS, self.n[i:i + 1].data_ptr(), st))
+                abi.check(lib.mfc_top_contours(self.rec[i].data_ptr(), self.n[i:i + 1].data_ptr(), MAX_CONTOURS, W, self.pack[i, 1:].data_ptr(), st))
             self.pack[:, 0] = self.n.double()
-            self.pack[:, 1:] = self.rec[:, :self.QUICK].reshape(4, -1)
             self.host.copy_(self.pack, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-        out = []
-        for i in range(4):
-            cnt = int(self.host[i, 0])
-            if cnt > MAX_CONTOURS:
-                raise RuntimeError("trace_contours: %d contours exceed the %d-record buffer" % (cnt, MAX_CONTOURS))
-            if cnt <= self.QUICK:
-                raw = self.host[i, 1:1 + cnt * 6].reshape(cnt, 6).numpy()
-            else:
-                raw = self.rec[i, :cnt].cpu().numpy()
-            out.append(contour_records(raw, W))
-        return out
+        return [top_records_from_pack(self.host[i].numpy(), W) for i in range(4)]
 
 
 _KP_WS = {}

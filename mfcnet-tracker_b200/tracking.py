@@ -17,7 +17,8 @@ import numpy as np
 import torch
 
 from . import abi
-from .heatmap import MAX_CONTOURS, _centroids_from_records, _stream, contour_records, create_circular_mask, gaussian_kernel1d
+from .heatmap import (MAX_CONTOURS, _centroids_from_records, _stream, create_circular_mask, gaussian_kernel1d,
+                      top_records_from_pack)
 
 # (base class, tip class, first tip column, first base column) of `compute_centroids_and_store` (:62-87)
 _SIDES = {"left": (3, 4, 0, 8), "right": (1, 2, 4, 10)}
@@ -75,8 +76,7 @@ def base_centroid_from_records(recs, area_threshold):
 
 class _TrackWorkspace:
     """Device buffers of one (device, H, W): six masks are traced per frame (2 bases, 2 raw tip masks, 2 local-maximum masks);
-    the records of four of them (bases, local maxima) come back in one pinned copy."""
-    QUICK = 64
+    the two largest contour records of four of them (bases, local maxima) come back in one pinned copy."""
 
     def __init__(self, device, H, W):
         self.device, self.H, self.W = device, H, W
@@ -97,8 +97,8 @@ class _TrackWorkspace:
         self.rec_tip = torch.empty((MAX_CONTOURS, 6), dtype=torch.float64, device=device)
         self.n = torch.zeros(6, dtype=torch.int32, device=device)                               # + the two raw tip masks
         self.sel = torch.empty(2, dtype=torch.int32, device=device)
-        self.pack = torch.empty((4, self.QUICK * 6 + 1), dtype=torch.float64, device=device)
-        self.host = torch.empty((4, self.QUICK * 6 + 1), dtype=torch.float64).pin_memory()
+        self.pack = torch.empty((4, 13), dtype=torch.float64, device=device)      # [count | the two largest records]
+        self.host = torch.empty((4, 13), dtype=torch.float64).pin_memory()
         self.host_n = torch.empty(6, dtype=torch.int32).pin_memory()
 
     def run(self, p, area_threshold, score):
@@ -133,19 +133,15 @@ class _TrackWorkspace:
                                                 self.lmax[k].data_ptr(), 1, H, W, st))
                 abi.check(lib.mfc_trace_contours(self.lmax[k].data_ptr(), H, W, lab, self.rec[2 * k + 1].data_ptr(), MAX_CONTOURS,
                                                  self.n[2 * k + 1:].data_ptr(), st))
+            for i in range(4):
+                abi.check(lib.mfc_top_contours(self.rec[i].data_ptr(), self.n[i:].data_ptr(), MAX_CONTOURS, W, self.pack[i, 1:].data_ptr(), st))
             self.pack[:, 0] = self.n[:4].double()
-            self.pack[:, 1:] = self.rec[:, :self.QUICK].reshape(4, -1)
             self.host.copy_(self.pack, non_blocking=True)
             self.host_n.copy_(self.n, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
         if int(self.host_n.max()) > MAX_CONTOURS:
             raise RuntimeError("track: more than %d contours in one mask" % MAX_CONTOURS)
-        out = []
-        for i in range(4):
-            cnt = int(self.host[i, 0])
-            raw = self.host[i, 1:1 + cnt * 6].reshape(cnt, 6).numpy() if cnt <= self.QUICK else self.rec[i, :cnt].cpu().numpy()
-            out.append(contour_records(raw, W))
-        return out   # base L, tip maxima L, base R, tip maxima R
+        return [top_records_from_pack(self.host[i].numpy(), W) for i in range(4)]   # base L, tip maxima L, base R, tip maxima R
 
 
 def _dist(x1, y1, x2, y2):

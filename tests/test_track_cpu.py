@@ -69,3 +69,23 @@ def test_tracker_refuses_cpu_tensors():
         class_map(torch.zeros(1, 5, 8, 8))
     with pytest.raises(ValueError):
         ToolTracker().step(torch.zeros(2, 5, 8, 8))
+
+
+def test_top_subset_keeps_the_sorted_prefix():
+    """heatmap.top_subset + the consumers' stable sort == the stable sort over all records (ties in area included)."""
+    from mfcnet_tracker_b200.heatmap import _centroids_from_records, contour_records, top_subset
+    from mfcnet_tracker_b200.tracking import base_centroid_from_records
+    rng = np.random.default_rng(9)
+    W = 50
+    for trial in range(200):
+        n = int(rng.integers(0, 40))
+        raw = np.zeros((n, 6))
+        raw[:, 0] = rng.integers(0, 6, n) * 2            # few distinct areas: many ties
+        raw[:, 1] = rng.integers(0, 1000, n)
+        raw[:, 2] = rng.integers(0, 1000, n)
+        pos = rng.permutation(W * 40)[:n]
+        raw[:, 3], raw[:, 4] = pos % W, pos // W
+        full = contour_records(raw, W)
+        sub = contour_records(top_subset(raw, W), W)
+        assert _centroids_from_records(sub) == _centroids_from_records(full), trial
+        assert base_centroid_from_records(sub, 3) == base_centroid_from_records(full, 3), trial
