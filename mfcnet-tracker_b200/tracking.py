@@ -100,8 +100,14 @@ class _TrackWorkspace:
         self.pack = torch.empty((4, 13), dtype=torch.float64, device=device)      # [count | the two largest records]
         self.host = torch.empty((4, 13), dtype=torch.float64).pin_memory()
         self.host_n = torch.empty(6, dtype=torch.int32).pin_memory()
+        self.done = torch.cuda.Event()
 
     def run(self, p, area_threshold, score):
+        self.enqueue(p, area_threshold, score)
+        return self.finish()
+
+    def enqueue(self, p, area_threshold, score):
+        """Issue the frame's device work and its (asynchronous) download on the current stream; no synchronisation."""
         lib = abi.load()
         H, W, dev = self.H, self.W, self.device
         st = _stream(dev)
@@ -138,7 +144,12 @@ class _TrackWorkspace:
             self.pack[:, 0] = self.n[:4].double()
             self.host.copy_(self.pack, non_blocking=True)
             self.host_n.copy_(self.n, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
+            self.done.record(torch.cuda.current_stream(dev))
+
+    def finish(self):
+        """Wait for the download of the frame issued by `enqueue` and decode it."""
+        W = self.W
+        self.done.synchronize()
         if int(self.host_n.max()) > MAX_CONTOURS:
             raise RuntimeError("track: more than %d contours in one mask" % MAX_CONTOURS)
         return [top_records_from_pack(self.host[i].numpy(), W) for i in range(4)]   # base L, tip maxima L, base R, tip maxima R
@@ -164,6 +175,7 @@ class ToolTracker:
         self._px = {"left": np.zeros(2), "right": np.zeros(2)}
         self._py = {"left": np.zeros(2), "right": np.zeros(2)}
         self._ws = {}
+        self._pending = None
 
     def _associate(self, side, row, base, tips):
         """:104-192 without the drawing calls."""
@@ -189,15 +201,32 @@ class ToolTracker:
         return found, row[t0:t0 + 4:2], row[t0 + 1:t0 + 4:2]
 
     def step(self, prob):
+        self.submit(prob)
+        return self.collect()
+
+    def submit(self, prob):
+        """First half of `step`: issues the frame's device work without synchronising, so that the caller can launch the next
+        frame's forward before `collect()` waits for this one (one frame in flight)."""
         if prob.dim() != 4 or prob.shape[0] != 1 or prob.shape[1] != 5:
             raise ValueError("ToolTracker.step expects a (1,5,H,W) probability map")
         if not prob.is_cuda:
             raise RuntimeError("ToolTracker.step: CUDA tensors only (no CPU fallback)")
+        if self._pending is not None:
+            raise RuntimeError("ToolTracker.submit: the previous frame has not been collected")
         p = prob.contiguous().float()
         key = (p.device, p.shape[2], p.shape[3])
         if key not in self._ws:
             self._ws[key] = _TrackWorkspace(*key)
-        base_l, tips_l, base_r, tips_r = self._ws[key].run(p, self.area_threshold, self.score_detection_threshold)
+        self._ws[key].enqueue(p, self.area_threshold, self.score_detection_threshold)
+        self._pending = (self._ws[key], p)      # p stays referenced until its kernels have run
+
+    def collect(self):
+        """Second half of `step`: the frame's `centroid_locations` row."""
+        if self._pending is None:
+            raise RuntimeError("ToolTracker.collect: nothing submitted")
+        ws, _ = self._pending
+        self._pending = None
+        base_l, tips_l, base_r, tips_r = ws.finish()
         row = np.full(12, np.nan)
         for side, base, tips in (("left", base_l, tips_l), ("right", base_r, tips_r)):
             found, cx, cy = self._associate(side, row, base_centroid_from_records(base, self.area_threshold), _centroids_from_records(tips))

@@ -69,6 +69,8 @@ def test_tracker_refuses_cpu_tensors():
         class_map(torch.zeros(1, 5, 8, 8))
     with pytest.raises(ValueError):
         ToolTracker().step(torch.zeros(2, 5, 8, 8))
+    with pytest.raises(RuntimeError):
+        ToolTracker().collect()
 
 
 def test_top_subset_keeps_the_sorted_prefix():
