@@ -139,17 +139,30 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restric
   if (i == 0) *n_out = 0;
 }
 
-// foreground: 8-connectivity; background: 4-connectivity (the complement convention of findContours)
+// foreground: 8-connectivity; background: 4-connectivity (the complement convention of findContours).
+// Only the unions that are not implied by others are issued (union-find does not care about the order, only about the edge set):
+//  * horizontal (i, i-1): pixels of one run inside a 32-pixel warp segment already share their initial label -> lane 0 only;
+//  * vertical (i, i-W): implied by the same edge one pixel to the left when i-1 continues i's run and i-W-1 continues the run
+//    above (i ~ i-1 ~ i-W-1 ~ i-W) -> only where one of the two runs starts;
+//  * diagonals (foreground): (i, i-W-1) is implied through i-W or through i-1 when either is foreground, (i, i-W+1) through
+//    i-W or through i+1.
+// On blob-like masks almost every pixel issues nothing.
 __global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lab, int H, int W) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
   const int x = i % W, y = i / W;
   const bool fg = mask[i] != 0;
-  if (x > 0 && (mask[i - 1] != 0) == fg) uf_union(lab, i, i - 1);
-  if (y > 0 && (mask[i - W] != 0) == fg) uf_union(lab, i, i - W);
-  if (fg && y > 0) {
-    if (x > 0 && mask[i - W - 1] != 0) uf_union(lab, i, i - W - 1);
-    if (x + 1 < W && mask[i - W + 1] != 0) uf_union(lab, i, i - W + 1);
+  const bool left_same = x > 0 && (mask[i - 1] != 0) == fg;
+  if (left_same && (threadIdx.x & 31) == 0) uf_union(lab, i, i - 1);
+  if (y == 0) return;
+  const bool up = mask[i - W] != 0;
+  if (up == fg) {
+    const bool up_left_same = x > 0 && (mask[i - W - 1] != 0) == up;
+    if (!(left_same && up_left_same)) uf_union(lab, i, i - W);
+  }
+  if (fg && !up) {
+    if (x > 0 && mask[i - W - 1] != 0 && mask[i - 1] == 0) uf_union(lab, i, i - W - 1);
+    if (x + 1 < W && mask[i - W + 1] != 0 && mask[i + 1] == 0) uf_union(lab, i, i - W + 1);
   }
 }
 
