@@ -197,6 +197,18 @@ def test_contour_labels_under_contention(M):
             assert np.array_equal(M.refine_tip_segmentation(dm, 10).cpu().numpy(), want_ref), (dens, rep)
 
 
+def test_contour_labels_odd_sizes(M):
+    """Widths that are not a multiple of the 32-pixel warp segment (runs and the unions skipped as implied straddle rows)."""
+    from mfcnet_tracker_b200 import heatmap as HM
+    rng = np.random.default_rng(17)
+    for (H, W) in ((37, 53), (50, 67), (1, 40), (33, 1), (64, 31), (9, 33)):
+        for dens in (0.3, 0.55, 0.8):
+            mask = (255 * (rng.random((H, W)) < dens)).astype(np.uint8)
+            dm = torch.from_numpy(mask).cuda()
+            assert HM.trace_contours(dm) == [tuple(r) for r in LO.contour_records(mask)], (H, W, dens)
+            assert np.array_equal(M.refine_tip_segmentation(dm, 3).cpu().numpy(), TO.refine_tip_segmentation(mask, 3)), (H, W, dens)
+
+
 def test_class_map_matches_script(M):
     for seed, thr in ((0, 0.0), (1, 0.3), (2, 0.5), (3, 0.21)):
         p = synth.uniform("cm/%d" % seed, (1, 5, 60, 80), seed)
