@@ -15,6 +15,11 @@ torch_oracle.py   fp32 functional restatement of the reference nn.Modules
 corr_oracle.c     plain-C restatement of the CuPy correlation kernels
 corr.py           ctypes loader for corr_oracle.c + numpy restatement
 localize_oracle.py  the reference's scipy/OpenCV localisation call sequence
+track_oracle.py   the video script's per-frame tracking (class map, tip refinement,
+                  base / tip association) on the same cv2 / scipy calls
+track_cases.py    synthetic probability-map sequences for it
+make_golden_track.py  executes the reference script's own four functions (cut
+                  out of its source with ast) and writes tests/golden/track_rows.json
 refload.py        import recipe for /root/reference (authoring container only)
 make_golden.py    runs the *real* reference modules and writes tests/golden/
 
