@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MFC_ABI_VERSION 4
+#define MFC_ABI_VERSION 5
 
 /* error codes */
 #define MFC_OK 0
@@ -142,6 +142,9 @@ typedef struct MfcConvDesc {
  * runs in the opposite direction of its producer starts with the part of its input that is still cache-resident ("snake"
  * order through the layers).  Results are identical up to the grouping of the GroupNorm partial sums. */
 #define MFC_CONV_REVERSE_ORDER 2
+/* mfc_conv2d_fwd will be given io->stats: the plan must keep the padded Cout within the 256 channels the epilogue's
+ * shared-memory scratch holds (part of the plan key, like MFC_CONV_HAS_RESIDUAL). */
+#define MFC_CONV_WANT_STATS 4
 
 int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info);
 
@@ -176,14 +179,27 @@ typedef struct MfcConvIO {
 } MfcConvIO;
 int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream);
 
-/* Plan-time autotuning: measures the planner's shortlisted tilings (tile shape, K staging, weight layout) of `d` on the
- * device with the caller's real buffers and keeps the fastest for every later mfc_conv2d_query / _pack_weights / _fwd of
- * the same geometry.  io->w_packed is ignored; the raw OIHW weights are packed into `scratch_packed`
+/* Plans.  The tiling of a geometry (B, sizes, channels, kernel, stride, pad, upsample, chunk count, affine-on-load,
+ * flags, dtype, out_stride) is fixed the first time mfc_conv2d_query / _pack_weights / _fwd sees it and never changes
+ * afterwards in that process: packed weights, the statistics buffer and mfc_gn_finalize's record count depend on it.
+ * It is taken from (1) mfc_conv2d_autotune, if that ran for the geometry first, (2) the imported tuning table,
+ * (3) the cost model.  (2) and (3) are deterministic: processes that do not tune live produce identical bits.
+ *
+ * mfc_conv2d_autotune measures the planner's shortlisted tilings (tile shape, K staging, weight layout) of `d` on the
+ * device with the caller's real buffers and keeps the fastest.  It is a no-op (returns MFC_OK) for a geometry that already
+ * has a plan or a table entry.  io->w_packed is ignored; the raw OIHW weights are packed into `scratch_packed`
  * (`scratch_bytes`: twice the packed_weight_bytes of mfc_conv2d_query covers every candidate; candidates that do not fit are
- * skipped) once per weight image.  io->stats, when given, must hold
- * [B][148][nb*nblk][2] floats.  Synchronises `stream`.  Idempotent per geometry; call it BEFORE mfc_conv2d_query. */
+ * skipped) once per weight image.  io->stats, when given, must hold [B][148][nb*nblk][2] floats.  Synchronises `stream`.
+ *
+ * Weights, scale and shift are read by the conv kernel BEFORE it waits for its predecessor on the stream (programmatic
+ * dependent launch): they must be complete -- the producing work synchronised -- before a conv that uses them is launched. */
 int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* w_oihw, int Cin_w, const int* chan_map,
                         void* scratch_packed, long long scratch_bytes, int reps, void* stream);
+/* Tuning table as text, one geometry per line ("<16 key ints> : TH TW slide CBc NB nstages", '#' = comment).
+ * export returns the bytes needed including the terminating 0 and writes at most `cap`; import returns the number of
+ * entries taken (geometries that already have a plan keep it) or a negative error code. */
+long long mfc_conv2d_plan_export(char* buf, long long cap);
+int mfc_conv2d_plan_import(const char* text);
 
 /* GroupNorm statistics -> per-(sample,channel) affine.  Replaces nn.GroupNorm
  * (models/resunet.py:72,77) split in two: partial sums come from the producing conv's

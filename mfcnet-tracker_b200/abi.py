@@ -14,6 +14,7 @@ MFC_F16, MFC_BF16 = 0, 1
 MFC_MAX_SRC = 8
 MFC_CONV_HAS_RESIDUAL = 1
 MFC_CONV_REVERSE_ORDER = 2
+MFC_CONV_WANT_STATS = 4
 OP_FORK, OP_JOIN, MFC_MAX_LANES = 100, 101, 4
 OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP, OP_FUSE_SUM, OP_RESIZE, OP_MAXPOOL2, OP_HEATMAP = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
@@ -114,6 +115,8 @@ _SIGNATURES = {
     "mfc_conv2d_pack_weights": ([C.POINTER(MfcConvDesc), c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "mfc_conv2d_fwd": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p], c_int),
     "mfc_conv2d_autotune": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p], c_int),
+    "mfc_conv2d_plan_export": ([C.c_char_p, c_ll], c_ll),
+    "mfc_conv2d_plan_import": ([C.c_char_p], c_int),
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
     "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p], c_int),
     "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),
@@ -183,17 +186,43 @@ def load(build_if_missing=True):
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.argtypes = args
             fn.restype = res
-        if lib.mfc_abi_version() != 4:
+        if lib.mfc_abi_version() != 5:
             raise RuntimeError("libmfcnet_b200.so ABI version mismatch")
+        _import_table(lib)
         _lib = _PlanOnly(lib) if plan_only() else lib
     return _lib
+
+
+TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning", "b200.tbl")
+
+
+def _import_table(lib):
+    """The committed tuning table (tools/tune_table.py, measured on a B200): conv tilings become a pure function of the
+    geometry, identical in every process.  MFC_CONV_TABLE=0 ignores it (cost model only), MFC_CONV_TABLE=<path> overrides."""
+    path = os.environ.get("MFC_CONV_TABLE", TABLE)
+    if path == "0" or not os.path.exists(path):
+        return 0
+    with open(path, "rb") as f:
+        n = lib.mfc_conv2d_plan_import(f.read())
+    if n < 0:
+        raise RuntimeError("tuning table %s: %s" % (path, (lib.mfc_last_error() or b"").decode()))
+    return n
+
+
+def export_table():
+    """Text of every measured / table-derived plan of this process (see tools/tune_table.py)."""
+    lib = load()
+    need = lib.mfc_conv2d_plan_export(None, 0)
+    buf = C.create_string_buffer(int(need))
+    lib.mfc_conv2d_plan_export(buf, need)
+    return buf.value.decode()
 
 
 class _PlanOnly:
     """MFC_B200_PLAN_ONLY=1 (CPU test-suite only): plan construction is exercised for real
     (descriptor validation, tiling queries, buffer shapes, command lists) but nothing is launched,
     so outputs are UNINITIALISED memory.  This is not a compute path."""
-    _REAL = ("mfc_abi_version", "mfc_last_error", "mfc_conv2d_query")
+    _REAL = ("mfc_abi_version", "mfc_last_error", "mfc_conv2d_query", "mfc_conv2d_plan_export", "mfc_conv2d_plan_import")
 
     def __init__(self, lib):
         self._lib = lib

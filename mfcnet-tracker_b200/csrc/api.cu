@@ -6,8 +6,8 @@
 #include <string.h>
 
 #include <map>
+#include <string>
 #include <mutex>
-#include <set>
 #include <tuple>
 #include <vector>
 
@@ -63,9 +63,24 @@ int arch_ok() {
 inline bool dtype_ok(int dt) { return dt == MFC_F16 || dt == MFC_BF16; }
 
 // ---- conv planner cache ---------------------------------------------------------------------
-using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int, int>;
+// A plan (tiling) is a pure function of the geometry key.  It comes from, in this order: (1) an entry this process
+// measured with mfc_conv2d_autotune BEFORE the geometry was first planned, (2) the imported tuning table
+// (mfc_conv2d_plan_import: choices measured once on a B200 and committed with the package), (3) the cost model.
+// Once a plan has been handed out (query / pack / fwd) it is frozen for the life of the process: packed weights,
+// statistics buffers and gn_finalize's record count all depend on it.  (2) and (3) are deterministic, so two processes
+// that do not tune live compute bit-identical results.
+using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int>;
+struct PlanEntry {
+  mfc::ConvTiling t;
+  bool handed_out = false;
+  bool tuned = false;   // measured in this process or resolved from the table (exported by mfc_conv2d_plan_export)
+};
+struct TableChoice {   // what identifies one candidate of conv_enumerate for a key
+  int TH, TW, slide, CBc, NB, nstages;
+};
 std::mutex g_plan_mu;
-std::map<PlanKey, mfc::ConvTiling> g_plans;
+std::map<PlanKey, PlanEntry> g_plans;
+std::map<PlanKey, TableChoice> g_table;
 
 int validate_desc(const MfcConvDesc* d) {
   if (!d) return fail(MFC_EINVAL, "conv: null descriptor");
@@ -98,7 +113,7 @@ int validate_desc(const MfcConvDesc* d) {
   return MFC_OK;
 }
 
-std::set<PlanKey> g_tuned;  // geometries whose plan was measured (mfc_conv2d_autotune)
+constexpr int kPlanFlags = MFC_CONV_HAS_RESIDUAL | MFC_CONV_WANT_STATS;
 
 PlanKey plan_key(const MfcConvDesc* d) {
   int chunks = 0, aff = 0;
@@ -107,27 +122,62 @@ PlanKey plan_key(const MfcConvDesc* d) {
     aff |= d->src[i].affine != nullptr;
   }
   return PlanKey{d->B, d->Hin, d->Win, d->Hout, d->Wout, d->Cout, d->kh, d->kw, d->stride, d->pad, d->upsample, chunks, aff,
-                 d->reserved & MFC_CONV_HAS_RESIDUAL};
+                 d->reserved & kPlanFlags, d->dtype, d->out_stride == 2 ? 2 : 1};
+}
+
+bool same_choice(const mfc::ConvTiling& t, const TableChoice& c) {
+  return t.TH == c.TH && t.TW == c.TW && t.slide == c.slide && t.CBc == c.CBc && t.NB == c.NB && t.nstages == c.nstages;
+}
+
+// statistics need the padded Cout to fit the per-warp shared-memory scratch (see conv_fwd_tiled)
+bool tiling_serves(const MfcConvDesc* d, const mfc::ConvTiling& t) {
+  return !(d->reserved & MFC_CONV_WANT_STATS) || t.NB * t.nblk <= 256;
+}
+
+// g_plan_mu held.  Resolves the plan of `d` (table choice, else the cost model) without marking it handed out.
+int resolve_locked(const MfcConvDesc* d, const PlanKey& key, PlanEntry** out) {
+  auto it = g_plans.find(key);
+  if (it == g_plans.end()) {
+    PlanEntry e;
+    memset(&e.t, 0, sizeof(e.t));
+    bool found = false;
+    auto tb = g_table.find(key);
+    if (tb != g_table.end()) {
+      std::vector<mfc::ConvTiling> all;
+      mfc::conv_candidates(*d, all);
+      for (const auto& t : all)
+        if (same_choice(t, tb->second) && tiling_serves(d, t)) {
+          e.t = t;
+          e.tuned = true;
+          found = true;
+          break;
+        }
+    }
+    if (!found) {
+      std::vector<mfc::ConvTiling> ranked;
+      mfc::conv_candidates(*d, ranked, /*sorted_by_cost=*/true);
+      for (const auto& t : ranked)
+        if (tiling_serves(d, t)) {
+          e.t = t;
+          found = true;
+          break;
+        }
+    }
+    if (!found) return fail(MFC_EINVAL, "conv: no tiling fits shared memory / TMEM for this shape");
+    it = g_plans.emplace(key, e).first;
+  }
+  *out = &it->second;
+  return MFC_OK;
 }
 
 int get_tiling(const MfcConvDesc* d, mfc::ConvTiling* out) {
   const PlanKey key = plan_key(d);
-  {
-    std::lock_guard<std::mutex> g(g_plan_mu);
-    auto it = g_plans.find(key);
-    if (it != g_plans.end()) {
-      *out = it->second;
-      return MFC_OK;
-    }
-  }
-  mfc::ConvTiling t;
-  memset(&t, 0, sizeof(t));
-  if (!mfc::conv_choose_tiling(*d, t)) return fail(MFC_EINVAL, "conv: no tiling fits shared memory / TMEM for this shape");
-  {
-    std::lock_guard<std::mutex> g(g_plan_mu);
-    g_plans[key] = t;
-  }
-  *out = t;
+  std::lock_guard<std::mutex> g(g_plan_mu);
+  PlanEntry* e = nullptr;
+  int rc = resolve_locked(d, key, &e);
+  if (rc != MFC_OK) return rc;
+  e->handed_out = true;
+  *out = e->t;
   return MFC_OK;
 }
 
@@ -339,8 +389,12 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
   if (!io || !w_oihw || !scratch_packed || reps < 1) return fail(MFC_EINVAL, "conv_autotune: bad argument");
   const PlanKey key = plan_key(d);
   {
+    // a plan that was already handed out (or measured, or taken from the table) is final: weights may have been packed
+    // and statistics buffers sized for it
     std::lock_guard<std::mutex> g(g_plan_mu);
-    if (g_tuned.count(key)) return MFC_OK;
+    auto it = g_plans.find(key);
+    if (it != g_plans.end() && (it->second.handed_out || it->second.tuned)) return MFC_OK;
+    if (g_table.count(key)) return MFC_OK;
   }
   std::vector<mfc::ConvTiling> cands;
   mfc::conv_shortlist(*d, getenv("MFC_CONV_TUNE_WIDTH") ? atoi(getenv("MFC_CONV_TUNE_WIDTH")) : 3, cands);
@@ -366,6 +420,7 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
         cudaError_t e = mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,
                                                  t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, scratch_packed,
                                                  d->dtype == MFC_BF16, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the conv reads its weights before griddepcontrol.wait
         if (e != cudaSuccess) rc = cuda_fail(e, "conv_autotune: pack");
         packed = true;
       }
@@ -397,10 +452,89 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
   if (best_i < 0) return fail(MFC_EINVAL, "conv_autotune: no candidate ran");
   {
     std::lock_guard<std::mutex> g(g_plan_mu);
-    g_plans[key] = cands[best_i];
-    g_tuned.insert(key);
+    auto it = g_plans.find(key);
+    if (it == g_plans.end() || !it->second.handed_out) {  // another thread may have planned this geometry meanwhile
+      PlanEntry e;
+      e.t = cands[best_i];
+      e.tuned = true;
+      g_plans[key] = e;
+    }
   }
   return MFC_OK;
+}
+
+/* Tuning table.  One line per geometry:
+ *   B Hin Win Hout Wout Cout kh kw stride pad upsample chunks affine flags dtype out_stride : TH TW slide CBc NB nstages
+ * export: every plan of this process that was measured (mfc_conv2d_autotune) or came from an imported table.  Returns the
+ * number of bytes the text needs (incl. the terminating 0); writes at most `cap` bytes. */
+long long mfc_conv2d_plan_export(char* buf, long long cap) {
+  std::lock_guard<std::mutex> g(g_plan_mu);
+  std::string out;
+  char line[256];
+  for (const auto& kv : g_plans) {
+    if (!kv.second.tuned) continue;
+    const PlanKey& k = kv.first;
+    const mfc::ConvTiling& t = kv.second.t;
+    snprintf(line, sizeof(line), "%d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d : %d %d %d %d %d %d\n", std::get<0>(k), std::get<1>(k),
+             std::get<2>(k), std::get<3>(k), std::get<4>(k), std::get<5>(k), std::get<6>(k), std::get<7>(k), std::get<8>(k),
+             std::get<9>(k), std::get<10>(k), std::get<11>(k), std::get<12>(k), std::get<13>(k), std::get<14>(k), std::get<15>(k),
+             t.TH, t.TW, t.slide, t.CBc, t.NB, t.nstages);
+    out += line;
+  }
+  for (const auto& kv : g_table) {  // imported entries that were not needed by this process are passed through
+    if (g_plans.count(kv.first)) continue;
+    const PlanKey& k = kv.first;
+    const TableChoice& c = kv.second;
+    snprintf(line, sizeof(line), "%d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d : %d %d %d %d %d %d\n", std::get<0>(k), std::get<1>(k),
+             std::get<2>(k), std::get<3>(k), std::get<4>(k), std::get<5>(k), std::get<6>(k), std::get<7>(k), std::get<8>(k),
+             std::get<9>(k), std::get<10>(k), std::get<11>(k), std::get<12>(k), std::get<13>(k), std::get<14>(k), std::get<15>(k),
+             c.TH, c.TW, c.slide, c.CBc, c.NB, c.nstages);
+    out += line;
+  }
+  const long long need = (long long)out.size() + 1;
+  if (buf && cap > 0) {
+    const long long n = need <= cap ? need - 1 : cap - 1;
+    memcpy(buf, out.data(), (size_t)n);
+    buf[n] = 0;
+  }
+  return need;
+}
+
+/* import: lines of the format above ('#' starts a comment).  Geometries already planned in this process keep their plan.
+ * Returns the number of entries taken, or a negative error code for a malformed line. */
+int mfc_conv2d_plan_import(const char* text) {
+  if (!text) return fail(MFC_EINVAL, "plan_import: null text");
+  std::lock_guard<std::mutex> g(g_plan_mu);
+  int taken = 0, lineno = 0;
+  const char* p = text;
+  while (*p) {
+    const char* e = strchr(p, '\n');
+    const size_t len = e ? (size_t)(e - p) : strlen(p);
+    ++lineno;
+    if (len > 0 && len < 240 && p[0] != '#') {
+      char line[256];
+      memcpy(line, p, len);
+      line[len] = 0;
+      int k[16];
+      TableChoice c;
+      const int n = sscanf(line, "%d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d : %d %d %d %d %d %d", &k[0], &k[1], &k[2], &k[3], &k[4],
+                           &k[5], &k[6], &k[7], &k[8], &k[9], &k[10], &k[11], &k[12], &k[13], &k[14], &k[15], &c.TH, &c.TW, &c.slide,
+                           &c.CBc, &c.NB, &c.nstages);
+      bool blank = true;
+      for (size_t i = 0; i < len; ++i) blank = blank && (line[i] == ' ' || line[i] == '\t' || line[i] == '\r');
+      if (!blank) {
+        if (n != 22) return fail(MFC_EINVAL, "plan_import: malformed line %d", lineno);
+        const PlanKey key{k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8], k[9], k[10], k[11], k[12], k[13], k[14], k[15]};
+        if (!g_plans.count(key)) {
+          g_table[key] = c;
+          ++taken;
+        }
+      }
+    }
+    if (!e) break;
+    p = e + 1;
+  }
+  return taken;
 }
 
 int mfc_gn_finalize(const float* stats, int B, int stats_per_image, int cpad, int C, int groups, long long pixels, const float* gamma,

@@ -1393,15 +1393,16 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
   }  // N-block options
 }
 
-bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
+// Every feasible tiling of `d`, in enumeration order or (stable-)sorted by modelled cost: the first entry of the sorted
+// list is the cost model's choice.
+void conv_candidates(const MfcConvDesc& d, std::vector<ConvTiling>& out, bool sorted_by_cost) {
   std::vector<std::pair<double, ConvTiling>> all;
   conv_enumerate(d, all);
-  if (all.empty()) return false;
-  size_t bi = 0;
-  for (size_t i = 1; i < all.size(); ++i)
-    if (all[i].first < all[bi].first) bi = i;
-  best = all[bi].second;
-  return true;
+  if (sorted_by_cost)
+    std::stable_sort(all.begin(), all.end(),
+                     [](const std::pair<double, ConvTiling>& a, const std::pair<double, ConvTiling>& b) { return a.first < b.first; });
+  out.reserve(all.size());
+  for (const auto& c : all) out.push_back(c.second);
 }
 
 // Candidates worth MEASURING (mfc_conv2d_autotune): the model's best few in every (weight layout, ring depth class)
@@ -1409,7 +1410,8 @@ bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& best) {
 void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling>& out) {
   std::vector<std::pair<double, ConvTiling>> all;
   conv_enumerate(d, all);
-  std::sort(all.begin(), all.end(), [](const std::pair<double, ConvTiling>& a, const std::pair<double, ConvTiling>& b) { return a.first < b.first; });
+  std::stable_sort(all.begin(), all.end(),
+                   [](const std::pair<double, ConvTiling>& a, const std::pair<double, ConvTiling>& b) { return a.first < b.first; });
   int taken[2][3][3] = {};
   int nb_seen[3] = {0, 0, 0};
   for (const auto& c : all) {

@@ -90,7 +90,7 @@ struct ConvParams {
 
 // host planner
 int conv_nb(int cout, int* nblk);
-bool conv_choose_tiling(const MfcConvDesc& d, ConvTiling& out);
+void conv_candidates(const MfcConvDesc& d, std::vector<ConvTiling>& out, bool sorted_by_cost = false);
 void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling>& out);
 
 }  // namespace mfc

@@ -27,8 +27,10 @@ def default_dtype():
 
 
 def autotune_enabled():
-    """MFC_CONV_TUNE=0 disables the plan-time measurement of conv tilings (the cost model's choice is used)."""
-    return os.environ.get("MFC_CONV_TUNE", "1") != "0"
+    """MFC_CONV_TUNE=1 measures the conv tilings of geometries that have no plan yet on the device at plan time
+    (tools/tune_table.py uses it to write the committed table).  Default off: tilings come from the committed tuning
+    table, else the cost model -- both deterministic, so every process computes the same bits."""
+    return os.environ.get("MFC_CONV_TUNE", "0") == "1"
 
 
 def snake_enabled():
@@ -157,6 +159,7 @@ class Program:
         self.n_kernels = 0   # kernel launches one run() issues
         self.bindings = {}   # external input key -> [setter(tensor)]
         self.meta = []       # per command: {'kind', 'name', 'bytes', 'flops'} (algorithmic, for the roofline)
+        self.packer = None   # WeightPacker whose device writes must have completed before the first run (Builder sets it)
 
     # ---- low-level recording -----------------------------------------------------------------
     def _push(self, op, a, b=None, launches=1, meta=None):
@@ -193,6 +196,8 @@ class Program:
     def run(self, stream=None):
         if self._array is None:
             self.finalize()
+        if self.packer is not None:
+            self.packer.settle()
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
         abi.check(self.lib.mfc_run_list(self._array, len(self.cmds), stream))
@@ -218,6 +223,7 @@ class Program:
         return [dict(self.meta[i], ms=float(ms[i])) for i in range(len(self.cmds))]
 
     def extend(self, other):
+        self.packer = self.packer or other.packer
         self.cmds += other.cmds
         self.meta += other.meta
         self.keep += other.keep
@@ -528,7 +534,16 @@ class WeightPacker:
                 sh = torch.zeros(cpad, dtype=torch.float32, device=self.device)
                 sh[: shift.numel()] = shift.detach().float()
             self.cache[k] = (PackedConv(packed, sc, sh), w, cm)
+            # conv_tc_kernel stages weights / scale / shift before its griddepcontrol.wait (they overlap the previous
+            # kernel's tail): everything written here must be complete before the first conv launch that uses it
+            self._dirty = True
         return self.cache[k][0]
+
+    def settle(self):
+        """Synchronise once after (re)packing: see pack()."""
+        if getattr(self, "_dirty", False) and self.device.type == "cuda" and not abi.plan_only():
+            torch.cuda.current_stream(self.device).synchronize()
+        self._dirty = False
 
 
 def params_fingerprint(module):
@@ -545,6 +560,7 @@ class Builder:
 
     def __init__(self, device, dtype_name, packer, arena):
         self.prog = Program(device, dtype_name)
+        self.prog.packer = packer
         self.packer = packer
         self.arena = arena
         self.device = self.prog.device
@@ -559,6 +575,8 @@ class Builder:
         d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity)
         if residual is not None:
             d.reserved |= abi.MFC_CONV_HAS_RESIDUAL
+        if want_stats:
+            d.reserved |= abi.MFC_CONV_WANT_STATS
         layout = []
         off = 0
         for i, s in enumerate(srcs):

@@ -72,6 +72,30 @@ def test_correlation_reference_operating_point_properties(M):
     assert (out - ex).abs().max().item() <= 2e-6
 
 
+def test_correlation_matches_the_reference_kernel_itself(M):
+    """The reference's own CUDA-C kernels (models/unflow_correlation.py:10-105), compiled with NVRTC and launched as
+    `_FunctionCorrelation.forward` launches them (oracle/corr_ref_nvrtc.py), at the reference's operating point
+    (C=256, 48x160, max displacement 20, stride 2: models/unflow_model.py:157-163) and on a ragged channel count."""
+    from oracle import corr_ref_nvrtc as R
+    if not R.available():
+        pytest.skip("baseline/_ref/unflow_correlation_kernels.json (python -m oracle.make_corr_ref) or cuda-python missing")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for (B, Cc, H, W) in [(1, 256, 48, 160), (2, 40, 12, 20)]:
+        a = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+        b = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+        ref = R.forward(a, b)
+        exact = M.correlation(a, b, exact_order=True)
+        fast = M.correlation(a, b)
+        torch.cuda.synchronize()
+        assert torch.equal(exact, ref), float((exact - ref).abs().max())      # same fp32 summation order: same bits
+        assert float((fast - ref).abs().max()) <= 2e-6                        # fp32 rounding only (|out| <~ 1)
+    # and the plain-C oracle agrees with the reference kernel bit for bit (pins oracle/corr_oracle.c)
+    a = synth.normal("gcorr/a", (1, 40, 9, 11), 3)
+    b = synth.normal("gcorr/b", (1, 40, 9, 11), 4)
+    ref = R.forward(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+    assert np.array_equal(corr.correlation_c(a, b, 20, 2), ref)
+
+
 def test_correlation_rejects_cpu(M):
     with pytest.raises(NotImplementedError):
         M.correlation(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8))

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     assert sorted(m.abi.EXPORTS) == names          # the ctypes binding covers the whole header
     lib.mfc_abi_version.restype = C.c_int
-    assert lib.mfc_abi_version() == 4
+    assert lib.mfc_abi_version() == 5
 
 
 def test_struct_sizes_match_header():
@@ -64,6 +64,66 @@ def test_struct_sizes_match_header():
     sizes = dict(line.split() for line in out.strip().splitlines())
     for n in names:
         assert C.sizeof(getattr(m.abi, n)) == int(sizes[n]), n
+
+
+def _desc(m, B=2, H=64, W=96, cin=16, cout=16, k=3, flags=0):
+    d = m.abi.MfcConvDesc()
+    d.B, d.Hin, d.Win, d.Hout, d.Wout, d.Cout = B, H, W, H, W, cout
+    d.kh = d.kw = k
+    d.stride, d.pad, d.upsample, d.dtype, d.nsrc, d.reserved = 1, k // 2, 1, m.abi.MFC_F16, 1, flags
+    d.src[0].nchunks = (cin + 7) // 8
+    return d
+
+
+_PLAN_PROBE = """
+import ctypes as C, json, sys
+sys.path.insert(0, %r)
+import mfcnet_tracker_b200 as m
+from tests.test_host_cpu import _desc
+lib = m.abi.load()
+out = []
+for (B, H, W, cin, cout, k) in [(24, 480, 640, 16, 16, 3), (8, 480, 640, 22, 15, 11), (1, 60, 80, 128, 128, 3), (3, 64, 96, 32, 16, 1)]:
+    info = m.abi.MfcConvInfo()
+    assert lib.mfc_conv2d_query(C.byref(_desc(m, B, H, W, cin, cout, k)), C.byref(info)) == 0
+    out.append([getattr(info, f) for f, _ in info._fields_])
+print(json.dumps(out))
+"""
+
+
+def test_plans_are_identical_across_processes():
+    """Tilings decide the fp32 summation order: they must be a pure function of the geometry (committed table, else the
+    cost model), not of per-process timing."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MFC_B200_PLAN_ONLY="1")
+    env.pop("MFC_CONV_TUNE", None)
+    outs = [subprocess.run([sys.executable, "-c", _PLAN_PROBE % ROOT], env=env, capture_output=True, text=True, check=True).stdout
+            for _ in range(2)]
+    assert outs[0] == outs[1] and outs[0].startswith("[[")
+
+
+def test_plan_table_roundtrip_and_frozen_plans():
+    """mfc_conv2d_plan_import decides the tiling of a geometry that has no plan yet; a plan that was handed out stays."""
+    import mfcnet_tracker_b200 as m
+    lib = m.abi.load()
+    d = _desc(m, B=5, H=40, W=56, cin=24, cout=24, k=3)        # a geometry nothing else in the suite plans
+    key = "5 40 56 40 56 24 3 3 1 1 1 3 0 0 0 1"
+    assert lib.mfc_conv2d_plan_import(("# comment\n%s : 4 56 0 4 32 4\n" % key).encode()) == 1
+    info = m.abi.MfcConvInfo()
+    assert lib.mfc_conv2d_query(C.byref(d), C.byref(info)) == 0
+    assert (info.tile_h, info.tile_w, info.nb, info.nstages, info.weight_layout) == (4, 56, 32, 4, 0)
+    # frozen: a second import for the same geometry is ignored, the exported table still carries the first choice
+    assert lib.mfc_conv2d_plan_import(("%s : 8 56 0 4 32 2\n" % key).encode()) == 0
+    assert lib.mfc_conv2d_query(C.byref(d), C.byref(info)) == 0 and info.tile_h == 4
+    assert (key + " : 4 56 0 4 32 4") in m.abi.export_table()
+    assert lib.mfc_conv2d_plan_import(b"1 2 3\n") < 0 and b"malformed" in lib.mfc_last_error()
+    # an entry that matches no candidate of the planner falls back to the cost model
+    d2 = _desc(m, B=5, H=40, W=56, cin=24, cout=40, k=3)
+    assert lib.mfc_conv2d_plan_import(b"5 40 56 40 56 40 3 3 1 1 1 3 0 0 0 1 : 999 56 0 4 32 3\n") == 1
+    assert lib.mfc_conv2d_query(C.byref(d2), C.byref(info)) == 0 and info.tile_h != 999
+    # statistics need a padded Cout <= 256: the flag is part of the key and constrains the choice
+    d3 = _desc(m, B=1, H=30, W=40, cin=64, cout=272, k=3, flags=m.abi.MFC_CONV_WANT_STATS)
+    assert lib.mfc_conv2d_query(C.byref(d3), C.byref(info)) != 0 or info.nb * info.nblk <= 256
 
 
 def test_invalid_descriptor_is_rejected_with_message():

@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mfcnet_tracker_b200 as M  # noqa: E402
+from oracle import corr_ref_nvrtc as REF  # noqa: E402  (the reference's own kernels, NVRTC-compiled: the timed baseline)
 
 
 def timeit(fn, iters):
@@ -51,11 +52,22 @@ def main():
         us = timeit(lambda: M.correlation(f1, f2, md, s2), 50)
         us_exact = timeit(lambda: M.correlation(f1, f2, md, s2, exact_order=True), 10)
         us_torch = timeit(lambda: torch_corr(f1, f2, md, s2), 5)
+        us_ref = err_ref = exact_equal = None
+        if REF.available():
+            us_ref = timeit(lambda: REF.forward(f1, f2, md, s2), 5)
+            ref = REF.forward(f1, f2, md, s2)
+            err_ref = float((M.correlation(f1, f2, md, s2) - ref).abs().max())
+            exact_equal = bool(torch.equal(M.correlation(f1, f2, md, s2, exact_order=True), ref))
         err = float((M.correlation(f1, f2, md, s2) - torch_corr(f1, f2, md, s2)).abs().max())
         nbytes = (2 * C + D * D) * H * W * 4 * B
         flops = 2 * D * D * C * H * W * B
         r = {"case": name, "B": B, "C": C, "H": H, "W": W, "max_disp": md, "stride2": s2, "us": round(us, 2),
              "us_exact_order_variant": round(us_exact, 2), "us_torch_ops_same_gpu": round(us_torch, 1), "max_abs_diff_vs_torch": err,
+             "us_reference_kernel": None if us_ref is None else round(us_ref, 1),
+             "reference_kernel": ("models/unflow_correlation.py kernels via NVRTC (2 rearrange + updateOutput launches, incl. its two zero-filled "
+                                  "padded NHWC copies)" + ("" if (md, s2) == (20, 2) else "; literals 20/21/10/2 re-parameterised for this displacement")),
+             "speedup_vs_reference_kernel": None if us_ref is None else round(us_ref / us, 1),
+             "max_abs_diff_vs_reference_kernel": err_ref, "exact_order_bit_equal_to_reference_kernel": exact_equal,
              "algorithmic_GBs": round(nbytes / us * 1e-3, 1), "frac_of_hbm_peak": round(nbytes / us * 1e-3 / peak, 3),
              "TFLOPs_fp32": round(flops / us * 1e-6, 2)}
         print(json.dumps(r), flush=True)
