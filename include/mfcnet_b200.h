@@ -176,6 +176,9 @@ typedef struct MfcConvIO {
   long long y_batch_stride;  /* bytes                                        */
   float* y_nchw;             /* fp32 [B][Cout][Hout][Wout] or NULL           */
   float* stats;              /* [B][stats_per_image][nb*nblk][2] or NULL     */
+  int* overflow;             /* NULL, or a device counter: fp16 range guard.  Every epilogue warp that stored a value
+                                beyond +-65504 into y_c8 (it became +-inf) adds 1.  The caller zeroes and reads it
+                                (mfc_run_list users: one counter for the whole program).                              */
 } MfcConvIO;
 int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream);
 
@@ -211,7 +214,7 @@ int mfc_gn_finalize(const float* stats, int B, int stats_per_image, int cpad, in
 /* out = silu(a*scale+shift) + r   (ResnetBlock tail with identity res_conv,
  * models/resunet.py:90-95).  All C8 [B][chunks][H][W][8]. */
 int mfc_affine_silu_add(const void* a, const float* affine, const void* r, void* out,
-                        int B, int chunks, long long pixels, int dtype, void* stream);
+                        int B, int chunks, long long pixels, int dtype, int* overflow /*or NULL*/, void* stream);
 
 /* nn.MaxPool2d(2, 2) (models/ternausnet.py:56,107) on a C8 tensor [B][chunks][H][W][8] -> [H/2][W/2]. */
 int mfc_maxpool2(const void* src, long long src_bstride_bytes, void* dst, long long dst_bstride_bytes,
@@ -242,6 +245,7 @@ typedef struct MfcFuseArgs {
   const float* shift;
   void* out;
   long long out_batch_stride;
+  int* overflow;            /* fp16 range guard counter or NULL (see MfcConvIO.overflow) */
 } MfcFuseArgs;
 int mfc_fuse_sum(const MfcFuseArgs* a, void* stream);
 
@@ -447,6 +451,7 @@ typedef struct MfcAddArgs {
   long long pixels;
   int B, chunks, dtype;
   int reserved;
+  int* overflow;   /* fp16 range guard counter or NULL (see MfcConvIO.overflow) */
 } MfcAddArgs;
 
 typedef struct MfcGatherArgs {

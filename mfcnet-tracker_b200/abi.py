@@ -46,7 +46,7 @@ class MfcConvDesc(C.Structure):
 class MfcConvIO(C.Structure):
     _fields_ = [("w_packed", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("residual", c_void_p),
                 ("res_affine", c_void_p), ("res_batch_stride", c_ll), ("y_c8", c_void_p), ("y_batch_stride", c_ll),
-                ("y_nchw", c_void_p), ("stats", c_void_p)]
+                ("y_nchw", c_void_p), ("stats", c_void_p), ("overflow", c_void_p)]
 
 
 class MfcWarpArgs(C.Structure):
@@ -65,7 +65,7 @@ class MfcGnArgs(C.Structure):
 
 class MfcAddArgs(C.Structure):
     _fields_ = [("a", c_void_p), ("affine", c_void_p), ("r", c_void_p), ("out", c_void_p), ("pixels", c_ll),
-                ("B", c_int), ("chunks", c_int), ("dtype", c_int), ("reserved", c_int)]
+                ("B", c_int), ("chunks", c_int), ("dtype", c_int), ("reserved", c_int), ("overflow", c_void_p)]
 
 
 class MfcGatherArgs(C.Structure):
@@ -80,7 +80,7 @@ class MfcFuseTerm(C.Structure):
 class MfcFuseArgs(C.Structure):
     _fields_ = [("B", c_int), ("chunks", c_int), ("H", c_int), ("W", c_int), ("nterms", c_int), ("act", c_int),
                 ("dtype", c_int), ("reserved", c_int), ("term", MfcFuseTerm * MFC_MAX_SRC), ("scale", c_void_p),
-                ("shift", c_void_p), ("out", c_void_p), ("out_batch_stride", c_ll)]
+                ("shift", c_void_p), ("out", c_void_p), ("out_batch_stride", c_ll), ("overflow", c_void_p)]
 
 
 class MfcResizeArgs(C.Structure):
@@ -118,7 +118,7 @@ _SIGNATURES = {
     "mfc_conv2d_plan_export": ([C.c_char_p, c_ll], c_ll),
     "mfc_conv2d_plan_import": ([C.c_char_p], c_int),
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
-    "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p], c_int),
+    "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_void_p], c_int),
     "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),
     "mfc_maxpool2": ([c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_fuse_sum": ([C.POINTER(MfcFuseArgs), c_void_p], c_int),

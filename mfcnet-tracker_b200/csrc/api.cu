@@ -269,8 +269,9 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.y_bs = io->y_batch_stride;
   p.y_nchw = io->y_nchw;
   p.stats = io->stats;
+  p.ovf = io->overflow;
   {
-    static const int dbg = getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0;
+    static const int dbg = (getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0) | (mfc::silu_accurate() ? 16 : 0);
     p.debug = dbg;
   }
   if (p.t.tma) {
@@ -547,10 +548,10 @@ int mfc_gn_finalize(const float* stats, int B, int stats_per_image, int cpad, in
 }
 
 int mfc_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks, long long pixels, int dtype,
-                        void* stream) {
+                        int* overflow, void* stream) {
   MFC_REQUIRE_ARCH();
   if (!a || !affine || !r || !out || B < 1 || chunks < 1 || pixels < 1 || !dtype_ok(dtype)) return fail(MFC_EINVAL, "affine_silu_add: bad argument");
-  MFC_LAUNCH(mfc::launch_affine_silu_add(a, affine, r, out, B, chunks, pixels, dtype == MFC_BF16, (cudaStream_t)stream), "affine_silu_add");
+  MFC_LAUNCH(mfc::launch_affine_silu_add(a, affine, r, out, B, chunks, pixels, dtype == MFC_BF16, overflow, (cudaStream_t)stream), "affine_silu_add");
 }
 
 // ---- fusion ------------------------------------------------------------------------------------
@@ -833,7 +834,7 @@ int run_list_impl(const MfcCmd* cmds, int n, void* main_stream, bool use_lanes) 
       }
       case MFC_OP_AFFINE_SILU_ADD: {
         const MfcAddArgs* g = (const MfcAddArgs*)c.a;
-        rc = mfc_affine_silu_add(g->a, g->affine, g->r, g->out, g->B, g->chunks, g->pixels, g->dtype, stream);
+        rc = mfc_affine_silu_add(g->a, g->affine, g->r, g->out, g->B, g->chunks, g->pixels, g->dtype, g->overflow, stream);
         break;
       }
       case MFC_OP_GATHER: {

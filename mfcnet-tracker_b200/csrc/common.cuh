@@ -303,6 +303,22 @@ __device__ __forceinline__ float silu_fast(float y) {
   return 0.5f * y * (1.0f + t);
 }
 
+// silu(y) from h = y/2.  Fast form h + h*tanh.approx(h): one MUFU op, |error| <= 2^-11 |h| (the approximation error of
+// tanh.approx.f32 is as large as the fp16 rounding of the result).  Accurate form y / (1 + 2^(-y log2 e)) with ex2.approx +
+// rcp.approx: two MUFU ops, ~1e-7 relative.
+__device__ __forceinline__ float silu_from_half(float h, bool accurate) {
+  if (accurate) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(h * -2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return (h + h) * r;
+  }
+  return fmaf(h, tanh_fast(h), h);
+}
+
+// |v| beyond the largest finite fp16 value rounds to +-inf in a C8 fp16 tensor
+constexpr float kF16Max = 65504.0f;
+
 // exact unsigned division by a runtime constant d (1 <= d <= 65535) for n < 2^22:
 // q = (n * m) >> 32 with m = floor(2^32/d)+1.
 struct FastDiv {

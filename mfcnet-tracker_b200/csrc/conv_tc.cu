@@ -99,7 +99,7 @@ __device__ __forceinline__ void issue_plane(const ConvParams& p, uint8_t* plane,
 
 // ---- producers: phase 2, in-place GroupNorm-affine + SiLU of the thread's own slots ----------------
 template <bool BF16>
-__device__ __forceinline__ void affine_silu_slot(uint32_t saddr, const float (&sc)[8], const float (&sh)[8]) {
+__device__ __forceinline__ void affine_silu_slot(uint32_t saddr, const float (&sc)[8], const float (&sh)[8], bool accurate) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
   float f[8];
@@ -107,7 +107,7 @@ __device__ __forceinline__ void affine_silu_slot(uint32_t saddr, const float (&s
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float h = fmaf(f[i], sc[i], sh[i]);
-    f[i] = fmaf(h, tanh_fast(h), h);
+    f[i] = silu_from_half(h, accurate);
   }
   v = pack8<BF16>(f);
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -129,6 +129,7 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
   const int s = p.stride;
   const int P = p.t.P;
   const int items = p.t.rows_sub * P;
+  const bool accurate = (p.debug & 16) != 0;
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -166,7 +167,7 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float h = fmaf(f[i], sc[i], sh[i]);
-          f[i] = fmaf(h, tanh_fast(h), h);
+          f[i] = silu_from_half(h, accurate);
         }
         v[u] = pack8<BF16>(f);
       }
@@ -186,7 +187,7 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
       const int c2 = idx - r2 * P;
       const int iy = iy_base + r2 * s + py;
       const int ix = ix_base + c2 * s + px;
-      if (iy >= 0 && iy < Hup && ix >= 0 && ix < Wup) affine_silu_slot<BF16>(smem_u32(sp) + (uint32_t)idx * 16u, sc, sh);
+      if (iy >= 0 && iy < Hup && ix >= 0 && ix < Wup) affine_silu_slot<BF16>(smem_u32(sp) + (uint32_t)idx * 16u, sc, sh, accurate);
     }
   }
 }
@@ -508,7 +509,7 @@ template <bool BF16, int MODE, bool NB16>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem_acc, uint32_t s_scale_addr, float* my_stats,
                                               float (&d1)[16], float (&d2)[16], const float (&sc)[16], const float (&sh)[16], int b,
                                               int oy0, int ox0, int nbk, int lq, int half, int lane, bool res_aff_smem, ResPrefetch& rp,
-                                              int total_items) {
+                                              int total_items, float& omax) {
   constexpr bool kRes = MODE == EPI_RES || MODE == EPI_GENERIC;
   constexpr bool kStats = MODE == EPI_STATS || MODE == EPI_GENERIC;
   constexpr bool kNchw = MODE == EPI_NCHW || MODE == EPI_GENERIC;
@@ -529,6 +530,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   const int ostr = p.out_stride, ooy = p.out_off_y, oox = p.out_off_x;
   const FastDiv divP = p.divP;
   const bool slide = p.t.slide != 0;
+  const bool accurate = (p.debug & 16) != 0;
   auto pixel_of = [&](int rr) -> PixRef {
     const int sl = rr * 128 + lq * 32 + lane;
     int row, col;
@@ -609,15 +611,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
                 for (int i = 0; i < 8; i += 2) {
                   const float4 a = lds_f4(sa + i * 8);
                   const float h0 = fmaf(rf[i], a.x, a.y), h1 = fmaf(rf[i + 1], a.z, a.w);
-                  rf[i] = fmaf(h0, tanh_fast(h0), h0);
-                  rf[i + 1] = fmaf(h1, tanh_fast(h1), h1);
+                  rf[i] = silu_from_half(h0, accurate);
+                  rf[i + 1] = silu_from_half(h1, accurate);
                 }
               } else {
                 const float2* ra = reinterpret_cast<const float2*>(p.res_aff) + ((size_t)b * cc_out + ch) * 8;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   float2 a = __ldg(ra + i);
-                  rf[i] = silu_fast(fmaf(rf[i], a.x, a.y));
+                  rf[i] = silu_from_half(0.5f * fmaf(rf[i], a.x, a.y), accurate);
                 }
               }
             }
@@ -659,6 +661,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
       }
     }
     if (valid) {
+      if (!BF16 && has_c8) {  // fp16 range guard: the largest magnitude this thread stores (checked once, at kernel exit)
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) omax = fmaxf(fmaxf(omax, fabsf(f[i])), fabsf(f[i + 1]));
+      }
       if (has_c8) {
         const uint32_t off0 = (uint32_t)(co0 >> 3) * HWo + pix;  // 16-byte slots from the sample's base: < 2^32
 #pragma unroll
@@ -1078,6 +1084,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     float* my_stats = s_stats + (size_t)warp * cpad * 2;
     const bool has_stats = kStats && p.stats != nullptr;
     float d1[16], d2[16], sc[16], sh[16];
+    float omax = 0.0f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       d1[i] = d2[i] = 0.0f;
@@ -1127,12 +1134,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
       if (!(p.debug & 2))
         epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
-                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem, rp, total_items);
+                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem, rp, total_items, omax);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc_i]);
     }
     if (has_stats && cur_b >= 0) flush_stats(p, s_stats, warp, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
+    // a stored value beyond the fp16 range became +-inf: count it where the host can see it (MfcConvIO.overflow)
+    if (!BF16 && p.ovf != nullptr && __any_sync(0xffffffffu, !(omax <= kF16Max)) && lane == 0) atomicAdd(p.ovf, 1);
   }
 
   // ---- teardown

@@ -83,9 +83,11 @@ struct ConvParams {
   long long y_bs;
   float* y_nchw;
   float* stats;
+  int* ovf;       // fp16 outputs only: incremented by every epilogue warp that stored a value beyond +-65504 (or NULL)
   alignas(64) CUtensorMap tmap[MFC_MAX_SRC];  // t.tma: source i as the 5-D tensor (8 ch, W, H, chunk, sample)
   int reverse, total_items;  // reverse: walk the work items from the last sample to the first (see MFC_CONV_REVERSE_ORDER)
-  int debug;  // measurement only (MFC_CONV_DEBUG): bit0 skip producer copies, bit1 skip epilogue body, bit2 skip MMAs
+  int debug;  // measurement only (MFC_CONV_DEBUG): bit0 skip producer copies, bit1 skip epilogue body, bit2 skip MMAs,
+              // bit3 role timing; bit4 (MFC_SILU_ACCURATE=1): two-MUFU SiLU instead of tanh.approx
 };
 
 // host planner

@@ -23,7 +23,8 @@ cudaError_t launch_bn_fold(const float* g, const float* b, const float* m, const
 cudaError_t launch_gn_finalize(const float* stats, int B, int tiles, int cpad, int C, int groups, long long pixels,
                                const float* gamma, const float* beta, float eps, float* affine, cudaStream_t st);
 cudaError_t launch_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks,
-                                   long long pixels, bool bf16, cudaStream_t st);
+                                   long long pixels, bool bf16, int* ovf, cudaStream_t st);
+bool silu_accurate();  // MFC_SILU_ACCURATE=1: two-MUFU SiLU (ex2 + rcp) instead of tanh.approx in every kernel
 
 // fusion_ops.cu
 cudaError_t launch_flow_warp(const MfcWarpArgs& a, cudaStream_t st);

@@ -1,9 +1,16 @@
 // pointwise.cu -- HBM-bound helpers around the conv kernel: layout conversion, weight/BN folding,
 // GroupNorm finalisation, ResnetBlock tail.  All 128-bit vectorised, one pixel-chunk (16 B) per lane.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/mfcnet_b200.h"
 
 namespace mfc {
+
+bool silu_accurate() {
+  static const bool v = getenv("MFC_SILU_ACCURATE") != nullptr && atoi(getenv("MFC_SILU_ACCURATE")) != 0;
+  return v;
+}
 
 // ---- fp32 NCHW planes -> one C8 plane ---------------------------------------------------------
 template <bool BF16>
@@ -151,9 +158,10 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, int tiles, i
 template <bool BF16>
 __global__ void affine_silu_add_kernel(const uint8_t* __restrict__ a, const float* __restrict__ affine,
                                        const uint8_t* __restrict__ r, uint8_t* __restrict__ out, int B, int chunks,
-                                       long long pixels) {
+                                       long long pixels, bool accurate, int* __restrict__ ovf) {
   pdl_launch_dependents();
   pdl_wait();
+  float omax = 0.0f;
   const long long total = (long long)B * chunks * pixels;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long bc = i / pixels;  // b*chunks + chunk
@@ -164,10 +172,12 @@ __global__ void affine_silu_add_kernel(const uint8_t* __restrict__ a, const floa
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float2 s = __ldg(af + j);
-      fa[j] = silu_fast(fmaf(fa[j], s.x, s.y)) + fr[j];
+      fa[j] = silu_from_half(0.5f * fmaf(fa[j], s.x, s.y), accurate) + fr[j];
+      omax = fmaxf(omax, fabsf(fa[j]));
     }
     *reinterpret_cast<uint4*>(out + i * 16) = pack8<BF16>(fa);
   }
+  if (!BF16 && ovf != nullptr && __any_sync(0xffffffffu, !(omax <= kF16Max)) && (threadIdx.x & 31) == 0) atomicAdd(ovf, 1);
 }
 
 static inline int grid_for(long long n, int threads) {
@@ -203,13 +213,14 @@ cudaError_t launch_gn_finalize(const float* stats, int B, int tiles, int cpad, i
   return launch_pdl(gn_finalize_kernel, dim3(B * groups), dim3(256), 0, st, stats, tiles, cpad, C, groups, pixels, gamma, beta, eps, affine);
 }
 cudaError_t launch_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks, long long pixels,
-                                   bool bf16, cudaStream_t st) {
+                                   bool bf16, int* ovf, cudaStream_t st) {
   const int grid = grid_for((long long)B * chunks * pixels, 256);
+  const bool acc = silu_accurate();
   if (bf16)
     return launch_pdl(affine_silu_add_kernel<true>, dim3(grid), dim3(256), 0, st, (const uint8_t*)a, affine, (const uint8_t*)r,
-                      (uint8_t*)out, B, chunks, pixels);
+                      (uint8_t*)out, B, chunks, pixels, acc, ovf);
   return launch_pdl(affine_silu_add_kernel<false>, dim3(grid), dim3(256), 0, st, (const uint8_t*)a, affine, (const uint8_t*)r,
-                    (uint8_t*)out, B, chunks, pixels);
+                    (uint8_t*)out, B, chunks, pixels, acc, ovf);
 }
 
 }  // namespace mfc

@@ -31,6 +31,7 @@ struct FuseParams {
   const float* shift;
   uint8_t* out;
   long long out_bs;
+  int* ovf;
 };
 
 template <bool BF16>
@@ -39,6 +40,7 @@ __global__ void fuse_sum_kernel(const __grid_constant__ FuseParams p) {
   pdl_wait();
   const long long pixels = (long long)p.H * p.W;
   const long long total = (long long)p.B * p.chunks * pixels;
+  float omax = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i % pixels;
     const long long t = i / pixels;
@@ -85,8 +87,11 @@ __global__ void fuse_sum_kernel(const __grid_constant__ FuseParams p) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.0f);
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) omax = fmaxf(omax, fabsf(acc[e]));
     *reinterpret_cast<uint4*>(p.out + (long long)b * p.out_bs + ((long long)ch * pixels + pix) * 16) = pack8<BF16>(acc);
   }
+  if (!BF16 && p.ovf != nullptr && __any_sync(0xffffffffu, !(omax <= kF16Max)) && (threadIdx.x & 31) == 0) atomicAdd(p.ovf, 1);
 }
 
 template <bool BF16>
@@ -175,7 +180,7 @@ cudaError_t launch_fuse_sum(const MfcFuseArgs& a, cudaStream_t st) {
     p.h[j] = j < a.nterms ? a.term[j].H : 0;
     p.w[j] = j < a.nterms ? a.term[j].W : 0;
   }
-  p.scale = a.scale; p.shift = a.shift; p.out = (uint8_t*)a.out; p.out_bs = a.out_batch_stride;
+  p.scale = a.scale; p.shift = a.shift; p.out = (uint8_t*)a.out; p.out_bs = a.out_batch_stride; p.ovf = a.overflow;
   const int grid = grid_for((long long)a.B * a.chunks * a.H * a.W, 256);
   if (a.dtype == MFC_BF16) return launch_pdl(fuse_sum_kernel<true>, dim3(grid), dim3(256), 0, st, p);
   return launch_pdl(fuse_sum_kernel<false>, dim3(grid), dim3(256), 0, st, p);

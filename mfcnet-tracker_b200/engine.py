@@ -41,6 +41,41 @@ def autotune_reps():
     return max(1, int(os.environ.get("MFC_CONV_TUNE_REPS", "3")))
 
 
+_OVF = {}
+
+
+def overflow_counter(device):
+    """The per-device fp16 range-guard counter every recorded conv / fuse_sum / affine_silu_add points at
+    (MfcConvIO.overflow): a kernel that stores a value beyond +-65504 into an fp16 activation tensor adds to it."""
+    device = canonical_device(device)
+    if device.type != "cuda" or abi.plan_only():
+        return None
+    if device not in _OVF:
+        _OVF[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _OVF[device]
+
+
+def check_overflow(device="cuda"):
+    """Synchronises and raises FloatingPointError if any fp16 activation overflowed on `device` since the last check.
+    Every program checks itself after its first run; MFC_B200_CHECK_OVERFLOW=1 checks after every run (one sync per
+    forward), and streaming / long-running callers can call this at their own cadence."""
+    c = overflow_counter(device)
+    if c is None:
+        return 0
+    n = int(c.item())
+    if n:
+        c.zero_()
+        raise FloatingPointError(
+            "mfcnet_tracker_b200: %d epilogue warp(s) stored activations beyond the fp16 range (+-65504 -> inf) on %s; "
+            "the result is invalid.  Use bf16 storage (MFC_B200_DTYPE=bf16 / model.dtype_name = 'bf16') for this checkpoint."
+            % (n, canonical_device(device)))
+    return 0
+
+
+def _check_every_run():
+    return os.environ.get("MFC_B200_CHECK_OVERFLOW", "0") == "1"
+
+
 def require_cuda(t, what):
     if not t.is_cuda and not abi.plan_only():
         raise RuntimeError("%s: mfcnet_tracker_b200 runs on a B200 only; got a %s tensor (there is no CPU fallback)"
@@ -160,6 +195,8 @@ class Program:
         self.bindings = {}   # external input key -> [setter(tensor)]
         self.meta = []       # per command: {'kind', 'name', 'bytes', 'flops'} (algorithmic, for the roofline)
         self.packer = None   # WeightPacker whose device writes must have completed before the first run (Builder sets it)
+        self._ovf = overflow_counter(self.device) if dtype_name == "fp16" else None
+        self._checked = False
 
     # ---- low-level recording -----------------------------------------------------------------
     def _push(self, op, a, b=None, launches=1, meta=None):
@@ -201,6 +238,9 @@ class Program:
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
         abi.check(self.lib.mfc_run_list(self._array, len(self.cmds), stream))
+        if self._ovf is not None and (not self._checked or _check_every_run()):
+            self._checked = True
+            check_overflow(self.device)
 
     def capture(self):
         """Capture this program into a CUDA graph (all of its pointers must be static from now on)."""
@@ -224,6 +264,7 @@ class Program:
 
     def extend(self, other):
         self.packer = self.packer or other.packer
+        self._ovf = self._ovf if self._ovf is not None else other._ovf
         self.cmds += other.cmds
         self.meta += other.meta
         self.keep += other.keep
@@ -320,6 +361,7 @@ class Program:
             io.res_affine = abi.ptr(residual.affine)
             io.res_batch_stride = residual.bstride
             self.keep += [residual.t, residual.affine]
+        io.overflow = abi.ptr(self._ovf)
         out = None
         B, Cout = d.B, d.Cout
         os_ = 2 if d.out_stride == 2 else 1
@@ -376,6 +418,7 @@ class Program:
         a = abi.MfcAddArgs()
         a.a, a.affine, a.r, a.out = a_act.t.data_ptr(), a_act.affine.data_ptr(), r_act.t.data_ptr(), out_t.data_ptr()
         a.pixels, a.B, a.chunks, a.dtype = a_act.H * a_act.W, a_act.B, a_act.chunks, self.cdtype
+        a.overflow = abi.ptr(self._ovf)
         for t in (a_act.t, r_act.t, out_t):
             if not t.is_contiguous():
                 raise ValueError("affine_silu_add needs dense C8 tensors")
@@ -399,6 +442,7 @@ class Program:
             nbytes += B * C_ * t.H * t.W * 2
         a.scale, a.shift = abi.ptr(scale), abi.ptr(shift)
         a.out, a.out_batch_stride = out_t.data_ptr(), out_t.stride(0) * out_t.element_size()
+        a.overflow = abi.ptr(self._ovf)
         self.keep += [out_t, scale, shift]
         self._push(abi.OP_FUSE_SUM, a, meta={"kind": "fuse_sum", "name": "", "flops": 0, "bytes": nbytes})
         return Act(out_t, C_)

@@ -30,7 +30,10 @@ from .ternausnet import TernausNet16
 def _sub_batch(n_frames, H, W):
     env = os.environ.get("MFC_B200_SUBBATCH")
     if env:
-        return max(1, min(n_frames, int(env)))
+        sb = max(1, min(n_frames, int(env)))
+        while n_frames % sb:      # sub-batches replay one arena: they must all have the same size
+            sb -= 1
+        return sb
     # pixels per SFC pass.  Measured on B200 (ResUNet-16, 24 frames of 480x640): sub-batches of 4 / 8 / 12 / 24
     # frames give 910 / 1080 / 1227 / 1331 frames/s -- amortising the ~61 launches of a pass over more frames
     # beats keeping the 39 MB (4-frame) layer outputs L2-resident, so the cap is only a memory bound.

@@ -31,37 +31,51 @@ def shard_frames(n_frames, world, rank, num_input_frames):
     return {"lo": lo, "hi": hi, "enc_lo": max(0, lo - (K - 1)), "n_out": hi - lo}
 
 
+def shard_clips(n_frames, world, rank, num_input_frames, clips_per_rank):
+    """The `clips_per_rank` contiguous sub-clips of `rank`'s share of the video (each with its own K-1-frame halo), for
+    StreamingMFCNet(batch=clips_per_rank): the clips of one GPU advance in lock step, one frame each per step, which turns the
+    batch-1 sliding window (launch / latency bound on a B200) into a batch of B.  Equivalent to shard_frames over
+    world * clips_per_rank virtual ranks; trailing clips may be shorter (or empty) and idle while the others finish."""
+    return [shard_frames(n_frames, world * clips_per_rank, rank * clips_per_rank + j, num_input_frames) for j in range(clips_per_rank)]
+
+
 class StreamingMFCNet:
     """Feeds frames one at a time through a `ResUNetMulti*`-style wrapper with SFC feature reuse.
 
-    step(frame, flows, depths) takes the newest frame (1,3,H,W), the K-1 flows of the current window
+    step(frame, flows, depths) takes the newest frame (B,3,H,W), the K-1 flows of the current window
     (flows[i-1]: current frame -> frame i earlier, as in the reference loop :264-271) and the K depth
-    maps in window order; returns fp32 logits (1,N,H,W) once K frames have been seen, else None.
+    maps in window order; returns fp32 logits (B,N,H,W) once K frames have been seen, else None.
+
+    `batch` = B independent clips advancing in lock step (e.g. the B clips one GPU owns when a long video is
+    sharded, or B cameras): ONE SFC pass over the B new frames and ONE fusion pass over the B windows per step, the
+    ring holding K x B class-map slots.  Per output frame that is 1 SFC + 1 fusion pass (67.7 GFLOP for ResUNet-16 /
+    K=3) instead of the K SFC passes the reference spends, at a batch size that fills the GPU.
     """
 
-    def __init__(self, model, H, W, device="cuda", dtype_name=None):
+    def __init__(self, model, H, W, device="cuda", dtype_name=None, batch=1):
         self.model = model
         self.K, self.N = model.num_frames, model.num_classes
         self.H, self.W = H, W
+        self.B = int(batch)
         self.device = engine.canonical_device(device)
         self.dt = dtype_name or model.dtype_name or engine.default_dtype()
         self.t = 0
         self._build()
 
     def _build(self):
-        m, K, N, H, W, dev = self.model, self.K, self.N, self.H, self.W, self.device
+        m, K, N, H, W, dev, B = self.model, self.K, self.N, self.H, self.W, self.device, self.B
         packer = engine.WeightPacker(dev, self.dt)
         self._fingerprint = engine.params_fingerprint(m)
         tdtype = engine._DTYPES[self.dt][0]
         cin = m.base_model.channels
-        self.ring = torch.zeros((K, (N + 7) // 8, H, W, 8), dtype=tdtype, device=dev)   # slot s holds frame t with t % K == s
-        self.x_c8 = torch.empty((1, (cin + 7) // 8, H, W, 8), dtype=tdtype, device=dev)
-        self.out = torch.empty((1, N, H, W), dtype=torch.float32, device=dev)
+        self.ring = torch.zeros((K, B, (N + 7) // 8, H, W, 8), dtype=tdtype, device=dev)   # slot s holds frame t with t % K == s
+        self.x_c8 = torch.empty((B, (cin + 7) // 8, H, W, 8), dtype=tdtype, device=dev)
+        self.out = torch.empty((B, N, H, W), dtype=torch.float32, device=dev)
         # static fp32 input buffers: every program reads these (the caller's tensors are copied in per step), so that all
         # pointers of a step are fixed and the step can be replayed as one CUDA graph
-        self.in_frame = torch.zeros((1, cin, H, W), dtype=torch.float32, device=dev)
-        self.in_flow = [torch.zeros((1, 2, H, W), dtype=torch.float32, device=dev) for _ in range(K - 1)] if m.optflow_inputs else None
-        self.in_depth = [torch.zeros((1, 1, H, W), dtype=torch.float32, device=dev) for _ in range(K)] if m.depth_inputs else None
+        self.in_frame = torch.zeros((B, cin, H, W), dtype=torch.float32, device=dev)
+        self.in_flow = [torch.zeros((B, 2, H, W), dtype=torch.float32, device=dev) for _ in range(K - 1)] if m.optflow_inputs else None
+        self.in_depth = [torch.zeros((B, 1, H, W), dtype=torch.float32, device=dev) for _ in range(K)] if m.depth_inputs else None
         arena_sfc, arena_fus = engine.Arena(dev), engine.Arena(dev)
         self.sfc, self.fus = [], []
         for s in range(K):
@@ -69,14 +83,14 @@ class StreamingMFCNet:
             b = engine.Builder(dev, self.dt, packer, arena_sfc)
             ext = Ext("frame", self.in_frame)
             for c0 in range(0, cin, 8):
-                b.prog.gather([(ext, c) for c in range(c0, min(c0 + 8, cin))], self.x_c8[:, c0 // 8], 1, H, W)
-            m.base_model.record(b, Act(self.x_c8, cin), maps_c8=self.ring[s:s + 1])
+                b.prog.gather([(ext, c) for c in range(c0, min(c0 + 8, cin))], self.x_c8[:, c0 // 8], B, H, W)
+            m.base_model.record(b, Act(self.x_c8, cin), maps_c8=self.ring[s])
             b.prog.finalize()
             self.sfc.append(b.prog)
         for s in range(K):  # s = slot of the current frame; frame i earlier lives in slot (s - i) % K
             arena_fus.reset()
             b = engine.Builder(dev, self.dt, packer, arena_fus)
-            maps = [Act(self.ring[(s - i) % K:(s - i) % K + 1], N) for i in range(K)]
+            maps = [Act(self.ring[(s - i) % K], N) for i in range(K)]
             flows = [Ext(("flow", i), self.in_flow[i]) for i in range(K - 1)] if m.optflow_inputs else None
             depths = [Ext(("depth", i), self.in_depth[i]) for i in range(K)] if m.depth_inputs else None
             m.multiframe_net.record(b, maps, flows, depths, self.out)
@@ -97,10 +111,15 @@ class StreamingMFCNet:
     def _load(self, dst, src):
         dst.copy_(src, non_blocking=True)   # fp32 cast + layout fix-up + staging in one copy on the current stream
 
-    def encode(self, frame):
-        """Run the SFC network on one frame into its ring slot (used alone for the shard halo)."""
+    def _rebuild_if_stale(self):
+        """New weights invalidate the plans AND the ring contents: the window is refilled before the next output."""
         if engine.params_fingerprint(self.model) != self._fingerprint:
             self._build()
+            self.t = 0
+
+    def encode(self, frame):
+        """Run the SFC network on one frame into its ring slot (used alone for the shard halo)."""
+        self._rebuild_if_stale()
         s = self.t % self.K
         with engine.device_guard(self.device):
             self._load(self.in_frame, frame)
@@ -109,11 +128,10 @@ class StreamingMFCNet:
         return s
 
     def step(self, frame, flows=None, depths=None, out=None):
+        self._rebuild_if_stale()
         if self.t < self.K - 1:
             self.encode(frame)
             return None
-        if engine.params_fingerprint(self.model) != self._fingerprint:
-            self._build()
         s = self.t % self.K
         with engine.device_guard(self.device):
             self._load(self.in_frame, frame)

@@ -130,6 +130,41 @@ def frames(tag, B, H, W, seed=0):
     return normal("frame/" + tag, (B, 3, H, W), seed)
 
 
+def smooth(name, shape, seed=0, cell=32, std=1.0, noise=0.02):
+    """Spatially coherent field: a coarse N(0,1) grid (one value per `cell` pixels) bilinearly interpolated -- weights are
+    multiples of 1/cell, all arithmetic exactly rounded float64 -- plus `noise` * N(0,1) per pixel.  Real video frames are
+    dominated by low spatial frequencies; white-noise frames are the worst case for argmax agreement (every pixel is a
+    potential near-tie), these are the realistic one."""
+    *lead, H, W = shape
+    gh, gw = H // cell + 2, W // cell + 2
+    coarse = normal(name + "/coarse", tuple(lead) + (gh, gw), seed).astype(np.float64)
+    ys, xs = np.arange(H), np.arange(W)
+    y0, x0 = ys // cell, xs // cell
+    fy = ((ys % cell).astype(np.float64) / cell)[:, None]
+    fx = ((xs % cell).astype(np.float64) / cell)[None, :]
+    c00 = coarse[..., y0[:, None], x0[None, :]]
+    c01 = coarse[..., y0[:, None], x0[None, :] + 1]
+    c10 = coarse[..., y0[:, None] + 1, x0[None, :]]
+    c11 = coarse[..., y0[:, None] + 1, x0[None, :] + 1]
+    f = (1 - fy) * ((1 - fx) * c00 + fx * c01) + fy * ((1 - fx) * c10 + fx * c11)
+    f = std * (1.5 * f) + noise * normal(name + "/noise", shape, seed).astype(np.float64)
+    return f.astype(np.float32)
+
+
+def smooth_frames(tag, B, H, W, seed=0):
+    """Realistic-margin variant of `frames`: same scale, low-frequency content."""
+    return smooth("sframe/" + tag, (B, 3, H, W), seed)
+
+
+def smooth_flow(tag, B, H, W, seed=0, scale=4.0):
+    return smooth("sflow/" + tag, (B, 2, H, W), seed, cell=64, std=scale, noise=0.05)
+
+
+def smooth_depth(tag, B, H, W, seed=0):
+    d = 0.5 + 0.25 * smooth("sdepth/" + tag, (B, 1, H, W), seed, cell=64, noise=0.01)
+    return np.clip(d, 0.0, 1.0).astype(np.float32)
+
+
 def depth(tag, B, H, W, seed=0):
     return uniform("depth/" + tag, (B, 1, H, W), seed)
 

@@ -18,11 +18,11 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 2e-2
 ARGMAX_AGREE = 0.999        # north_star bound, asserted on the full-size (480x640) case
-# The 48x64 / 64x96 golden cases use random-init weights whose class margins are often below the
-# logit tolerance itself; a handful of such near-tie pixels flips with ANY change of fp32 summation
-# order.  There we require (a) >= 99.7 % overall and (b) 100 % agreement on every pixel whose
-# reference top-2 margin exceeds twice the measured logit error (those cannot legitimately flip).
-ARGMAX_AGREE_SMALL = 0.997
+# The 48x64 / 64x96 golden cases (3 072 / 6 144 pixels, random-init weights, white-noise frames: every pixel a potential
+# near-tie) are held to the same 99.9 % -- at most 3 / 6 flipped pixels -- AND to 100 % agreement on every pixel whose
+# reference top-2 margin exceeds twice the measured logit error (those cannot legitimately flip).  Tilings are a pure
+# function of the geometry (committed tuning table), so these numbers are reproducible bit for bit.
+ARGMAX_AGREE_SMALL = 0.999
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
 
 
@@ -205,6 +205,184 @@ def test_mfcnet_full_size_vs_oracle_on_gpu(M):
         assert torch.equal(y, y2)
 
 
+def _tf32_off():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _hrnet_head_rule(sd):
+    """Random-init HRNet logits are O(1e3); the fixtures scale the head by 1e-3 so that the absolute 2e-2 bound means
+    what it says (oracle/make_golden.py::_load_sd)."""
+    for k in list(sd):
+        if k.endswith("last_layer.3.weight") or k.endswith("last_layer.3.bias"):
+            sd[k] = sd[k] * 1e-3
+    return sd
+
+
+@pytest.mark.parametrize("variant", ["large", "basic"])
+def test_benchmarked_plan_parity_b8_480x640(M, variant):
+    """The EXACT plan bench.py times (BASELINE configs[1]): batch 8 windows of 3 frames at 480x640 -- 24-frame SFC
+    sub-batch, snake order, B >= 2 tilings -- against the fp32 torch oracle on the same GPU.  Gate = north_star:
+    max-abs logit error <= 2e-2, argmax agreement >= 99.9 %."""
+    _tf32_off()
+    N, K, B, H, W = 5, 3, 8, 480, 640
+    cls = M.ResUNetMultiLarge if variant == "large" else M.ResUNetMultiBasic
+    net = cls(N, K, optflow_inputs=True, depth_inputs=True)
+    man = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in net.state_dict().items()]
+    sd = G.state_dict(man, 0)          # bench.py's weights (seed 0)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(1234)      # bench.py's rank-0 inputs
+    xs = [torch.randn(B, 3, H, W, device="cuda", generator=g) for _ in range(K)]
+    fl = [4.0 * torch.randn(B, 2, H, W, device="cuda", generator=g) for _ in range(K - 1)]
+    dp = [torch.rand(B, 1, H, W, device="cuda", generator=g) for _ in range(K)]
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        y = net(xs, optflow=fl, depth=dp)
+        assert net._plans[(B, H, W)]["sub_batch"] == 24
+        ref = torch.cat([TO.mfcnet_forward(sdg, [x[b:b + 1] for x in xs], [f[b:b + 1] for f in fl], [d[b:b + 1] for d in dp],
+                                           base=TO.resunet_forward, variant=variant, N=N) for b in range(B)])
+    err, agree = _cmp("mfcnet/bench_b8_%s_480x640" % variant, y, ref.cpu().numpy(), "fp16")
+    assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE, (err, agree)
+
+
+def test_realistic_margin_variants_480x640(M):
+    """SURVEY section 8d's argmax-agreement variants.  White-noise frames through a random-init network make EVERY pixel a
+    potential near-tie; two variants with realistic class margins are checked besides: (a) spatially coherent frames
+    (synth.smooth_*: what a video looks like), where ties only occur on region boundaries -- gate 99.99 %; (b) the last
+    layer scaled x10 (logits, and therefore the absolute error bound, scale with it)."""
+    _tf32_off()
+    N, K, B, H, W = 5, 3, 1, 480, 640
+    net = M.ResUNetMultiLarge(N, K, optflow_inputs=True, depth_inputs=True)
+    man = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in net.state_dict().items()]
+    sd = G.state_dict(man, 21)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    xs = [torch.from_numpy(synth.smooth_frames(f"rm/{i}", B, H, W, 21)).cuda() for i in range(K)]
+    fl = [torch.from_numpy(synth.smooth_flow(f"rm/{i}", B, H, W, 21)).cuda() for i in range(K - 1)]
+    dp = [torch.from_numpy(synth.smooth_depth(f"rm/{i}", B, H, W, 21)).cuda() for i in range(K)]
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = TO.mfcnet_forward(sdg, xs, fl, dp, base=TO.resunet_forward, variant="large", N=N)
+        y = net(xs, optflow=fl, depth=dp)
+    err, agree = _cmp("mfcnet/realistic_smooth_480x640", y, ref.cpu().numpy(), "fp16")
+    assert err <= LOGIT_TOL and agree >= 0.9999, (err, agree)
+    # (b) x10 head on the white-noise inputs of the full-size test
+    sd10 = dict(sd)
+    sd10["multiframe_net.multiframe_net.9.weight"] = sd["multiframe_net.multiframe_net.9.weight"] * 10.0
+    net.load_state_dict(sd10)
+    xs = [torch.from_numpy(synth.frames(f"full/{i}", B, H, W, 11)).cuda() for i in range(K)]
+    fl = [torch.from_numpy(synth.flow(f"full/{i}", B, H, W, 11)).cuda() for i in range(K - 1)]
+    dp = [torch.from_numpy(synth.depth(f"full/{i}", B, H, W, 11)).cuda() for i in range(K)]
+    with torch.no_grad():
+        ref = TO.mfcnet_forward({k: v.cuda() for k, v in sd10.items()}, xs, fl, dp, base=TO.resunet_forward, variant="large", N=N)
+        y = net(xs, optflow=fl, depth=dp)
+    err, agree = _cmp("mfcnet/head_x10_480x640", y, ref.cpu().numpy(), "fp16")
+    assert err <= 10 * LOGIT_TOL and agree >= ARGMAX_AGREE, (err, agree)
+
+
+def test_config4_hrnet_k5_full_size(M):
+    """BASELINE config 4's model: HRNet-W48 MFCNet, 5-frame window, flow + depth, 480x640 (B=1), vs the fp32 oracle."""
+    _tf32_off()
+    N, K, B, H, W = 5, 5, 1, 480, 640
+    net = M.HRNetMultiLarge(N, K, pretrained=False, optflow_inputs=True, depth_inputs=True)
+    man = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in net.state_dict().items()]
+    sd = _hrnet_head_rule(G.state_dict(man, 5))
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    xs = [torch.from_numpy(synth.frames(f"c4/{i}", B, H, W, 5)).cuda() for i in range(K)]
+    fl = [torch.from_numpy(synth.flow(f"c4/{i}", B, H, W, 5)).cuda() for i in range(K - 1)]
+    dp = [torch.from_numpy(synth.depth(f"c4/{i}", B, H, W, 5)).cuda() for i in range(K)]
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = TO.mfcnet_forward(sdg, xs, fl, dp, base=TO.hrnet_forward, variant="large", N=N)
+        y = net(xs, optflow=fl, depth=dp)
+    err, agree = _cmp("mfcnet/hrnet_k5_480x640", y, ref.cpu().numpy(), "fp16")
+    assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE, (err, agree)
+
+
+@pytest.mark.parametrize("name", ["HRNetMultiBasic", "TernausNetMultiLarge", "ResUNetMultiLarge_k5", "ResUNetMultiBasic_k5"])
+def test_remaining_wrappers_vs_oracle(M, name):
+    """Wrapper / K combinations without a committed golden, at 64x96 against the fp32 oracle (itself pinned by the goldens of
+    the other wrappers that share its code)."""
+    _tf32_off()
+    N, B, H, W = 5, 2, 64, 96
+    K = 5 if name.endswith("_k5") else 3
+    cls = getattr(M, name.split("_")[0])
+    net = cls(N, K, pretrained=False, loadpath=None, optflow_inputs=True, depth_inputs=True)
+    man = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in net.state_dict().items()]
+    rules = None
+    base, head, variant = TO.resunet_forward, "logits", ("basic" if "Basic" in name else "large")
+    if name.startswith("HRNet"):
+        base = TO.hrnet_forward
+    if name.startswith("Ternaus"):
+        base, head, rules = TO.ternaus_probs, "probs", {"__all_4d__": 2 ** 0.5, "__alias__": "ternaus"}
+    sd = G.state_dict(man, 9, scale_keys=rules)
+    if name.startswith("HRNet"):
+        sd = _hrnet_head_rule(sd)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    xs = [torch.from_numpy(synth.frames(f"rw/{i}", B, H, W, 9)).cuda() for i in range(K)]
+    fl = [torch.from_numpy(synth.flow(f"rw/{i}", B, H, W, 9)).cuda() for i in range(K - 1)]
+    dp = [torch.from_numpy(synth.depth(f"rw/{i}", B, H, W, 9)).cuda() for i in range(K)]
+    with torch.no_grad():
+        ref = TO.mfcnet_forward({k: v.cuda() for k, v in sd.items()}, xs, fl, dp, base=base, variant=variant, N=N, head=head)
+        y = net(xs, optflow=fl, depth=dp)
+    err, agree = _cmp("mfcnet/%s_64x96" % name, y, ref.cpu().numpy(), "fp16")
+    assert err <= LOGIT_TOL and agree >= ARGMAX_AGREE_SMALL, (err, agree)
+
+
+_HASH_PROBE = """
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+import mfcnet_tracker_b200 as M
+from oracle import synth
+from tests import golden_util as G
+N, K, B, H, W = 5, 3, 2, 96, 128
+net = M.ResUNetMultiLarge(N, K, optflow_inputs=True, depth_inputs=True)
+man = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in net.state_dict().items()]
+net.load_state_dict(G.state_dict(man, 4))
+net = net.cuda().eval()
+xs = [torch.from_numpy(synth.frames(f"hp/{i}", B, H, W, 4)).cuda() for i in range(K)]
+fl = [torch.from_numpy(synth.flow(f"hp/{i}", B, H, W, 4)).cuda() for i in range(K - 1)]
+dp = [torch.from_numpy(synth.depth(f"hp/{i}", B, H, W, 4)).cuda() for i in range(K)]
+with torch.no_grad():
+    y = net(xs, optflow=fl, depth=dp)
+print(hashlib.sha256(y.cpu().numpy().tobytes()).hexdigest())
+"""
+
+
+def test_two_processes_compute_identical_bits():
+    """Tilings (hence fp32 summation order) come from the committed table / the cost model, never from per-process timing:
+    two fresh processes must produce the same bits."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k != "MFC_CONV_TUNE"}
+    outs = [subprocess.run([sys.executable, "-c", _HASH_PROBE % root], env=env, capture_output=True, text=True, timeout=600)
+            for _ in range(2)]
+    for r in outs:
+        assert r.returncode == 0, r.stderr[-2000:]
+    assert outs[0].stdout.strip() == outs[1].stdout.strip() and len(outs[0].stdout.strip()) == 64
+
+
+def test_fp16_overflow_is_reported(M):
+    """fp16 storage saturates at 65504: a checkpoint whose activations leave that range must fail loudly, not silently
+    (the conv epilogue counts stores beyond the range; the first run of every plan checks the counter)."""
+    net = M.ResUnet_VB(channels=3, dim=8, out_dim=5).cuda().eval()
+    x = torch.randn(1, 3, 32, 48, device="cuda")
+    with torch.no_grad():
+        y = net(x)                                  # healthy weights: no error
+        assert torch.isfinite(y).all()
+        net.init_conv.weight.mul_(3.0e5)            # stem output ~ 1e5 .. 1e6 > 65504
+        with pytest.raises(FloatingPointError):
+            net(x)
+        M.engine.check_overflow("cuda")             # the counter was reset by the failed check
+        net.dtype_name = "bf16"                     # the documented way out: bf16 storage has fp32's range
+        y = net(x)
+        assert torch.isfinite(y).all()
+
+
 def test_no_cpu_fallback(M):
     net = M.ResUnet_VB(channels=3, dim=8, out_dim=5).eval()
     with pytest.raises(RuntimeError):
@@ -233,11 +411,12 @@ def test_streaming_runner_matches_window_forward(M, family):
         with torch.no_grad():
             net.base_model.last_layer[3].weight.mul_(1e-3)
             net.base_model.last_layer[3].bias.mul_(1e-3)
-    run = M.StreamingMFCNet(net, H, W)
+    Bc = 1 if family == "hrnet" else 3      # the ResUNet case runs three clips in lock step (StreamingMFCNet(batch=3))
+    run = M.StreamingMFCNet(net, H, W, batch=Bc)
     T = 3 * K + 2             # long enough to replay every ring slot's graph at least once
-    frames = [torch.randn(1, 3, H, W, device="cuda") for _ in range(T)]
-    flows = [[2 * torch.randn(1, 2, H, W, device="cuda") for _ in range(K - 1)] for _ in range(T)]
-    depths = [[torch.rand(1, 1, H, W, device="cuda") for _ in range(K)] for _ in range(T)]
+    frames = [torch.randn(Bc, 3, H, W, device="cuda") for _ in range(T)]
+    flows = [[2 * torch.randn(Bc, 2, H, W, device="cuda") for _ in range(K - 1)] for _ in range(T)]
+    depths = [[torch.rand(Bc, 1, H, W, device="cuda") for _ in range(K)] for _ in range(T)]
     worst = 0.0
     with torch.no_grad():
         for t in range(T):

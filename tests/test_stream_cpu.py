@@ -21,6 +21,19 @@ def test_shard_frames_cover_every_output_once():
         assert seen == list(range(K - 1, F)) if F >= K else seen == []
 
 
+def test_shard_clips_cover_every_output_once():
+    from mfcnet_tracker_b200.stream import shard_clips
+    for F, world, K, B in [(9000, 8, 5, 4), (9000, 1, 5, 8), (50, 2, 3, 4), (9, 2, 5, 4)]:
+        seen = []
+        for r in range(world):
+            clips = shard_clips(F, world, r, K, B)
+            assert len(clips) == B
+            for c in clips:
+                assert c["enc_lo"] == max(0, c["lo"] - (K - 1))
+                seen += list(range(c["lo"], c["hi"]))
+        assert seen == list(range(K - 1, F))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -82,5 +95,10 @@ def test_streaming_runner_plans(monkeypatch):
             outs = [run.step(torch.zeros(1, 3, 64, 96), fl, dp) for _ in range(5)]
             assert outs[0] is None and outs[1] is None and all(o.shape == (1, 5, 64, 96) for o in outs[2:])
             assert run.launches_per_frame == 61 + 5   # 1 gather + 60 SFC launches, aux gather/warp + 4 fusion convs
+            # B clips in lock step: same launches, batch-B buffers
+            run4 = StreamingMFCNet(net, 64, 96, device="cpu", batch=4)
+            fl4, dp4 = [torch.zeros(4, 2, 64, 96)] * 2, [torch.zeros(4, 1, 64, 96)] * 3
+            outs = [run4.step(torch.zeros(4, 3, 64, 96), fl4, dp4) for _ in range(4)]
+            assert outs[1] is None and outs[2].shape == (4, 5, 64, 96) and run4.launches_per_frame == 61 + 5
     finally:
         m.abi._lib = None
