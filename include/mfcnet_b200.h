@@ -150,9 +150,11 @@ int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info);
 
 /* OIHW fp32 (device) -> the packed tcgen05 B-operand image.
  * chan_map[k] (device int32, length cin_chunks*8, or NULL = identity) gives, for padded
- * input channel k of the concat (8 per plane), the index into the weight's Cin axis or -1. */
+ * input channel k of the concat (8 per plane), the index into the weight's Cin axis or -1.
+ * scale[Cout] (device fp32 or NULL): per-output-channel factor multiplied into the weights before they are rounded
+ * (a folded BatchNorm scale; mfc_conv2d_fwd is then called with io->scale = NULL). */
 int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w, const int* chan_map,
-                            void* packed, void* stream);
+                            const float* scale, void* packed, void* stream);
 
 /* Fused convolution.  Replaces every nn.Conv2d / WeightStandardizedConv2d +
  * following BatchNorm/ReLU, the torch.cat skip-concats (models/resunet.py:168,174), the
@@ -198,6 +200,8 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream);
  * dependent launch): they must be complete -- the producing work synchronised -- before a conv that uses them is launched. */
 int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* w_oihw, int Cin_w, const int* chan_map,
                         void* scratch_packed, long long scratch_bytes, int reps, void* stream);
+/* Packed-weight scratch bytes that cover every candidate mfc_conv2d_autotune measures for `d` (does not plan `d`). */
+long long mfc_conv2d_autotune_scratch_bytes(const MfcConvDesc* d);
 /* Tuning table as text, one geometry per line ("<16 key ints> : TH TW slide CBc NB nstages", '#' = comment).
  * export returns the bytes needed including the terminating 0 and writes at most `cap`; import returns the number of
  * entries taken (geometries that already have a plan keep it) or a negative error code. */

@@ -112,9 +112,10 @@ _SIGNATURES = {
     "mfc_weight_standardize": ([c_void_p, c_void_p, c_int, c_int, c_float, c_void_p], c_int),
     "mfc_bn_fold": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p], c_int),
     "mfc_conv2d_query": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvInfo)], c_int),
-    "mfc_conv2d_pack_weights": ([C.POINTER(MfcConvDesc), c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
+    "mfc_conv2d_pack_weights": ([C.POINTER(MfcConvDesc), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "mfc_conv2d_fwd": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p], c_int),
     "mfc_conv2d_autotune": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p], c_int),
+    "mfc_conv2d_autotune_scratch_bytes": ([C.POINTER(MfcConvDesc)], c_ll),
     "mfc_conv2d_plan_export": ([C.c_char_p, c_ll], c_ll),
     "mfc_conv2d_plan_import": ([C.c_char_p], c_int),
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),

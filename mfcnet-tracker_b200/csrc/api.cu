@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <mutex>
@@ -270,6 +271,12 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.y_nchw = io->y_nchw;
   p.stats = io->stats;
   p.ovf = io->overflow;
+  p.acc_init = (p.t.slide && io->scale == nullptr && io->shift != nullptr) ? 1 : 0;
+  {
+    static const int no_fast = getenv("MFC_CONV_EPI_FAST") ? (atoi(getenv("MFC_CONV_EPI_FAST")) == 0) : 0;  // measurement switch
+    const bool affine_rows = p.t.slide || (p.t.P == p.t.TW && p.t.TW == d->Wout && p.t.tiles_x == 1);
+    p.epi_fast = (!no_fast && p.t.NB == 16 && p.t.nblk == 1 && p.out_stride == 1 && p.t.kacc == 1 && affine_rows) ? 1 : 0;
+  }
   {
     static const int dbg = (getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0) | (mfc::silu_accurate() ? 16 : 0);
     p.debug = dbg;
@@ -354,7 +361,8 @@ int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info) {
   return MFC_OK;
 }
 
-int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w, const int* chan_map, void* packed, void* stream) {
+int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w, const int* chan_map, const float* scale, void* packed,
+                            void* stream) {
   MFC_REQUIRE_ARCH();
   int rc = validate_desc(d);
   if (rc != MFC_OK) return rc;
@@ -363,7 +371,7 @@ int mfc_conv2d_pack_weights(const MfcConvDesc* d, const float* w_oihw, int Cin_w
   rc = get_tiling(d, &t);
   if (rc != MFC_OK) return rc;
   MFC_LAUNCH(mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,
-                                      t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, packed,
+                                      t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, scale, packed,
                                       d->dtype == MFC_BF16, (cudaStream_t)stream),
              "conv_pack");
 }
@@ -376,6 +384,17 @@ int mfc_conv2d_fwd(const MfcConvDesc* d, const MfcConvIO* io, void* stream) {
   rc = get_tiling(d, &t);
   if (rc != MFC_OK) return rc;
   return conv_fwd_tiled(d, io, t, stream);
+}
+
+/* Bytes of packed-weight scratch that cover every candidate mfc_conv2d_autotune would measure for `d` (0 on a bad
+ * descriptor).  Does not plan the geometry (mfc_conv2d_query would freeze its plan). */
+long long mfc_conv2d_autotune_scratch_bytes(const MfcConvDesc* d) {
+  if (validate_desc(d) != MFC_OK) return 0;
+  std::vector<mfc::ConvTiling> cands;
+  mfc::conv_shortlist(*d, getenv("MFC_CONV_TUNE_WIDTH") ? atoi(getenv("MFC_CONV_TUNE_WIDTH")) : 3, cands);
+  long long need = 0;
+  for (const auto& t : cands) need = std::max(need, (long long)t.nblk * t.ksteps * t.entries * 2 * t.nrows_b * 16);
+  return need;
 }
 
 /* Measures the planner's shortlisted tilings of `d` on the device with the caller's real buffers and keeps the fastest for
@@ -419,7 +438,7 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
       if ((long long)t.nblk * t.ksteps * t.entries * 2 * t.nrows_b * 16 > scratch_bytes) continue;
       if (!packed) {
         cudaError_t e = mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,
-                                                 t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, scratch_packed,
+                                                 t.pair ? d->kw : 0, d->kh * d->kw, t.slide ? d->kh : 0, d->kw, nullptr, scratch_packed,
                                                  d->dtype == MFC_BF16, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the conv reads its weights before griddepcontrol.wait
         if (e != cudaSuccess) rc = cuda_fail(e, "conv_autotune: pack");

@@ -134,6 +134,24 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
       : "memory");
 }
+// store 16 per-column values to 32 lanes x 16 consecutive fp32 columns (every lane gets the same 16 values)
+__device__ __forceinline__ void tmem_st16v(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+// 32 columns: a[0..15] then b[0..15]
+__device__ __forceinline__ void tmem_st32v(uint32_t taddr, const float (&a)[16], const float (&b)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]), "f"(a[8]), "f"(a[9]),
+      "f"(a[10]), "f"(a[11]), "f"(a[12]), "f"(a[13]), "f"(a[14]), "f"(a[15]), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]), "f"(b[4]),
+      "f"(b[5]), "f"(b[6]), "f"(b[7]), "f"(b[8]), "f"(b[9]), "f"(b[10]), "f"(b[11]), "f"(b[12]), "f"(b[13]), "f"(b[14]), "f"(b[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {

@@ -146,18 +146,29 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
     // columns past the tile's own halo (slide mode pads the row pitch to 128) are never read for a valid output
     const uint32_t W = (uint32_t)min(p.Win, ix_base + p.t.TW + (p.kw - 1));
     const uint32_t base = smem_u32(plane);
-    const FastDiv divP = p.divP;
     constexpr int U = 4;
+    // (row, col) of the thread's U slots, advanced incrementally: one iteration moves every slot by U*NT = step_r rows +
+    // step_c columns (one carry), so there is no division in the loop (with the sliding mode's pitch of 128, U*NT = 768 is
+    // exactly six rows: the columns never change)
+    const FastDiv divP = p.divP;
+    const int step_r = (int)fdiv((uint32_t)(U * NT), divP), step_c = U * NT - step_r * P;
+    int rr[U], cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = tid + u * NT;
+      rr[u] = (int)fdiv((uint32_t)idx, divP);
+      cc[u] = idx - rr[u] * P;
+      rr[u] += iy_base;
+      cc[u] += ix_base;
+    }
+    const int c_wrap = ix_base + P;
     for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
       uint4 v[U];
       bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int idx = idx0 + u * NT;
-        const int r = (int)fdiv((uint32_t)idx, divP);
-        const int c = idx - r * P;
-        ok[u] = idx < items && (uint32_t)(iy_base + r) < H && (uint32_t)(ix_base + c) < W;  // padding stays zero
-        if (ok[u]) v[u] = lds16_u32(base + (uint32_t)idx * 16u);
+        ok[u] = idx0 + u * NT < items && (uint32_t)rr[u] < H && (uint32_t)cc[u] < W;  // padding stays zero
+        if (ok[u]) v[u] = lds16_u32(base + (uint32_t)(idx0 + u * NT) * 16u);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -172,8 +183,15 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
         v[u] = pack8<BF16>(f);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int u = 0; u < U; ++u) {
         if (ok[u]) sts16_u32(base + (uint32_t)(idx0 + u * NT) * 16u, v[u]);
+        rr[u] += step_r;
+        cc[u] += step_c;
+        if (cc[u] >= c_wrap) {
+          cc[u] -= P;
+          ++rr[u];
+        }
+      }
     }
     return;
   }
@@ -566,7 +584,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     return two;
   };
   // scale / shift of one sub-step: accumulators -> fp32 values
+  const bool acc_init = p.acc_init != 0;
   auto scale_shift = [&](const uint32_t* a16, int co0, float (&f)[16]) {
+    if (acc_init) {  // the accumulators started from the shift: nothing left to add
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(a16[i]);
+      return;
+    }
     // with the 32 GroupNorm accumulators live (STATS) the scale/shift registers would push the loop over the
     // register budget: read them from smem there (8 broadcast LDS.128 per step)
     if constexpr (NB16 && (MODE == EPI_PLAIN || MODE == EPI_NCHW)) {
@@ -704,11 +728,32 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     }
     const bool more = r2 < R;
     tmem_ld_wait();
-    if (slide) {  // slide mode accumulates into zeroed columns
-      if (two)
-        tmem_st32_zero(tm_lane + (uint32_t)(r * NB + j));
-      else
-        tmem_st16_zero(tm_lane + (uint32_t)(r * NB + j));
+    if (slide) {  // slide mode accumulates into initialised columns: zeros, or the per-channel shift (acc_init)
+      const uint32_t col = tm_lane + (uint32_t)(r * NB + j);
+      if (acc_init) {
+        const int ca = NB16 ? 0 : nbk * NB + j, cb = NB16 ? 0 : ca + 16;
+        float va[16], vb[16];
+        const uint32_t sa = s_scale_addr + (uint32_t)(cpad + ca) * 4, sb = s_scale_addr + (uint32_t)(cpad + cb) * 4;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 a = lds_f4(sa + i * 4);
+          va[i] = a.x; va[i + 1] = a.y; va[i + 2] = a.z; va[i + 3] = a.w;
+        }
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 a = lds_f4(sb + i * 4);
+            vb[i] = a.x; vb[i + 1] = a.y; vb[i + 2] = a.z; vb[i + 3] = a.w;
+          }
+          tmem_st32v(col, va, vb);
+        } else {
+          tmem_st16v(col, va);
+        }
+      } else if (two) {
+        tmem_st32_zero(col);
+      } else {
+        tmem_st16_zero(col);
+      }
     }
     for (int a = 1; a < p.t.kacc; ++a) {  // K-split accumulator sets: add the partial sums
       uint32_t part[16];
@@ -759,6 +804,175 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   if (slide) tmem_st_wait();
 }
 
+// Fast epilogue for the layers that dominate ResUNet-16 (NB == 16: all output channels in one 16-column block, one N-block,
+// out_stride 1) when the pixel of (run r, lane) is AFFINE in r -- sliding mode (a run is one output row: pixel = pix0 + r*Wout,
+// valid <=> column valid && r < rows) or full-width tiles of a halo-free conv (a run is 128 consecutive pixels:
+// pixel = pix0 + r*128, valid <=> r*128 + lane index < rows*Wout).  No division, no per-sub-step address rebuild; with acc_init
+// the values leave TMEM finished (no scale/shift pass).  Same order of operations as epilogue_tile (same bits).
+template <bool BF16, int MODE>
+__device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t tmem_acc, uint32_t s_shift_addr, float (&d1)[16],
+                                                   float (&d2)[16], int b, int oy0, int ox0, int lq, int half, int lane, float& omax) {
+  constexpr bool kStats = MODE == EPI_STATS;
+  constexpr bool kNchw = MODE == EPI_NCHW;
+  constexpr bool kPrefetch = !kStats;   // the statistics accumulators leave no room for a second accumulator array
+  const int R = p.t.R;
+  int r = 2 * half;
+  if (r >= R) return;
+  const bool slide = p.t.slide != 0, acc_init = p.acc_init != 0, relu = p.act == 1;
+  const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
+  const int Wout = p.Wout, Cout = p.Cout;
+  const uint32_t HWo = (uint32_t)(p.Hout * Wout);
+  const int rows_valid = min(p.t.TH, p.Hout - oy0);
+  const int col = lq * 32 + lane;
+  uint32_t pix0, pstep;
+  int vofs, vstep, vlimit;
+  if (slide) {
+    pix0 = (uint32_t)(oy0 * Wout + ox0 + col);
+    pstep = (uint32_t)Wout;
+    vofs = 0;
+    vstep = 1;
+    vlimit = (col < p.t.TW && ox0 + col < Wout) ? rows_valid : 0;
+  } else {
+    pix0 = (uint32_t)(oy0 * Wout + col);
+    pstep = 128u;
+    vofs = col;
+    vstep = 128;
+    vlimit = rows_valid * Wout;
+  }
+  const bool has_c8 = !kNchw || p.y != nullptr;
+  const bool has_nchw = kNchw && p.y_nchw != nullptr;
+  uint8_t* const yp = has_c8 ? p.y + (size_t)b * p.y_bs + (size_t)pix0 * 16 : nullptr;
+  const size_t plane = (size_t)HWo * 16;
+  const bool two_planes = Cout > 8;
+  float* const np = has_nchw ? p.y_nchw + (size_t)b * Cout * HWo + pix0 : nullptr;
+  const uint32_t tm_lane = tmem_acc + ((uint32_t)(lq * 32) << 16);
+
+  auto load = [&](int rr, uint32_t (&a)[32]) {
+    const uint32_t c = tm_lane + (uint32_t)(rr * 16);
+    if (rr + 1 < R)
+      tmem_ld32(c, a);
+    else
+      tmem_ld16_lo(c, a);
+  };
+  auto reinit = [&](int rr) {  // slide mode: the drained columns start the next item from the shift (or zero)
+    const uint32_t c = tm_lane + (uint32_t)(rr * 16);
+    const bool two = rr + 1 < R;
+    if (acc_init) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 a = lds_f4(s_shift_addr + i * 4);
+        v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
+      }
+      if (two)
+        tmem_st32v(c, v, v);
+      else
+        tmem_st16v(c, v);
+    } else if (two) {
+      tmem_st32_zero(c);
+    } else {
+      tmem_st16_zero(c);
+    }
+  };
+  auto substep = [&](uint32_t* a16, int rr) {
+    const bool valid = rr * vstep + vofs < vlimit;
+    // scale / shift IN PLACE in the accumulator registers, so that the (common) case without either costs nothing
+    if (!acc_init && (has_scale || has_shift)) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 c = lds_f4(s_shift_addr + i * 4);
+        if (has_scale) {   // (kept for ABI callers; the Python engine folds scales into the weights)
+          const float4 a = lds_f4(s_shift_addr - 64 + i * 4);
+          a16[i + 0] = __float_as_uint(fmaf(__uint_as_float(a16[i + 0]), a.x, c.x));
+          a16[i + 1] = __float_as_uint(fmaf(__uint_as_float(a16[i + 1]), a.y, c.y));
+          a16[i + 2] = __float_as_uint(fmaf(__uint_as_float(a16[i + 2]), a.z, c.z));
+          a16[i + 3] = __float_as_uint(fmaf(__uint_as_float(a16[i + 3]), a.w, c.w));
+        } else {
+          a16[i + 0] = __float_as_uint(__uint_as_float(a16[i + 0]) + c.x);
+          a16[i + 1] = __float_as_uint(__uint_as_float(a16[i + 1]) + c.y);
+          a16[i + 2] = __float_as_uint(__uint_as_float(a16[i + 2]) + c.z);
+          a16[i + 3] = __float_as_uint(__uint_as_float(a16[i + 3]) + c.w);
+        }
+      }
+    }
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(a16[i]);
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+    }
+    if (!valid) return;
+    if (kStats) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        d1[i] += f[i];
+        d2[i] = fmaf(f[i], f[i], d2[i]);
+      }
+    }
+    const uint32_t poff = (uint32_t)rr * pstep;
+    if (has_c8) {
+      if (!BF16) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) omax = fmaxf(fmaxf(omax, fabsf(f[i])), fabsf(f[i + 1]));
+      }
+      uint8_t* q = yp + (size_t)poff * 16;
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = f[i];
+      *reinterpret_cast<uint4*>(q) = pack8<BF16>(g);
+      if (two_planes) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = f[8 + i];
+        *reinterpret_cast<uint4*>(q + plane) = pack8<BF16>(g);
+      }
+    }
+    if (kNchw && has_nchw) {
+      float* q = np + poff;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < Cout) q[(size_t)i * HWo] = f[i];
+    }
+  };
+  auto process = [&](uint32_t (&a)[32], int rr) {
+    substep(a, rr);
+    if (rr + 1 < R) substep(a + 16, rr + 1);
+  };
+
+  if constexpr (kPrefetch) {
+    // two accumulator arrays alternate: the TMEM load of the next step is in flight during the stores of this one
+    uint32_t A[32], Bv[32];
+    load(r, A);
+    while (true) {
+      tmem_ld_wait();
+      if (slide) reinit(r);
+      const bool more1 = r + 4 < R;
+      if (more1) load(r + 4, Bv);
+      process(A, r);
+      if (!more1) break;
+      r += 4;
+      tmem_ld_wait();
+      if (slide) reinit(r);
+      const bool more2 = r + 4 < R;
+      if (more2) load(r + 4, A);
+      process(Bv, r);
+      if (!more2) break;
+      r += 4;
+    }
+  } else {
+    uint32_t A[32];
+    while (true) {
+      load(r, A);
+      tmem_ld_wait();
+      if (slide) reinit(r);
+      process(A, r);
+      r += 4;
+      if (r >= R) break;
+    }
+  }
+  if (slide) tmem_st_wait();
+}
+
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 // Writes this CTA's GroupNorm partial record of one sample ([cpad][2] floats) and clears the accumulators.
@@ -800,7 +1014,7 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
   acc += clock64() - t0;
 }
 
-template <bool BF16, int MODE, bool NB16>
+template <bool BF16, int MODE, bool NB16, bool FAST>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -869,9 +1083,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long t_alloc = clock64();
-  if (p.t.slide) {  // every MMA of this mode accumulates: start from zeroed accumulators (the epilogue re-zeroes what it drains)
+  if (p.t.slide) {  // every MMA of this mode accumulates: start from initialised accumulators (the epilogue re-initialises
+                    // what it drains): zeros, or -- acc_init -- the per-channel shift, column c = [buffer][run][channel c % NB]
     if (warp < 4) {
-      for (uint32_t c = 0; c < p.t.tmem_cols; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+      for (uint32_t c = 0; c < p.t.tmem_cols; c += 16) {
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + c;
+        if (p.acc_init) {
+          float v[16];
+          const float* src = s_shift + (c % (uint32_t)NB);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = src[i];
+          tmem_st16v(ta, v);
+        } else {
+          tmem_st16_zero(ta);
+        }
+      }
       tmem_st_wait();
     }
     tc_fence_before();
@@ -1088,8 +1314,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       d1[i] = d2[i] = 0.0f;
-      sc[i] = NB16 ? s_scale[i] : 1.0f;
-      sh[i] = NB16 ? s_shift[i] : 0.0f;
+      sc[i] = (NB16 && !FAST) ? s_scale[i] : 1.0f;
+      sh[i] = (NB16 && !FAST) ? s_shift[i] : 0.0f;
     }
     // stats layout: [B][grid][cpad][2]; this CTA owns record blockIdx.x of every sample
     const size_t rec_stride = (size_t)cpad * 2;
@@ -1132,9 +1358,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         }
         __syncwarp();
       }
-      if (!(p.debug & 2))
-        epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
-                                        c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem, rp, total_items, omax);
+      if (!(p.debug & 2)) {
+        if constexpr (FAST)
+          epilogue_tile_fast<BF16, MODE>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_shift), d1, d2, c.b, c.oy0, c.ox0, lq,
+                                         half, lane, omax);
+        else
+          epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
+                                          c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem, rp, total_items, omax);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc_i]);
@@ -1167,7 +1398,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 template <bool BF16>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin_w, int taps, const int* __restrict__ chan_map,
                                     int cin_chunks, int ksteps, int NB, int nblk, int pair_kw, int taps_w, int slide_kh, int kw,
-                                    uint16_t* __restrict__ out) {
+                                    const float* __restrict__ scale, uint16_t* __restrict__ out) {
   const int rows = slide_kh > 0 ? slide_kh * NB : NB;
   const size_t total = (size_t)nblk * ksteps * taps * 2 * rows * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -1200,6 +1431,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
     if (co < Cout && kp < cin_chunks * 8 && tw >= 0) {
       const int ci = chan_map ? chan_map[kp] : kp;
       if (ci >= 0 && ci < Cin_w) v = w[((size_t)co * Cin_w + ci) * taps_w + tw];
+      if (scale) v *= scale[co];  // folded BatchNorm scale: one rounding, of the product
     }
     if constexpr (BF16) {
       __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -1437,13 +1669,13 @@ void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling
   }
 }
 
-template <bool BF16, int MODE, bool NB16>
+template <bool BF16, int MODE, bool NB16, bool FAST>
 static cudaError_t launch_conv_inst(const ConvParams& p, cudaStream_t st) {
   static int configured_for = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_for != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BF16, MODE, NB16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerCtaMax);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BF16, MODE, NB16, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerCtaMax);
     if (e != cudaSuccess) return e;
     configured_for = dev;
   }
@@ -1459,12 +1691,15 @@ static cudaError_t launch_conv_inst(const ConvParams& p, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BF16, MODE, NB16>, p);
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BF16, MODE, NB16, FAST>, p);
 }
 
 template <bool BF16, int MODE>
 static cudaError_t launch_conv_mode(const ConvParams& p, cudaStream_t st) {
-  return p.t.NB == 16 ? launch_conv_inst<BF16, MODE, true>(p, st) : launch_conv_inst<BF16, MODE, false>(p, st);
+  if constexpr (MODE == EPI_PLAIN || MODE == EPI_STATS || MODE == EPI_NCHW) {
+    if (p.epi_fast) return launch_conv_inst<BF16, MODE, true, true>(p, st);
+  }
+  return p.t.NB == 16 ? launch_conv_inst<BF16, MODE, true, false>(p, st) : launch_conv_inst<BF16, MODE, false, false>(p, st);
 }
 
 template <bool BF16>
@@ -1482,17 +1717,17 @@ cudaError_t launch_conv(const ConvParams& p, bool bf16, cudaStream_t st) {
 }
 
 cudaError_t launch_pack_weights(const float* w, int Cout, int Cin_w, int taps, const int* chan_map, int cin_chunks,
-                                int ksteps, int NB, int nblk, int pair_kw, int taps_w, int slide_kh, int kw, void* out, bool bf16,
-                                cudaStream_t st) {
+                                int ksteps, int NB, int nblk, int pair_kw, int taps_w, int slide_kh, int kw, const float* scale,
+                                void* out, bool bf16, cudaStream_t st) {
   const size_t total = (size_t)nblk * ksteps * taps * 2 * (slide_kh > 0 ? slide_kh * NB : NB) * 8;
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 4096);
   if (bf16)
     pack_weights_kernel<true><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, pair_kw, taps_w,
-                                                          slide_kh, kw, (uint16_t*)out);
+                                                          slide_kh, kw, scale, (uint16_t*)out);
   else
     pack_weights_kernel<false><<<blocks, threads, 0, st>>>(w, Cout, Cin_w, taps, chan_map, cin_chunks, ksteps, NB, nblk, pair_kw, taps_w,
-                                                           slide_kh, kw, (uint16_t*)out);
+                                                           slide_kh, kw, scale, (uint16_t*)out);
   return cudaGetLastError();
 }
 

@@ -11,8 +11,8 @@ namespace mfc {
 // conv_tc.cu
 cudaError_t launch_conv(const ConvParams& p, bool bf16, cudaStream_t st);
 cudaError_t launch_pack_weights(const float* w, int Cout, int Cin_w, int taps, const int* chan_map, int cin_chunks,
-                                int ksteps, int NB, int nblk, int pair_kw, int taps_w, int slide_kh, int kw, void* out, bool bf16,
-                                cudaStream_t st);
+                                int ksteps, int NB, int nblk, int pair_kw, int taps_w, int slide_kh, int kw, const float* scale,
+                                void* out, bool bf16, cudaStream_t st);
 
 // pointwise.cu
 cudaError_t launch_gather(const MfcGather& g, void* dst, long long dst_bs, int B, int H, int W, bool bf16, cudaStream_t st);

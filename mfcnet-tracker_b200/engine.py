@@ -567,17 +567,16 @@ class WeightPacker:
             cm = None
             if cmap is not None:
                 cm = torch.tensor(cmap, dtype=torch.int32, device=self.device)
-            abi.check(self.lib.mfc_conv2d_pack_weights(C.byref(desc), w.data_ptr(), w.shape[1], abi.ptr(cm), packed.data_ptr(),
-                                                       self._stream()))
+            # a per-channel scale (folded BatchNorm) goes INTO the weights: the epilogue only adds the shift
+            scf = scale.detach().contiguous().float() if scale is not None else None
+            abi.check(self.lib.mfc_conv2d_pack_weights(C.byref(desc), w.data_ptr(), w.shape[1], abi.ptr(cm), abi.ptr(scf),
+                                                       packed.data_ptr(), self._stream()))
             cpad = info.nb * info.nblk
             sc = sh = None
-            if scale is not None:
-                sc = torch.zeros(cpad, dtype=torch.float32, device=self.device)
-                sc[: scale.numel()] = scale.detach().float()
             if shift is not None:
                 sh = torch.zeros(cpad, dtype=torch.float32, device=self.device)
                 sh[: shift.numel()] = shift.detach().float()
-            self.cache[k] = (PackedConv(packed, sc, sh), w, cm)
+            self.cache[k] = (PackedConv(packed, sc, sh), w, cm, scf)
             # conv_tc_kernel stages weights / scale / shift before its griddepcontrol.wait (they overlap the previous
             # kernel's tail): everything written here must be complete before the first conv launch that uses it
             self._dirty = True
@@ -632,7 +631,7 @@ class Builder:
         if shift is None and bias is not None:
             shift = bias
         if autotune_enabled() and self.device.type == "cuda" and not abi.plan_only():
-            self._autotune(d, srcs, w_oihw, cmap, scale is not None, shift is not None, residual, want_stats, out_c8, out_nchw, y_c8)
+            self._autotune(d, srcs, w_oihw, cmap, False, shift is not None, residual, want_stats, out_c8, out_nchw, y_c8)
         info = self.prog.query(d)
         packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift)
         out, stats, io = self.prog.conv(d, info, srcs, packed, residual=residual, want_stats=want_stats, out_c8=out_c8,
@@ -643,7 +642,7 @@ class Builder:
         """Plan-time measurement of the candidate tilings of this conv on the device, with buffers of the real sizes and
         the real epilogue mode (mfc_conv2d_autotune keeps the fastest; temporaries are released afterwards)."""
         lib = self.prog.lib
-        info = self.prog.query(d)
+        need = int(lib.mfc_conv2d_autotune_scratch_bytes(C.byref(d)))   # NOT mfc_conv2d_query: that would freeze the plan
         dev = self.device
         cpad = d.Cout + 256      # upper bound over the N-block widths the tuner may try
         io = abi.MfcConvIO()
@@ -673,7 +672,7 @@ class Builder:
             io.stats = tmp((d.B, 148, cpad, 2), torch.float32).data_ptr()
         w = w_oihw.detach().contiguous().float()
         cm = torch.tensor(cmap, dtype=torch.int32, device=dev) if cmap is not None else None
-        scratch = tmp((2 * int(info.packed_weight_bytes) + 4096,), torch.uint8)
+        scratch = tmp((need + 4096,), torch.uint8)
         stream = torch.cuda.current_stream(dev).cuda_stream
         abi.check(lib.mfc_conv2d_autotune(C.byref(d), C.byref(io), w.data_ptr(), w.shape[1], abi.ptr(cm), scratch.data_ptr(),
                                           scratch.numel(), autotune_reps(), stream))

@@ -55,8 +55,19 @@ def _upsample(dim, dim_out):
     return nn.Sequential(nn.Identity(), nn.Conv2d(dim, dim_out, 3, padding=1))
 
 
-def record_resnet_block(bld, name, blk, srcs):
-    """Records a ResnetBlock over the channel-concat `srcs`; returns the materialised output Act."""
+def _residual_as_source():
+    """MFC_RES_AS_SOURCE=0: keep the 1x1 res_conv's `+ silu(GN(h2))` in the conv epilogue (residual operand) instead of feeding
+    h2 through the conv as extra input channels with identity weights (measurement switch)."""
+    import os
+    return os.environ.get("MFC_RES_AS_SOURCE", "1") != "0"
+
+
+def record_resnet_block(bld, name, blk, srcs, tail=None, tail_kw=None):
+    """Records a ResnetBlock over the channel-concat `srcs`; returns the materialised output Act.
+
+    `tail` = a 1x1 nn.Conv2d applied to the block's output (the network's output_layer): both are linear after the SiLU, so
+    it is composed into the block's own 1x1 conv -- tail(res_conv(x) + s) = (Wt Wr) x + Wt s + (Wt br + bt) -- and the block
+    output is never written.  Returns the result of Builder.conv for that fused layer (tail_kw: its output arguments)."""
     H, W = srcs[0].H, srcs[0].W
     h1, st1, info1, _ = bld.conv(name + ".block1.proj", srcs, bld.packer.standardized(name + ".block1.proj", blk.block1.proj.weight),
                                  3, bias=blk.block1.proj.bias, pad=1, want_stats=True)
@@ -68,13 +79,31 @@ def record_resnet_block(bld, name, blk, srcs):
     aff2 = bld.group_norm_affine(st2, info2, blk.block2.norm.weight, blk.block2.norm.bias, blk.dim_out, blk.groups, H * W,
                                  blk.block2.norm.eps)
     h2 = h2.with_affine(aff2)
+    if isinstance(blk.res_conv, nn.Conv2d) and _residual_as_source():
+        # res_conv(x) + silu(GN(h2)) = ONE 1x1 conv over the concat [x..., silu(GN(h2))] with the weights [Wr | I]: the GroupNorm
+        # affine + SiLU of h2 runs in the tile loader like for any other source, the identity columns pass it through the tensor
+        # core exactly (fp16 x 1.0, fp32 accumulate), and the epilogue is the plain one (no residual operand to fetch).
+        C_ = blk.dim_out
+        wr = blk.res_conv.weight.detach().float().reshape(C_, -1)
+        w = torch.cat([wr, torch.eye(C_, dtype=wr.dtype, device=wr.device)], 1)
+        b = blk.res_conv.bias.detach().float()
+        if tail is not None:
+            wt = tail.weight.detach().float().reshape(tail.out_channels, C_)
+            w = wt @ w
+            b = wt @ b + (tail.bias.detach().float() if tail.bias is not None else 0.0)
+            return bld.conv(name + ".res_conv+tail", list(srcs) + [h2], w.reshape(tail.out_channels, -1, 1, 1), 1, bias=b, **(tail_kw or {}))
+        out, _, _, _ = bld.conv(name + ".res_conv+h2", list(srcs) + [h2], w.reshape(C_, -1, 1, 1), 1, bias=b)
+        return out
     if isinstance(blk.res_conv, nn.Conv2d):
         out, _, _, _ = bld.conv(name + ".res_conv", srcs, blk.res_conv.weight, 1, bias=blk.res_conv.bias, residual=h2)
-        return out
-    if len(srcs) != 1 or srcs[0].affine is not None:
-        raise RuntimeError("identity residual needs one materialised source")
-    out_t = bld.arena.alloc(tuple(h2.t.shape), bld.tdtype)
-    return bld.prog.affine_silu_add(h2, srcs[0], out_t)
+    else:
+        if len(srcs) != 1 or srcs[0].affine is not None:
+            raise RuntimeError("identity residual needs one materialised source")
+        out_t = bld.arena.alloc(tuple(h2.t.shape), bld.tdtype)
+        out = bld.prog.affine_silu_add(h2, srcs[0], out_t)
+    if tail is not None:
+        return bld.conv(name + ".tail", [out], tail.weight, 1, bias=tail.bias, **(tail_kw or {}))
+    return out
 
 
 class ResUnet_VB(nn.Module):
@@ -143,9 +172,8 @@ class ResUnet_VB(nn.Module):
                 x, _, _, _ = bld.conv("ups.%d.1.1" % i, [x], cv.weight, 3, bias=cv.bias, pad=1, upsample=2)
             else:
                 x, _, _, _ = bld.conv("ups.%d.1" % i, [x], up.weight, 3, bias=up.bias, pad=1)
-        x = record_resnet_block(bld, "final_res_block", self.final_res_block, [x, stem])
-        out, _, _, io = bld.conv("output_layer", [x], self.output_layer.weight, 1, bias=self.output_layer.bias,
-                                 out_c8=maps_c8 is not None, y_c8=maps_c8, out_nchw=logits_nchw)
+        out, _, _, io = record_resnet_block(bld, "final_res_block", self.final_res_block, [x, stem], tail=self.output_layer,
+                                            tail_kw=dict(out_c8=maps_c8 is not None, y_c8=maps_c8, out_nchw=logits_nchw))
         return out, io
 
     def _plan(self, B, H, W, device, dt):

@@ -9,8 +9,10 @@
  * the channel count (:102-104).  The reference hard-codes pad 20 / stride 2 / 21x21; here they
  * are the parameters (max_disp, stride2) with the same meaning.
  *
- * Parity status: UNPINNED -- the reference kernel needs CuPy + a GPU and the reference ships no
- * golden vectors for it; this file is pinned only by hand-computed cases (tests/test_oracle_corr.py).
+ * Parity status: PINNED.  tests/golden/corr_ref.npz holds outputs of the reference's own CUDA-C kernels, compiled with
+ * NVRTC and launched with the reference's launch configuration on a B200 (oracle/corr_ref_nvrtc.py,
+ * oracle/make_golden_corr.py); this restatement reproduces them bit for bit (tests/test_oracle_cpu.py), and the GPU
+ * suite additionally runs the reference kernels live next to the product (tests/test_gpu_kernels.py).
  */
 #include <math.h>
 #include <stdlib.h>

@@ -72,6 +72,18 @@ def test_correlation_reference_operating_point_properties(M):
     assert (out - ex).abs().max().item() <= 2e-6
 
 
+def test_correlation_matches_reference_kernel_golden(M):
+    """Committed outputs of the reference's own kernels (tests/golden/corr_ref.npz, oracle/make_golden_corr.py):
+    exact_order must match bit for bit, the fast kernels to fp32 rounding."""
+    from oracle import make_golden_corr as MG
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "corr_ref.npz"))
+    for tag, B, Cc, H, W in MG.FWD_CASES:
+        a, b = MG.inputs(tag, B, Cc, H, W)
+        ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        assert np.array_equal(M.correlation(ta, tb, exact_order=True).cpu().numpy(), gold[tag]), tag
+        assert np.abs(M.correlation(ta, tb).cpu().numpy() - gold[tag]).max() <= 2e-6, tag
+
+
 def test_correlation_matches_the_reference_kernel_itself(M):
     """The reference's own CUDA-C kernels (models/unflow_correlation.py:10-105), compiled with NVRTC and launched as
     `_FunctionCorrelation.forward` launches them (oracle/corr_ref_nvrtc.py), at the reference's operating point

@@ -23,7 +23,8 @@ ARGMAX_AGREE = 0.999        # north_star bound, asserted on the full-size (480x6
 # reference top-2 margin exceeds twice the measured logit error (those cannot legitimately flip).  Tilings are a pure
 # function of the geometry (committed tuning table), so these numbers are reproducible bit for bit.
 ARGMAX_AGREE_SMALL = 0.999
-REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
+REPORT = os.environ.get("MFC_PARITY_REPORT") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
+                                                            "parity_report.jsonl")
 
 
 def _report(**kw):

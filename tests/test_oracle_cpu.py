@@ -16,6 +16,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # ---------------------------------------------------------------- correlation
+def test_corr_oracle_c_matches_reference_kernel_golden():
+    """tests/golden/corr_ref.npz holds outputs of the REFERENCE's own CUDA kernels (models/unflow_correlation.py:10-105,
+    NVRTC-compiled and launched as `_FunctionCorrelation.forward` does: oracle/make_golden_corr.py, run on a B200).  The C
+    restatement must reproduce them bit for bit -- this is what pins oracle/corr_oracle.c."""
+    from oracle import make_golden_corr as MG
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corr_ref.npz"))
+    for tag, B, Cc, H, W in MG.FWD_CASES:
+        a, b = MG.inputs(tag, B, Cc, H, W)
+        assert np.array_equal(corr.correlation_c(a, b, 20, 2), gold[tag]), tag
+
+
 def test_corr_oracle_hand_case():
     """1 channel, delta inputs: out[tc][y][x] = f1[y][x]*f2[y+dy][x+dx] (models/unflow_correlation.py:74-90)."""
     f1 = np.zeros((1, 1, 5, 6), np.float32)

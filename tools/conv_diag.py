@@ -115,6 +115,17 @@ CASES = [
     dict(B=1, H=480, W=640, cins=[16], Cout=16, k=3, stats=True),
     dict(B=2, H=480, W=640, cins=[16, 16], Cout=16, k=3, src_affine=True),
     dict(B=1, H=480, W=640, cins=[5, 5, 5, 7], Cout=15, k=11, act=1, scale=True, bias=False),
+    # fast epilogue paths: full-width tiles of halo-free convs (residual-as-source 1x1, fused output layer, 2x2 s2),
+    # sliding mode with shift-initialised accumulators (+ReLU, + statistics, odd sizes)
+    dict(B=2, H=32, W=48, cins=[16, 16, 16], Cout=16, k=1, src_affine=True),
+    dict(B=3, H=60, W=80, cins=[16, 16, 16], Cout=5, k=1),
+    dict(B=2, H=480, W=640, cins=[16, 16, 16], Cout=16, k=1),
+    dict(B=2, H=480, W=640, cins=[16, 16, 16], Cout=5, k=1),
+    dict(B=2, H=240, W=320, cins=[16], Cout=16, k=2, stride=2, pad=0),
+    dict(B=2, H=33, W=47, cins=[15], Cout=15, k=3, act=1, scale=True),
+    dict(B=2, H=37, W=131, cins=[16], Cout=16, k=3, stats=True, src_affine=True),
+    dict(B=1, H=5, W=7, cins=[16], Cout=16, k=3, stats=True),
+    dict(B=2, H=480, W=640, cins=[15], Cout=5, k=1, bias=False),
 ]
 
 
