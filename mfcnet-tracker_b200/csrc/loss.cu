@@ -42,7 +42,10 @@ __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const float*
       if (c < N) se += expf(v[c] - mx);
     const float lse = mx + logf(se);
     const int t = (int)target[i];
-    const float w = cw ? __ldg(cw + t) : 1.0f;
+    // labels outside [0, N) (nn.NLLLoss's ignore_index = -100 of src/loss.py:38, 255 = void, ...) carry no NLL weight and never
+    // match a class in the Jaccard sums; their probabilities still count in sum(p_c), as `(targets == c)` does upstream
+    const bool t_ok = (unsigned)t < (unsigned)N;
+    const float w = !t_ok ? 0.0f : (cw ? __ldg(cw + t) : 1.0f);
 #pragma unroll
     for (int c = 0; c < kLossMaxClasses; ++c)
       if (c < N) {

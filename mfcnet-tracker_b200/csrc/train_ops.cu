@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
       }
     const float inv = 1.0f / se;
     const int t = (int)target[i];
-    const float wn = s_coef[0] * s_cw[t];
+    const float wn = (unsigned)t < (unsigned)N ? s_coef[0] * s_cw[t] : 0.0f;  // out-of-range label: ignored by the NLL term
     float gp[kLossMaxClassesT];  // d jacc / d p_c
     float dot = 0.0f;
 #pragma unroll

@@ -9,6 +9,7 @@ channel) affine that the consuming conv applies while staging its input tile.
 """
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -197,6 +198,7 @@ class Program:
         self.packer = None   # WeightPacker whose device writes must have completed before the first run (Builder sets it)
         self._ovf = overflow_counter(self.device) if dtype_name == "fp16" else None
         self._checked = False
+        self._lock = threading.Lock()   # a program's pointer slots are shared state: one caller binds + issues at a time
 
     # ---- low-level recording -----------------------------------------------------------------
     def _push(self, op, a, b=None, launches=1, meta=None):
@@ -241,6 +243,17 @@ class Program:
         if self._ovf is not None and (not self._checked or _check_every_run()):
             self._checked = True
             check_overflow(self.device)
+
+    def call(self, tensors, set_outputs=None, stream=None):
+        """rebind(tensors) + set_outputs() + run() as one critical section: two threads (or two streams of one thread) that
+        share a module -- and with it this cached program -- cannot interleave their pointer updates.  The kernels themselves
+        are enqueued on the caller's stream; intermediate buffers of the plan are reused in stream order."""
+        with self._lock:
+            self.rebind(tensors)
+            if set_outputs is not None:
+                set_outputs()
+            with device_guard(self.device):
+                self.run(stream)
 
     def capture(self):
         """Capture this program into a CUDA graph (all of its pointers must be static from now on)."""

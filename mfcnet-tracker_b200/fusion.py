@@ -122,10 +122,7 @@ class MultiFrameNetBase(nn.Module):
             self._plans[key] = (bld.prog, io, arena)
         prog, io, _ = self._plans[key]
         out = torch.empty((B, self.num_classes, H, W), dtype=torch.float32, device=x.device)
-        prog.rebind(self._split(x))
-        io.y_nchw = out.data_ptr()
-        with engine.device_guard(x.device):
-            prog.run()
+        prog.call(self._split(x), lambda: setattr(io, "y_nchw", out.data_ptr()))
         engine.record_stream(x)
         return out
 

@@ -268,9 +268,6 @@ class HighResolutionNet(nn.Module):
         dt = self._check_weights(x.device)
         prog, rz, _ = self._plan(B, H, W, x.device, dt)
         out = torch.empty((B, self.out_dim, H, W), dtype=torch.float32, device=x.device)
-        prog.rebind({"x": x})
-        rz.dst_nchw = out.data_ptr()
-        with engine.device_guard(x.device):
-            prog.run()
+        prog.call({"x": x}, lambda: setattr(rz, "dst_nchw", out.data_ptr()))
         engine.record_stream(x)
         return out

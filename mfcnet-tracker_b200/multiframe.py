@@ -126,11 +126,8 @@ class _MultiFrame(nn.Module):
             tensors.update({("flow", i): optflow[i].contiguous().float() for i in range(K - 1)})
         if depth is not None:
             tensors.update({("depth", i): depth[i].contiguous().float() for i in range(K)})
-        plan["prog"].rebind(tensors)
         out = torch.empty((B, self.num_classes, H, W), dtype=torch.float32, device=dev)
-        plan["io"].y_nchw = out.data_ptr()
-        with engine.device_guard(dev):
-            plan["prog"].run()
+        plan["prog"].call(tensors, lambda: setattr(plan["io"], "y_nchw", out.data_ptr()))
         for t in tensors.values():
             engine.record_stream(t)
         return out

@@ -205,10 +205,7 @@ class ResUnet_VB(nn.Module):
         dt = self._check_weights(x.device)
         prog, io, _ = self._plan(B, H, W, x.device, dt)
         out = torch.empty((B, self.out_dim, H, W), dtype=torch.float32, device=x.device)
-        prog.rebind({"x": x})
-        io.y_nchw = out.data_ptr()
-        with engine.device_guard(x.device):
-            prog.run()
+        prog.call({"x": x}, lambda: setattr(io, "y_nchw", out.data_ptr()))
         # x and out are referenced by raw pointer until the kernels run: keep them alive on this stream
         engine.record_stream(x)
         return out

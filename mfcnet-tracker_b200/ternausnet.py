@@ -197,13 +197,7 @@ class _TernausNet(nn.Module):
         dt = self._check_weights(x.device)
         prog, last, _ = self._plan(B, H, W, x.device, dt)
         out = torch.empty((B, self.num_classes, H, W), dtype=torch.float32, device=x.device)
-        prog.rebind({"x": x})
-        if self.num_classes > 1:
-            last.logp = out.data_ptr()
-        else:
-            last.y_nchw = out.data_ptr()
-        with engine.device_guard(x.device):
-            prog.run()
+        prog.call({"x": x}, lambda: setattr(last, "logp" if self.num_classes > 1 else "y_nchw", out.data_ptr()))
         engine.record_stream(x)
         return out
 

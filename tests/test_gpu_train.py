@@ -44,6 +44,36 @@ def test_loss_grad_matches_autograd(M, case):
     assert err < 1e-5 * float(ref.abs().max()) + 1e-9, (err, float(ref.abs().max()))
 
 
+def test_loss_ignores_out_of_range_labels(M):
+    """nn.NLLLoss's ignore_index = -100 (src/loss.py:38 uses the default): such pixels add nothing to the NLL term nor to the
+    per-class target masks, and other out-of-range labels (255 = void) must not read outside the class-weight table."""
+    from oracle import synth
+    B, N, H, W = 2, 5, 40, 56
+    o, t = synth.loss_case("ign", B, N, H, W, seed=2, fg=0.2)
+    t[:, :5, :] = -100
+    cw = CW[:N]
+    x = torch.from_numpy(o).double().requires_grad_(True)
+    tt = torch.from_numpy(t)
+    logp = F.log_softmax(x, dim=1)
+    nll = F.nll_loss(logp, tt, weight=torch.tensor(cw, dtype=torch.float64))       # ignore_index=-100
+    jac = 0.0
+    for c in range(1, N):
+        m = (tt == c).double()
+        p = logp[:, c].exp()
+        inter = (p * m).sum()
+        jac = jac - torch.log((inter + 1e-15) / (p.sum() + m.sum() - inter + 1e-15))
+    total = 0.7 * nll + 0.3 * jac / N
+    total.backward()
+    losses, grad = M.loss_and_grad(torch.from_numpy(o).cuda(), tt.cuda(), cw)
+    assert abs(float(losses[0]) - float(total)) < 1e-5 * max(1.0, abs(float(total)))
+    ref = x.grad.float()
+    assert float((grad.cpu() - ref).abs().max()) < 1e-5 * float(ref.abs().max()) + 1e-9
+    t2 = t.copy()
+    t2[t2 == -100] = 255                                                           # any other out-of-range value: same result
+    losses2, grad2 = M.loss_and_grad(torch.from_numpy(o).cuda(), torch.from_numpy(t2).cuda(), cw)
+    assert float(losses2[0]) == float(losses[0]) and torch.equal(grad2, grad)
+
+
 def test_adam_matches_torch(M):
     from mfcnet_tracker_b200 import abi
     lib = abi.load()
