@@ -106,7 +106,7 @@ typedef struct MfcConvInfo {
   long long packed_weight_bytes;
   int weight_layout;   /* 0 = one B block per filter tap, 1 = sliding-accumulate layout (vertical taps stacked along N);
                           packed weights are only valid for descriptors that report the same layout and nb/nblk/ksteps */
-  int reserved;
+  int flags;           /* bit 0: the plan runs the affine-addressed fast epilogue (required by io->head_w) */
 } MfcConvInfo;
 
 typedef struct MfcSrc {
@@ -145,6 +145,9 @@ typedef struct MfcConvDesc {
 /* mfc_conv2d_fwd will be given io->stats: the plan must keep the padded Cout within the 256 channels the epilogue's
  * shared-memory scratch holds (part of the plan key, like MFC_CONV_HAS_RESIDUAL). */
 #define MFC_CONV_WANT_STATS 4
+/* mfc_conv2d_fwd will be given io->head_w: the plan is restricted to tilings whose epilogue holds all output channels of a
+ * pixel in one thread with affine pixel addressing (Cout <= 16; part of the plan key). */
+#define MFC_CONV_WANT_HEAD 8
 
 int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info);
 
@@ -178,6 +181,15 @@ typedef struct MfcConvIO {
   long long y_batch_stride;  /* bytes                                        */
   float* y_nchw;             /* fp32 [B][Cout][Hout][Wout] or NULL           */
   float* stats;              /* [B][stats_per_image][nb*nblk][2] or NULL     */
+  /* Optional fused 1x1 "head": a second linear layer applied to the epilogue values v (after shift / residual / act),
+   *   y_nchw[b][n][pixel] = head_b[n] + sum_co head_w[n*16 + co] * v[co],   n < head_n <= 8,
+   * evaluated in fp32 on the values still in registers: the conv's own output need not be stored (y_c8 may be NULL) and the
+   * last activation / weights of a network are never rounded to fp16 (models/multiframe_model.py:72-73: the fusion head's
+   * final 1x1 conv).  Needs the descriptor flag MFC_CONV_WANT_HEAD, Cout <= 16, y_nchw, no stats / residual. */
+  const float* head_w;       /* [head_n][16] fp32 (device; columns >= Cout zero) or NULL */
+  const float* head_b;       /* [head_n] or NULL                                         */
+  int head_n;
+  int reserved;
   int* overflow;             /* NULL, or a device counter: fp16 range guard.  Every epilogue warp that stored a value
                                 beyond +-65504 into y_c8 (it became +-inf) adds 1.  The caller zeroes and reads it
                                 (mfc_run_list users: one counter for the whole program).                              */
@@ -202,6 +214,9 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
                         void* scratch_packed, long long scratch_bytes, int reps, void* stream);
 /* Packed-weight scratch bytes that cover every candidate mfc_conv2d_autotune measures for `d` (does not plan `d`). */
 long long mfc_conv2d_autotune_scratch_bytes(const MfcConvDesc* d);
+/* Diagnostic: the candidates mfc_conv2d_autotune would measure, one per line
+ * "TH TW slide CBc NB nstages kstages R nacc tiles_x grid", in the cost model's order.  Returns the bytes needed. */
+long long mfc_conv2d_shortlist(const MfcConvDesc* d, int per_bucket, char* buf, long long cap);
 /* Tuning table as text, one geometry per line ("<16 key ints> : TH TW slide CBc NB nstages", '#' = comment).
  * export returns the bytes needed including the terminating 0 and writes at most `cap`; import returns the number of
  * entries taken (geometries that already have a plan keep it) or a negative error code. */

@@ -15,6 +15,7 @@ MFC_MAX_SRC = 8
 MFC_CONV_HAS_RESIDUAL = 1
 MFC_CONV_REVERSE_ORDER = 2
 MFC_CONV_WANT_STATS = 4
+MFC_CONV_WANT_HEAD = 8
 OP_FORK, OP_JOIN, MFC_MAX_LANES = 100, 101, 4
 OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP, OP_FUSE_SUM, OP_RESIZE, OP_MAXPOOL2, OP_HEATMAP = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
@@ -29,7 +30,7 @@ class MfcConvInfo(C.Structure):
     _fields_ = [("nb", c_int), ("nblk", c_int), ("cin_chunks", c_int), ("ksteps", c_int), ("tile_h", c_int),
                 ("tile_w", c_int), ("tiles_per_image", c_int), ("stats_per_image", c_int), ("runs", c_int),
                 ("kstages", c_int), ("nstages", c_int), ("grid", c_int), ("smem_bytes", c_int), ("tmem_cols", c_int), ("packed_weight_bytes", c_ll),
-                ("weight_layout", c_int), ("reserved", c_int)]
+                ("weight_layout", c_int), ("flags", c_int)]
 
 
 class MfcSrc(C.Structure):
@@ -46,7 +47,8 @@ class MfcConvDesc(C.Structure):
 class MfcConvIO(C.Structure):
     _fields_ = [("w_packed", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("residual", c_void_p),
                 ("res_affine", c_void_p), ("res_batch_stride", c_ll), ("y_c8", c_void_p), ("y_batch_stride", c_ll),
-                ("y_nchw", c_void_p), ("stats", c_void_p), ("overflow", c_void_p)]
+                ("y_nchw", c_void_p), ("stats", c_void_p), ("head_w", c_void_p), ("head_b", c_void_p), ("head_n", c_int), ("reserved", c_int),
+                ("overflow", c_void_p)]
 
 
 class MfcWarpArgs(C.Structure):
@@ -116,6 +118,7 @@ _SIGNATURES = {
     "mfc_conv2d_fwd": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p], c_int),
     "mfc_conv2d_autotune": ([C.POINTER(MfcConvDesc), C.POINTER(MfcConvIO), c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p], c_int),
     "mfc_conv2d_autotune_scratch_bytes": ([C.POINTER(MfcConvDesc)], c_ll),
+    "mfc_conv2d_shortlist": ([C.POINTER(MfcConvDesc), c_int, C.c_char_p, c_ll], c_ll),
     "mfc_conv2d_plan_export": ([C.c_char_p, c_ll], c_ll),
     "mfc_conv2d_plan_import": ([C.c_char_p], c_int),
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
@@ -223,7 +226,8 @@ class _PlanOnly:
     """MFC_B200_PLAN_ONLY=1 (CPU test-suite only): plan construction is exercised for real
     (descriptor validation, tiling queries, buffer shapes, command lists) but nothing is launched,
     so outputs are UNINITIALISED memory.  This is not a compute path."""
-    _REAL = ("mfc_abi_version", "mfc_last_error", "mfc_conv2d_query", "mfc_conv2d_plan_export", "mfc_conv2d_plan_import")
+    _REAL = ("mfc_abi_version", "mfc_last_error", "mfc_conv2d_query", "mfc_conv2d_plan_export", "mfc_conv2d_plan_import", "mfc_conv2d_shortlist",
+             "mfc_conv2d_autotune_scratch_bytes")
 
     def __init__(self, lib):
         self._lib = lib

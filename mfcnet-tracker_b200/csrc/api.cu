@@ -114,7 +114,7 @@ int validate_desc(const MfcConvDesc* d) {
   return MFC_OK;
 }
 
-constexpr int kPlanFlags = MFC_CONV_HAS_RESIDUAL | MFC_CONV_WANT_STATS;
+constexpr int kPlanFlags = MFC_CONV_HAS_RESIDUAL | MFC_CONV_WANT_STATS | MFC_CONV_WANT_HEAD;
 
 PlanKey plan_key(const MfcConvDesc* d) {
   int chunks = 0, aff = 0;
@@ -130,9 +130,18 @@ bool same_choice(const mfc::ConvTiling& t, const TableChoice& c) {
   return t.TH == c.TH && t.TW == c.TW && t.slide == c.slide && t.CBc == c.CBc && t.NB == c.NB && t.nstages == c.nstages;
 }
 
-// statistics need the padded Cout to fit the per-warp shared-memory scratch (see conv_fwd_tiled)
+// pixel of (run, lane) affine in the run index: sliding mode, or full-width tiles of a halo-free conv
+bool tiling_fast_epilogue(const MfcConvDesc* d, const mfc::ConvTiling& t) {
+  const bool affine_rows = t.slide || (t.P == t.TW && t.TW == d->Wout && t.tiles_x == 1);
+  return t.NB == 16 && t.nblk == 1 && d->out_stride != 2 && t.kacc == 1 && affine_rows;
+}
+
+// statistics need the padded Cout to fit the per-warp shared-memory scratch (see conv_fwd_tiled); a fused head needs the
+// fast epilogue
 bool tiling_serves(const MfcConvDesc* d, const mfc::ConvTiling& t) {
-  return !(d->reserved & MFC_CONV_WANT_STATS) || t.NB * t.nblk <= 256;
+  if ((d->reserved & MFC_CONV_WANT_STATS) && t.NB * t.nblk > 256) return false;
+  if ((d->reserved & MFC_CONV_WANT_HEAD) && !tiling_fast_epilogue(d, t)) return false;
+  return true;
 }
 
 // g_plan_mu held.  Resolves the plan of `d` (table choice, else the cost model) without marking it handed out.
@@ -260,6 +269,15 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.idesc = mfc::make_idesc_f16(p.t.NB, d->dtype == MFC_BF16);
   p.reverse = (d->reserved & MFC_CONV_REVERSE_ORDER) ? 1 : 0;
   p.total_items = p.B * p.t.tiles_x * p.t.tiles_y * p.t.nblk;
+  {
+    static const int chunk_env = getenv("MFC_CONV_CHUNK") ? atoi(getenv("MFC_CONV_CHUNK")) : 4;
+    const int c = chunk_env < 1 ? 1 : (chunk_env > 64 ? 64 : chunk_env);
+    const int per_group = p.t.grid * c;
+    p.chunk = (p.t.nblk == 1 && c > 1 && p.total_items >= 2 * per_group) ? c : 1;
+    p.full_items = p.chunk > 1 ? (p.total_items / per_group) * per_group : 0;
+    p.div_grid = mfc::make_fastdiv((uint32_t)p.t.grid);
+    p.div_chunk = mfc::make_fastdiv((uint32_t)p.chunk);
+  }
   p.w = (const uint8_t*)io->w_packed;
   p.scale = io->scale;
   p.shift = io->shift;
@@ -274,8 +292,15 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.acc_init = (p.t.slide && io->scale == nullptr && io->shift != nullptr) ? 1 : 0;
   {
     static const int no_fast = getenv("MFC_CONV_EPI_FAST") ? (atoi(getenv("MFC_CONV_EPI_FAST")) == 0) : 0;  // measurement switch
-    const bool affine_rows = p.t.slide || (p.t.P == p.t.TW && p.t.TW == d->Wout && p.t.tiles_x == 1);
-    p.epi_fast = (!no_fast && p.t.NB == 16 && p.t.nblk == 1 && p.out_stride == 1 && p.t.kacc == 1 && affine_rows) ? 1 : 0;
+    p.epi_fast = (tiling_fast_epilogue(d, p.t) && (!no_fast || io->head_w)) ? 1 : 0;
+  }
+  if (io->head_w) {
+    if (!(d->reserved & MFC_CONV_WANT_HEAD) || !p.epi_fast || !io->y_nchw || io->stats || io->residual || io->head_n < 1 || io->head_n > 8 ||
+        d->Cout > 16)
+      return fail(MFC_EINVAL, "conv: fused head needs MFC_CONV_WANT_HEAD, Cout <= 16, y_nchw, 1 <= head_n <= 8, no stats / residual");
+    p.head_w = io->head_w;
+    p.head_b = io->head_b;
+    p.head_n = io->head_n;
   }
   {
     static const int dbg = (getenv("MFC_CONV_DEBUG") ? atoi(getenv("MFC_CONV_DEBUG")) : 0) | (mfc::silu_accurate() ? 16 : 0);
@@ -358,6 +383,7 @@ int mfc_conv2d_query(const MfcConvDesc* d, MfcConvInfo* info) {
   info->tmem_cols = (int)t.tmem_cols;
   info->packed_weight_bytes = (long long)t.nblk * t.ksteps * t.entries * 2 * t.nrows_b * 16;
   info->weight_layout = t.slide;
+  info->flags = tiling_fast_epilogue(d, t) ? 1 : 0;
   return MFC_OK;
 }
 
@@ -394,6 +420,28 @@ long long mfc_conv2d_autotune_scratch_bytes(const MfcConvDesc* d) {
   mfc::conv_shortlist(*d, getenv("MFC_CONV_TUNE_WIDTH") ? atoi(getenv("MFC_CONV_TUNE_WIDTH")) : 3, cands);
   long long need = 0;
   for (const auto& t : cands) need = std::max(need, (long long)t.nblk * t.ksteps * t.entries * 2 * t.nrows_b * 16);
+  return need;
+}
+
+/* Diagnostic: the candidates mfc_conv2d_autotune would measure for `d`, one per line
+ * "TH TW slide CBc NB nstages kstages R nacc tiles_x grid", in the cost model's order.  Returns the bytes needed. */
+long long mfc_conv2d_shortlist(const MfcConvDesc* d, int per_bucket, char* buf, long long cap) {
+  if (validate_desc(d) != MFC_OK) return 0;
+  std::vector<mfc::ConvTiling> cands;
+  mfc::conv_shortlist(*d, per_bucket, cands);
+  std::string out;
+  char line[160];
+  for (const auto& t : cands) {
+    snprintf(line, sizeof(line), "%d %d %d %d %d %d %d %d %d %d %d\n", t.TH, t.TW, t.slide, t.CBc, t.NB, t.nstages, t.kstages, t.R, t.nacc,
+             t.tiles_x, t.grid);
+    out += line;
+  }
+  const long long need = (long long)out.size() + 1;
+  if (buf && cap > 0) {
+    const long long n = need <= cap ? need - 1 : cap - 1;
+    memcpy(buf, out.data(), (size_t)n);
+    buf[n] = 0;
+  }
   return need;
 }
 
@@ -435,6 +483,7 @@ int mfc_conv2d_autotune(const MfcConvDesc* d, const MfcConvIO* io, const float* 
       const mfc::ConvTiling& t = cands[i];
       if (done[i] || t.slide != cands[g0].slide || t.NB != cands[g0].NB) continue;
       done[i] = 1;
+      if (!tiling_serves(d, t)) continue;
       if ((long long)t.nblk * t.ksteps * t.entries * 2 * t.nrows_b * 16 > scratch_bytes) continue;
       if (!packed) {
         cudaError_t e = mfc::launch_pack_weights(w_oihw, d->Cout, Cin_w, t.entries, chan_map, t.cin_chunks, t.ksteps, t.NB, t.nblk,

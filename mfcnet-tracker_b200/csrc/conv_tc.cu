@@ -430,6 +430,11 @@ __device__ __forceinline__ int stat_channel(int lane) {
 // path (fewer instructions, and a smaller hot loop for the instruction cache); anything else runs GENERIC.
 enum : int { EPI_PLAIN = 0, EPI_STATS = 1, EPI_RES = 2, EPI_NCHW = 3, EPI_GENERIC = 4 };
 
+__device__ __forceinline__ float lds_f1(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -441,6 +446,12 @@ struct ItemCoord {
 };
 __device__ __forceinline__ ItemCoord decode_item(const ConvParams& p, int w) {
   ItemCoord c;
+  if (p.chunk > 1 && w < p.full_items) {  // sequence index (round k, CTA j) -> chunked item index
+    const uint32_t k = fdiv((uint32_t)w, p.div_grid);
+    const uint32_t j = (uint32_t)w - k * p.div_grid.d;
+    const uint32_t kc = fdiv(k, p.div_chunk);
+    w = (int)((kc * p.div_grid.d + j) * (uint32_t)p.chunk + (k - kc * (uint32_t)p.chunk));
+  }
   if (p.reverse) w = p.total_items - 1 - w;
   uint32_t tile = fdiv((uint32_t)w, p.div_nblk);
   c.nbk = w - (int)tile * p.t.nblk;
@@ -810,8 +821,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
 // pixel = pix0 + r*128, valid <=> r*128 + lane index < rows*Wout).  No division, no per-sub-step address rebuild; with acc_init
 // the values leave TMEM finished (no scale/shift pass).  Same order of operations as epilogue_tile (same bits).
 template <bool BF16, int MODE>
-__device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t tmem_acc, uint32_t s_shift_addr, float (&d1)[16],
-                                                   float (&d2)[16], int b, int oy0, int ox0, int lq, int half, int lane, float& omax) {
+__device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t tmem_acc, uint32_t s_shift_addr, uint32_t s_head_addr,
+                                                   float (&d1)[16], float (&d2)[16], int b, int oy0, int ox0, int lq, int half, int lane,
+                                                   float& omax) {
   constexpr bool kStats = MODE == EPI_STATS;
   constexpr bool kNchw = MODE == EPI_NCHW;
   constexpr bool kPrefetch = !kStats;   // the statistics accumulators leave no room for a second accumulator array
@@ -841,10 +853,12 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
   }
   const bool has_c8 = !kNchw || p.y != nullptr;
   const bool has_nchw = kNchw && p.y_nchw != nullptr;
+  const int head_n = kNchw ? p.head_n : 0;            // > 0: fused 1x1 head, y_nchw gets head_n channels
+  const int n_out = head_n > 0 ? head_n : Cout;
   uint8_t* const yp = has_c8 ? p.y + (size_t)b * p.y_bs + (size_t)pix0 * 16 : nullptr;
   const size_t plane = (size_t)HWo * 16;
   const bool two_planes = Cout > 8;
-  float* const np = has_nchw ? p.y_nchw + (size_t)b * Cout * HWo + pix0 : nullptr;
+  float* const np = has_nchw ? p.y_nchw + (size_t)b * n_out * HWo + pix0 : nullptr;
   const uint32_t tm_lane = tmem_acc + ((uint32_t)(lq * 32) << 16);
 
   auto load = [&](int rr, uint32_t (&a)[32]) {
@@ -929,9 +943,26 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
     }
     if (kNchw && has_nchw) {
       float* q = np + poff;
+      if (head_n > 0) {
+        // second linear layer on the values in registers, fp32 throughout: head_w rows of 16 floats + bias in shared memory
+        for (int n = 0; n < head_n; ++n) {
+          const uint32_t wa = s_head_addr + (uint32_t)n * 64u;
+          float o0 = lds_f1(s_head_addr + 512u + (uint32_t)n * 4u), o1 = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < Cout) q[(size_t)i * HWo] = f[i];
+          for (int i = 0; i < 16; i += 4) {
+            const float4 w = lds_f4(wa + i * 4);
+            o0 = fmaf(w.x, f[i + 0], o0);
+            o1 = fmaf(w.y, f[i + 1], o1);
+            o0 = fmaf(w.z, f[i + 2], o0);
+            o1 = fmaf(w.w, f[i + 3], o1);
+          }
+          q[(size_t)n * HWo] = o0 + o1;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < Cout) q[(size_t)i * HWo] = f[i];
+      }
     }
   };
   auto process = [&](uint32_t (&a)[32], int rr) {
@@ -1059,6 +1090,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     }
     if (p.stats)
       for (int i = tid; i < kEpiWarps * cpad * 2; i += kConvThreads) s_stats[i] = 0.0f;
+    if (FAST && MODE == EPI_NCHW && p.head_w != nullptr) {
+      // fused head: [8][16] weights then [8] biases, parked in the statistics scratch (1 KB at cpad 16; no stats in this mode)
+      for (int i = tid; i < 8 * 16; i += kConvThreads) s_stats[i] = i < p.head_n * 16 ? __ldg(p.head_w + i) : 0.0f;
+      for (int i = tid; i < 8; i += kConvThreads) s_stats[128 + i] = (p.head_b != nullptr && i < p.head_n) ? __ldg(p.head_b + i) : 0.0f;
+    }
   }
   if (p.t.pair) {
     // tap pairing: the second K half of the last horizontal pair of an odd-width kernel reads one slot past
@@ -1360,8 +1396,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
       if (!(p.debug & 2)) {
         if constexpr (FAST)
-          epilogue_tile_fast<BF16, MODE>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_shift), d1, d2, c.b, c.oy0, c.ox0, lq,
-                                         half, lane, omax);
+          epilogue_tile_fast<BF16, MODE>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_shift), smem_u32(s_stats), d1, d2, c.b,
+                                         c.oy0, c.ox0, lq, half, lane, omax);
         else
           epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
                                           c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem, rp, total_items, omax);
@@ -1653,7 +1689,10 @@ void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling
   conv_enumerate(d, all);
   std::stable_sort(all.begin(), all.end(),
                    [](const std::pair<double, ConvTiling>& a, const std::pair<double, ConvTiling>& b) { return a.first < b.first; });
-  int taken[2][3][3] = {};
+  // buckets: formulation x ring depth class x N-block width x (single / split K stage) x (full-width tiles or not).
+  // The last two matter for the halo-free multi-source 1x1 layers, where the model's favourites (all K planes in one
+  // stage, narrow tiles) leave no room for a deep ring.
+  int taken[2][3][3][2][2] = {};
   int nb_seen[3] = {0, 0, 0};
   for (const auto& c : all) {
     const ConvTiling& t = c.second;
@@ -1662,7 +1701,7 @@ void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling
     while (nbi < 3 && nb_seen[nbi] != 0 && nb_seen[nbi] != t.NB) ++nbi;
     if (nbi == 3) continue;
     nb_seen[nbi] = t.NB;
-    int& n = taken[t.slide ? 1 : 0][depth][nbi];
+    int& n = taken[t.slide ? 1 : 0][depth][nbi][t.kstages > 1 ? 1 : 0][t.tiles_x == 1 ? 1 : 0];
     if (n >= per_bucket) continue;
     ++n;
     out.push_back(t);

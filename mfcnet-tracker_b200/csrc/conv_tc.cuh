@@ -83,12 +83,18 @@ struct ConvParams {
   long long y_bs;
   float* y_nchw;
   float* stats;
+  const float* head_w;   // fused 1x1 head (fast NCHW epilogue only): [head_n][16] weights, [head_n] bias (or NULL), see MfcConvIO
+  const float* head_b;
+  int head_n;
   int* ovf;       // fp16 outputs only: incremented by every epilogue warp that stored a value beyond +-65504 (or NULL)
   alignas(64) CUtensorMap tmap[MFC_MAX_SRC];  // t.tma: source i as the 5-D tensor (8 ch, W, H, chunk, sample)
   int acc_init;   // slide mode without an epilogue scale: the accumulators are initialised with the per-channel shift (instead of
                   // zeros) at kernel start and whenever the epilogue drains them, so values leave TMEM finished
   int epi_fast;   // NB == 16, one N-block, out_stride 1, and the pixel of (run, lane) is affine in the run index: sliding mode
                   // (a run = one output row) or full-width tiles of a halo-free conv (a run = 128 consecutive pixels)
+  int chunk;             // work items are dealt to the CTAs in chunks of `chunk` consecutive items (same sample, adjacent tiles):
+  int full_items;        // fewer GroupNorm-record flushes and sample switches per CTA; items >= full_items (the tail) go round-robin
+  FastDiv div_grid, div_chunk;
   int reverse, total_items;  // reverse: walk the work items from the last sample to the first (see MFC_CONV_REVERSE_ORDER)
   int debug;  // measurement only (MFC_CONV_DEBUG): bit0 skip producer copies, bit1 skip epilogue body, bit2 skip MMAs,
               // bit3 role timing; bit4 (MFC_SILU_ACCURATE=1): two-MUFU SiLU instead of tanh.approx

@@ -34,6 +34,11 @@ def autotune_enabled():
     return os.environ.get("MFC_CONV_TUNE", "0") == "1"
 
 
+def head_fusion_enabled():
+    """MFC_CONV_HEAD=0: keep a network's final 1x1 conv as its own launch (measurement switch)."""
+    return os.environ.get("MFC_CONV_HEAD", "1") != "0"
+
+
 def snake_enabled():
     return os.environ.get("MFC_CONV_SNAKE", "1") != "0"
 
@@ -623,16 +628,38 @@ class Builder:
         self.tdtype = self.prog.tdtype
 
     def conv(self, key, srcs, w_oihw, k, *, bias=None, scale=None, shift=None, stride=1, pad=0, upsample=1, act=0,
-             residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None, parity=None):
+             residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None, parity=None,
+             head=None):
         """srcs: list of Act (channel concat in order).  w_oihw: fp32 device weight whose Cin axis
         is the concat of the sources' REAL channels (or, with first_weight_channel=[...], starts
-        at the given offsets).  Returns (Act|None, stats|None, info, io)."""
+        at the given offsets).  head=(w [Nh, Cout] fp32, bias [Nh] or None): a following 1x1 conv evaluated in fp32 inside this
+        conv's epilogue (MfcConvIO.head_w; Cout <= 16), `out_nchw` then has Nh channels.  Returns (Act|None, stats|None, info, io)."""
         Cout = w_oihw.shape[0]
+        # A halo-free stride-1 conv (1x1) does not care about the 2-D geometry of its planes: present every plane as an
+        # image 128 pixels wide (H*W/128 rows).  Tiles then span the full width, so a tile of R rows IS R MMA runs of 128
+        # consecutive pixels, one contiguous TMA box per plane (R*2 KB) instead of TH short row segments, and the epilogue's
+        # pixel addresses are affine in the run index.  Pure re-interpretation: same bytes, same arithmetic.
+        H0, W0 = srcs[0].H, srcs[0].W
+        flat = (k == 1 and stride == 1 and upsample == 1 and pad == 0 and parity is None and W0 != 128 and (H0 * W0) % 128 == 0
+                and os.environ.get("MFC_CONV_FLAT", "1") != "0")
+        if flat:
+            rows = H0 * W0 // 128
+
+            def fl(a):
+                return None if a is None else Act(a.t.view(a.t.shape[0], a.t.shape[1], rows, 128, 8), a.C, a.affine)
+            srcs = [fl(a) for a in srcs]
+            residual = fl(residual)
+            if y_c8 is not None:
+                y_c8 = y_c8.view(y_c8.shape[0], y_c8.shape[1], rows, 128, 8)
+            if out_nchw is not None:
+                out_nchw = out_nchw.view(out_nchw.shape[0], out_nchw.shape[1], rows, 128)
         d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity)
         if residual is not None:
             d.reserved |= abi.MFC_CONV_HAS_RESIDUAL
         if want_stats:
             d.reserved |= abi.MFC_CONV_WANT_STATS
+        if head is not None:
+            d.reserved |= abi.MFC_CONV_WANT_HEAD
         layout = []
         off = 0
         for i, s in enumerate(srcs):
@@ -644,14 +671,29 @@ class Builder:
         if shift is None and bias is not None:
             shift = bias
         if autotune_enabled() and self.device.type == "cuda" and not abi.plan_only():
-            self._autotune(d, srcs, w_oihw, cmap, False, shift is not None, residual, want_stats, out_c8, out_nchw, y_c8)
+            self._autotune(d, srcs, w_oihw, cmap, False, shift is not None, residual, want_stats, out_c8, out_nchw, y_c8,
+                           None if head is None else head[0].shape[0])
         info = self.prog.query(d)
         packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift)
         out, stats, io = self.prog.conv(d, info, srcs, packed, residual=residual, want_stats=want_stats, out_c8=out_c8,
                                         out_nchw=out_nchw, arena=self.arena, y_c8=y_c8, name=key)
+        if head is not None:
+            hw, hb = head
+            nh = hw.shape[0]
+            w16 = torch.zeros((nh, 16), dtype=torch.float32, device=self.device)
+            w16[:, :Cout] = hw.detach().float().reshape(nh, Cout)
+            hbf = hb.detach().float().contiguous() if hb is not None else None
+            io.head_w, io.head_b, io.head_n = w16.data_ptr(), abi.ptr(hbf), nh
+            self.prog.keep += [w16, hbf]
+            self.packer._dirty = True          # read before griddepcontrol.wait, like the packed weights
+            m = self.prog.meta[-1]
+            m["flops"] += 2 * d.B * d.Hout * d.Wout * Cout * nh
+            m["bytes"] += d.B * d.Hout * d.Wout * (4 * nh - 4 * Cout)   # the fp32 map written has nh channels, not Cout
+        if flat and out is not None:
+            out = Act(out.t.view(out.t.shape[0], out.t.shape[1], H0, W0, 8), out.C, out.affine)
         return out, stats, info, io
 
-    def _autotune(self, d, srcs, w_oihw, cmap, has_scale, has_shift, residual, want_stats, out_c8, out_nchw, y_c8):
+    def _autotune(self, d, srcs, w_oihw, cmap, has_scale, has_shift, residual, want_stats, out_c8, out_nchw, y_c8, head_n=None):
         """Plan-time measurement of the candidate tilings of this conv on the device, with buffers of the real sizes and
         the real epilogue mode (mfc_conv2d_autotune keeps the fastest; temporaries are released afterwards)."""
         lib = self.prog.lib
@@ -681,6 +723,8 @@ class Builder:
             io.y_batch_stride = y.stride(0) * y.element_size()
         if out_nchw is not None:
             io.y_nchw = out_nchw.data_ptr()
+        if head_n is not None:
+            io.head_w, io.head_n = tmp((head_n, 16), torch.float32, 0.0).data_ptr(), head_n
         if want_stats:
             io.stats = tmp((d.B, 148, cpad, 2), torch.float32).data_ptr()
         w = w_oihw.detach().contiguous().float()

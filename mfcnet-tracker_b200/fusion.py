@@ -41,13 +41,23 @@ def _stack(in_ch, N, K):
 
 
 def record_stack(bld, name, seq, srcs, first_weight_channel, out_nchw):
-    """Records the 4-conv fusion stack over concat sources `srcs`; the last conv writes fp32 NCHW."""
+    """Records the 4-conv fusion stack over concat sources `srcs`; the result is written as fp32 NCHW.
+    With at most 16 stack channels (N*K <= 16: the 3-frame, 5-class configuration) the final bias-free 1x1 conv is
+    evaluated in fp32 inside the third conv's epilogue (Builder.conv(head=...)): one launch and one tensor round trip less,
+    and the last activation / weights are never rounded to fp16."""
     x = srcs
     fwc = first_weight_channel
-    for ci, bi in ((0, 1), (3, 4), (6, 7)):
+    layers = ((0, 1), (3, 4), (6, 7))
+    for li, (ci, bi) in enumerate(layers):
         conv, bn = seq[ci], seq[bi]
         sc, sh = bld.packer.bn_affine("%s.%d" % (name, bi), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
         k = conv.kernel_size[0]
+        last = li == len(layers) - 1
+        if last and conv.out_channels <= 16 and seq[9].bias is None and engine.head_fusion_enabled():
+            _, _, _, io = bld.conv("%s.%d+9" % (name, ci), x, conv.weight, k, scale=sc, shift=sh, pad=conv.padding[0], act=1,
+                                   first_weight_channel=fwc, out_c8=False, out_nchw=out_nchw,
+                                   head=(seq[9].weight.detach().reshape(seq[9].out_channels, -1), None))
+            return io
         y, _, _, _ = bld.conv("%s.%d" % (name, ci), x, conv.weight, k, scale=sc, shift=sh, pad=conv.padding[0], act=1,
                               first_weight_channel=fwc)
         x, fwc = [y], None

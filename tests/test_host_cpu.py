@@ -168,9 +168,9 @@ def test_mfcnet_wrapper_keys_and_plan(M, variant):
     y = net(xs, optflow=[torch.zeros(2, 2, 64, 96)] * 2, depth=[torch.zeros(2, 1, 64, 96)] * 3)
     assert y.shape == (2, 5, 64, 96)
     plan = net._plans[(2, 64, 96)]
-    # 3 frame gathers + SFC passes of 59 launches + aux gather (large) or warp (basic) + 4 fusion convs
+    # 3 frame gathers + SFC passes of 59 launches + aux gather (large) or warp (basic) + 3 fusion convs (the final 1x1 is fused into the third)
     n_sfc = (3 * 2) // plan["sub_batch"]
-    assert plan["prog"].n_kernels == 3 + 59 * n_sfc + 1 + 4
+    assert plan["prog"].n_kernels == 3 + 59 * n_sfc + 1 + 3
     with pytest.raises(ValueError):
         net(xs)                                    # flow / depth missing
     with pytest.raises(RuntimeError):

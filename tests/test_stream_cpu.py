@@ -94,11 +94,11 @@ def test_streaming_runner_plans(monkeypatch):
             dp = [torch.zeros(1, 1, 64, 96)] * 3
             outs = [run.step(torch.zeros(1, 3, 64, 96), fl, dp) for _ in range(5)]
             assert outs[0] is None and outs[1] is None and all(o.shape == (1, 5, 64, 96) for o in outs[2:])
-            assert run.launches_per_frame == 60 + 5   # 1 gather + 59 SFC launches, aux gather/warp + 4 fusion convs
+            assert run.launches_per_frame == 60 + 4   # 1 gather + 59 SFC launches, aux gather/warp + 3 fusion convs
             # B clips in lock step: same launches, batch-B buffers
             run4 = StreamingMFCNet(net, 64, 96, device="cpu", batch=4)
             fl4, dp4 = [torch.zeros(4, 2, 64, 96)] * 2, [torch.zeros(4, 1, 64, 96)] * 3
             outs = [run4.step(torch.zeros(4, 3, 64, 96), fl4, dp4) for _ in range(4)]
-            assert outs[1] is None and outs[2].shape == (4, 5, 64, 96) and run4.launches_per_frame == 60 + 5
+            assert outs[1] is None and outs[2].shape == (4, 5, 64, 96) and run4.launches_per_frame == 60 + 4
     finally:
         m.abi._lib = None

@@ -29,7 +29,7 @@ def from_c8(t, Cc):
 
 
 def run_case(dt, B, H, W, cins, Cout, k, stride=1, pad=None, ups=1, act=0, bias=True, scale=False, residual=False,
-             res_affine=False, src_affine=False, stats=False, seed=0):
+             res_affine=False, src_affine=False, stats=False, head=0, seed=0):
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(seed)
     tdtype = engine._DTYPES[dt][0]
@@ -79,13 +79,20 @@ def run_case(dt, B, H, W, cins, Cout, k, stride=1, pad=None, ups=1, act=0, bias=
         ref = ref + rq
     if act:
         ref = F.relu(ref)
-    out_nchw = torch.full((B, Cout, Ho, Wo), float("nan"), device=dev)
+    hd = None
+    if head:   # fused fp32 1x1 head: out_nchw holds `head` channels = hw @ v + hb
+        hw = (torch.randn(head, Cout, generator=g) / Cout ** 0.5).to(dev)
+        hb = (0.1 * torch.randn(head, generator=g)).to(dev)
+        hd = (hw, hb)
+    out_nchw = torch.full((B, head or Cout, Ho, Wo), float("nan"), device=dev)
     out, st, info, io = bld.conv("c", acts, w, k, bias=b, scale=sc, stride=stride, pad=pad, upsample=ups, act=act,
-                                 residual=res_act, want_stats=stats, out_nchw=out_nchw)
+                                 residual=res_act, want_stats=stats, out_nchw=out_nchw, head=hd)
     bld.prog.run()
     torch.cuda.synchronize()
-    e_nchw = (out_nchw - ref).abs().max().item()
     e_c8 = (from_c8(out.t, Cout) - ref).abs().max().item()
+    if head:
+        ref = torch.einsum("nc,bchw->bnhw", hw, ref) + hb[None, :, None, None]
+    e_nchw = (out_nchw - ref).abs().max().item()
     res = {"dt": dt, "B": B, "H": H, "W": W, "cins": cins, "Cout": Cout, "k": k, "s": stride, "ups": ups,
            "tile": [info.tile_h, info.tile_w], "R": info.runs, "kst": info.kstages, "nb": info.nb, "nblk": info.nblk,
            "err_nchw": e_nchw, "err_c8": e_c8, "ref_absmax": ref.abs().max().item()}
@@ -126,6 +133,9 @@ CASES = [
     dict(B=2, H=37, W=131, cins=[16], Cout=16, k=3, stats=True, src_affine=True),
     dict(B=1, H=5, W=7, cins=[16], Cout=16, k=3, stats=True),
     dict(B=2, H=480, W=640, cins=[15], Cout=5, k=1, bias=False),
+    dict(B=2, H=33, W=47, cins=[15], Cout=15, k=3, act=1, scale=True, head=5),
+    dict(B=2, H=480, W=640, cins=[15], Cout=15, k=3, act=1, scale=True, head=5),
+    dict(B=1, H=64, W=96, cins=[16, 16], Cout=16, k=1, head=3),
 ]
 
 
