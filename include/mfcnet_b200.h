@@ -186,6 +186,9 @@ typedef struct MfcConvIO {
    * evaluated in fp32 on the values still in registers: the conv's own output need not be stored (y_c8 may be NULL) and the
    * last activation / weights of a network are never rounded to fp16 (models/multiframe_model.py:72-73: the fusion head's
    * final 1x1 conv).  Needs the descriptor flag MFC_CONV_WANT_HEAD, Cout <= 16, y_nchw, no stats / residual. */
+  void* y_lo;                /* NULL, or a second C8 output (geometry / stride of y_c8) receiving the rounding residue
+                                v - fp(v) of every stored value: [y_c8, y_lo] read as two concat sources with the same weights
+                                carry the activation to ~22 bits (a network's last hidden activation)                    */
   const float* head_w;       /* [head_n][16] fp32 (device; columns >= Cout zero) or NULL */
   const float* head_b;       /* [head_n] or NULL                                         */
   int head_n;
@@ -265,6 +268,9 @@ typedef struct MfcFuseArgs {
   void* out;
   long long out_batch_stride;
   int* overflow;            /* fp16 range guard counter or NULL (see MfcConvIO.overflow) */
+  void* out_lo;             /* NULL, or a second C8 tensor (same geometry / stride as `out`) that receives the rounding
+                               residue v - fp(v): a consumer that reads [out, out_lo] as two concat sources with the same
+                               weights sees the value to ~22 bits (used for a network's last activation) */
 } MfcFuseArgs;
 int mfc_fuse_sum(const MfcFuseArgs* a, void* stream);
 

@@ -47,7 +47,7 @@ class MfcConvDesc(C.Structure):
 class MfcConvIO(C.Structure):
     _fields_ = [("w_packed", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("residual", c_void_p),
                 ("res_affine", c_void_p), ("res_batch_stride", c_ll), ("y_c8", c_void_p), ("y_batch_stride", c_ll),
-                ("y_nchw", c_void_p), ("stats", c_void_p), ("head_w", c_void_p), ("head_b", c_void_p), ("head_n", c_int), ("reserved", c_int),
+                ("y_nchw", c_void_p), ("stats", c_void_p), ("y_lo", c_void_p), ("head_w", c_void_p), ("head_b", c_void_p), ("head_n", c_int), ("reserved", c_int),
                 ("overflow", c_void_p)]
 
 
@@ -82,7 +82,7 @@ class MfcFuseTerm(C.Structure):
 class MfcFuseArgs(C.Structure):
     _fields_ = [("B", c_int), ("chunks", c_int), ("H", c_int), ("W", c_int), ("nterms", c_int), ("act", c_int),
                 ("dtype", c_int), ("reserved", c_int), ("term", MfcFuseTerm * MFC_MAX_SRC), ("scale", c_void_p),
-                ("shift", c_void_p), ("out", c_void_p), ("out_batch_stride", c_ll), ("overflow", c_void_p)]
+                ("shift", c_void_p), ("out", c_void_p), ("out_batch_stride", c_ll), ("overflow", c_void_p), ("out_lo", c_void_p)]
 
 
 class MfcResizeArgs(C.Structure):

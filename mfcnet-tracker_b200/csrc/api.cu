@@ -285,6 +285,8 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.res_aff = io->res_affine;
   p.res_bs = io->res_batch_stride;
   p.y = (uint8_t*)io->y_c8;
+  p.y_lo = (uint8_t*)io->y_lo;
+  if (io->y_lo && (!io->y_c8 || ((uintptr_t)io->y_lo & 15))) return fail(MFC_EINVAL, "conv: y_lo needs y_c8 and 16-byte alignment");
   p.y_bs = io->y_batch_stride;
   p.y_nchw = io->y_nchw;
   p.stats = io->stats;

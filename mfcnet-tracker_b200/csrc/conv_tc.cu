@@ -710,6 +710,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
             for (int i = 0; i < 8; ++i) g[i] = f[h * 8 + i];
             uint4 ov = pack8<BF16>(g);
             *reinterpret_cast<uint4*>(y_b + (size_t)(off0 + (uint32_t)h * HWo) * 16) = ov;
+            if (p.y_lo != nullptr) {  // rounding residue v - fp(v) (see MfcConvIO.y_lo)
+              float hh[8];
+              unpack8<BF16>(ov, hh);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hh[i] = g[i] - hh[i];
+              *reinterpret_cast<uint4*>(p.y_lo + (size_t)b * p.y_bs + (size_t)(off0 + (uint32_t)h * HWo) * 16) = pack8<BF16>(hh);
+            }
           }
         }
       }
@@ -858,6 +865,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
   uint8_t* const yp = has_c8 ? p.y + (size_t)b * p.y_bs + (size_t)pix0 * 16 : nullptr;
   const size_t plane = (size_t)HWo * 16;
   const bool two_planes = Cout > 8;
+  const ptrdiff_t lo_delta = (has_c8 && p.y_lo != nullptr) ? p.y_lo - p.y : 0;
   float* const np = has_nchw ? p.y_nchw + (size_t)b * n_out * HWo + pix0 : nullptr;
   const uint32_t tm_lane = tmem_acc + ((uint32_t)(lq * 32) << 16);
 
@@ -931,14 +939,21 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
         for (int i = 0; i < 16; i += 2) omax = fmaxf(fmaxf(omax, fabsf(f[i])), fabsf(f[i + 1]));
       }
       uint8_t* q = yp + (size_t)poff * 16;
-      float g[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = f[i];
-      *reinterpret_cast<uint4*>(q) = pack8<BF16>(g);
-      if (two_planes) {
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two_planes) break;
+        float g[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = f[8 + i];
-        *reinterpret_cast<uint4*>(q + plane) = pack8<BF16>(g);
+        for (int i = 0; i < 8; ++i) g[i] = f[h * 8 + i];
+        const uint4 ov = pack8<BF16>(g);
+        *reinterpret_cast<uint4*>(q + (h ? plane : 0)) = ov;
+        if (lo_delta != 0) {  // rounding residue v - fp(v) into the second output (see MfcConvIO.y_lo)
+          float hh[8];
+          unpack8<BF16>(ov, hh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hh[i] = g[i] - hh[i];
+          *reinterpret_cast<uint4*>(q + (h ? plane : 0) + lo_delta) = pack8<BF16>(hh);
+        }
       }
     }
     if (kNchw && has_nchw) {

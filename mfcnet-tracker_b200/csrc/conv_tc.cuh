@@ -80,6 +80,7 @@ struct ConvParams {
   const float* res_aff;
   long long res_bs;
   uint8_t* y;
+  uint8_t* y_lo;   // optional rounding-residue output (same geometry as y)
   long long y_bs;
   float* y_nchw;
   float* stats;

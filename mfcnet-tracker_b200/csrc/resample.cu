@@ -32,6 +32,7 @@ struct FuseParams {
   uint8_t* out;
   long long out_bs;
   int* ovf;
+  uint8_t* out_lo;
 };
 
 template <bool BF16>
@@ -89,7 +90,16 @@ __global__ void fuse_sum_kernel(const __grid_constant__ FuseParams p) {
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) omax = fmaxf(omax, fabsf(acc[e]));
-    *reinterpret_cast<uint4*>(p.out + (long long)b * p.out_bs + ((long long)ch * pixels + pix) * 16) = pack8<BF16>(acc);
+    const uint4 hi = pack8<BF16>(acc);
+    const long long off = (long long)b * p.out_bs + ((long long)ch * pixels + pix) * 16;
+    *reinterpret_cast<uint4*>(p.out + off) = hi;
+    if (p.out_lo) {  // rounding residue, exactly representable differences rounded once more
+      float h[8];
+      unpack8<BF16>(hi, h);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = acc[e] - h[e];
+      *reinterpret_cast<uint4*>(p.out_lo + off) = pack8<BF16>(h);
+    }
   }
   if (!BF16 && p.ovf != nullptr && __any_sync(0xffffffffu, !(omax <= kF16Max)) && (threadIdx.x & 31) == 0) atomicAdd(p.ovf, 1);
 }
@@ -180,7 +190,7 @@ cudaError_t launch_fuse_sum(const MfcFuseArgs& a, cudaStream_t st) {
     p.h[j] = j < a.nterms ? a.term[j].H : 0;
     p.w[j] = j < a.nterms ? a.term[j].W : 0;
   }
-  p.scale = a.scale; p.shift = a.shift; p.out = (uint8_t*)a.out; p.out_bs = a.out_batch_stride; p.ovf = a.overflow;
+  p.scale = a.scale; p.shift = a.shift; p.out = (uint8_t*)a.out; p.out_bs = a.out_batch_stride; p.ovf = a.overflow; p.out_lo = (uint8_t*)a.out_lo;
   const int grid = grid_for((long long)a.B * a.chunks * a.H * a.W, 256);
   if (a.dtype == MFC_BF16) return launch_pdl(fuse_sum_kernel<true>, dim3(grid), dim3(256), 0, st, p);
   return launch_pdl(fuse_sum_kernel<false>, dim3(grid), dim3(256), 0, st, p);

@@ -34,6 +34,24 @@ def autotune_enabled():
     return os.environ.get("MFC_CONV_TUNE", "0") == "1"
 
 
+def hilo_enabled():
+    """MFC_HILO=0: do not carry a network's last hidden activation / last weights as fp16 (hi, lo) pairs (measurement switch)."""
+    return os.environ.get("MFC_HILO", "1") != "0"
+
+
+def hilo_last_conv(bld, key, x, x_lo, w, bias, **kw):
+    """The LAST 1x1 conv of a network with both its activation and its weights carried to ~22 bits through the fp16 tensor core:
+    x = x_hi + x_lo (x_lo = the rounding residue the producer emitted), w = w_hi + w_lo, and
+    w x ~ w_hi x_hi + w_hi x_lo + w_lo x_hi as ONE conv over the sources [x_hi, x_lo, x_hi] with the weights [w | w | w - fp16(w)]
+    (the packer rounds each block to fp16: the first two become w_hi, the third w_lo).  The last layer's rounding noise goes
+    straight into the logits -- nothing downstream averages it -- which is why it is worth three K-blocks instead of one."""
+    tdtype = bld.tdtype
+    wf = w.detach().float()
+    w_lo = wf - wf.to(tdtype).float()
+    wcat = torch.cat([wf, wf, w_lo], 1)
+    return bld.conv(key, [x, x_lo, x], wcat, 1, bias=bias, **kw)
+
+
 def head_fusion_enabled():
     """MFC_CONV_HEAD=0: keep a network's final 1x1 conv as its own launch (measurement switch)."""
     return os.environ.get("MFC_CONV_HEAD", "1") != "0"
@@ -121,10 +139,10 @@ class Ext:
 
 class Act:
     """A C8 activation: tensor [B, chunks, H, W, 8] + real channel count + optional pending affine."""
-    __slots__ = ("t", "C", "affine")
+    __slots__ = ("t", "C", "affine", "lo")
 
     def __init__(self, t, C_, affine=None):
-        self.t, self.C, self.affine = t, C_, affine
+        self.t, self.C, self.affine, self.lo = t, C_, affine, None
 
     @property
     def B(self):
@@ -366,7 +384,7 @@ class Program:
         return info
 
     def conv(self, d, info, srcs, packed, residual=None, want_stats=False, out_c8=True, out_nchw=None, arena=None,
-             y_c8=None, name=""):
+             y_c8=None, name="", want_lo=False):
         """Record one fused conv for descriptor `d` (from conv_desc) / `info` (from query).
         `packed` = PackedConv (weights + scale/shift).  Returns (Act or None, stats or None, io)."""
         io = abi.MfcConvIO()
@@ -390,6 +408,12 @@ class Program:
             io.y_c8 = y_c8.data_ptr()
             io.y_batch_stride = out.bstride
             self.keep.append(y_c8)
+            if want_lo:    # rounding residue of the stored values (MfcConvIO.y_lo): same shape / strides
+                self.lo = arena.alloc(tuple(y_c8.shape), self.tdtype)
+                if self.lo.stride() != y_c8.stride():
+                    raise ValueError("y_lo needs the strides of y_c8")
+                io.y_lo = self.lo.data_ptr()
+                self.keep.append(self.lo)
         if out_nchw is not None:
             io.y_nchw = out_nchw.data_ptr()
             self.keep.append(out_nchw)
@@ -445,7 +469,7 @@ class Program:
                                                     "bytes": 3 * a_act.B * a_act.C * a_act.H * a_act.W * 2})
         return Act(out_t, a_act.C)
 
-    def fuse_sum(self, terms, out_t, C_, scale=None, shift=None, act=1):
+    def fuse_sum(self, terms, out_t, C_, scale=None, shift=None, act=1, out_lo=None):
         """out = act(scale * sum(terms) + shift); terms: Acts at the output size or lower (bilinear
         align_corners=False upsampling on read).  Returns the output Act."""
         a = abi.MfcFuseArgs()
@@ -461,7 +485,12 @@ class Program:
         a.scale, a.shift = abi.ptr(scale), abi.ptr(shift)
         a.out, a.out_batch_stride = out_t.data_ptr(), out_t.stride(0) * out_t.element_size()
         a.overflow = abi.ptr(self._ovf)
-        self.keep += [out_t, scale, shift]
+        if out_lo is not None:
+            if out_lo.shape != out_t.shape or out_lo.stride() != out_t.stride():
+                raise ValueError("fuse_sum: out_lo must match out")
+            a.out_lo = out_lo.data_ptr()
+            nbytes += B * C_ * H * W * 2
+        self.keep += [out_t, scale, shift, out_lo]
         self._push(abi.OP_FUSE_SUM, a, meta={"kind": "fuse_sum", "name": "", "flops": 0, "bytes": nbytes})
         return Act(out_t, C_)
 
@@ -629,7 +658,7 @@ class Builder:
 
     def conv(self, key, srcs, w_oihw, k, *, bias=None, scale=None, shift=None, stride=1, pad=0, upsample=1, act=0,
              residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None, parity=None,
-             head=None):
+             head=None, want_lo=False):
         """srcs: list of Act (channel concat in order).  w_oihw: fp32 device weight whose Cin axis
         is the concat of the sources' REAL channels (or, with first_weight_channel=[...], starts
         at the given offsets).  head=(w [Nh, Cout] fp32, bias [Nh] or None): a following 1x1 conv evaluated in fp32 inside this
@@ -676,7 +705,9 @@ class Builder:
         info = self.prog.query(d)
         packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift)
         out, stats, io = self.prog.conv(d, info, srcs, packed, residual=residual, want_stats=want_stats, out_c8=out_c8,
-                                        out_nchw=out_nchw, arena=self.arena, y_c8=y_c8, name=key)
+                                        out_nchw=out_nchw, arena=self.arena, y_c8=y_c8, name=key, want_lo=want_lo)
+        if want_lo:        # [out, out.lo] as two sources with the same weights = the activation to ~22 bits
+            out.lo = Act(self.prog.lo.view(out.t.shape), out.C)
         if head is not None:
             hw, hb = head
             nh = hw.shape[0]
@@ -690,7 +721,10 @@ class Builder:
             m["flops"] += 2 * d.B * d.Hout * d.Wout * Cout * nh
             m["bytes"] += d.B * d.Hout * d.Wout * (4 * nh - 4 * Cout)   # the fp32 map written has nh channels, not Cout
         if flat and out is not None:
+            lo = out.lo
             out = Act(out.t.view(out.t.shape[0], out.t.shape[1], H0, W0, 8), out.C, out.affine)
+            if lo is not None:
+                out.lo = Act(lo.t.view(out.t.shape), lo.C)
         return out, stats, info, io
 
     def _autotune(self, d, srcs, w_oihw, cmap, has_scale, has_shift, residual, want_stats, out_c8, out_nchw, y_c8, head_n=None):

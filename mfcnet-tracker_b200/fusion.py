@@ -59,8 +59,11 @@ def record_stack(bld, name, seq, srcs, first_weight_channel, out_nchw):
                                    head=(seq[9].weight.detach().reshape(seq[9].out_channels, -1), None))
             return io
         y, _, _, _ = bld.conv("%s.%d" % (name, ci), x, conv.weight, k, scale=sc, shift=sh, pad=conv.padding[0], act=1,
-                              first_weight_channel=fwc)
+                              first_weight_channel=fwc, want_lo=last and engine.hilo_enabled())
         x, fwc = [y], None
+    if x[0].lo is not None:     # wider stacks (N*K > 16): the final 1x1 conv sees its input and weights as (hi, lo) pairs
+        _, _, _, io = engine.hilo_last_conv(bld, "%s.9" % name, x[0], x[0].lo, seq[9].weight, seq[9].bias, out_c8=False, out_nchw=out_nchw)
+        return io
     _, _, _, io = bld.conv("%s.9" % name, x, seq[9].weight, 1, out_c8=False, out_nchw=out_nchw)
     return io
 

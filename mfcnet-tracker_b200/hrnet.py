@@ -224,9 +224,15 @@ class HighResolutionNet(nn.Module):
         sc = torch.zeros(cpad, dtype=torch.float32, device=bld.device)
         sh = torch.zeros(cpad, dtype=torch.float32, device=bld.device)
         sc[:ctot], sh[:ctot] = scale, shift
-        z = bld.prog.fuse_sum(terms, bld.arena.alloc(tuple(terms[0].t.shape), bld.tdtype), ctot, scale=sc, shift=sh, act=1)
-        low = bld.arena.alloc((B, self.out_dim, z.H, z.W), torch.float32)
-        bld.conv("last_layer.3", [z], c3.weight, 1, bias=c3.bias, out_c8=False, out_nchw=low)
+        zshape = tuple(terms[0].t.shape)
+        low = bld.arena.alloc((B, self.out_dim, terms[0].H, terms[0].W), torch.float32)
+        if engine.hilo_enabled():
+            z_lo = bld.arena.alloc(zshape, bld.tdtype)
+            z = bld.prog.fuse_sum(terms, bld.arena.alloc(zshape, bld.tdtype), ctot, scale=sc, shift=sh, act=1, out_lo=z_lo)
+            engine.hilo_last_conv(bld, "last_layer.3", z, Act(z_lo, ctot), c3.weight, c3.bias, out_c8=False, out_nchw=low)
+        else:
+            z = bld.prog.fuse_sum(terms, bld.arena.alloc(zshape, bld.tdtype), ctot, scale=sc, shift=sh, act=1)
+            bld.conv("last_layer.3", [z], c3.weight, 1, bias=c3.bias, out_c8=False, out_nchw=low)
         rz = bld.prog.resize(low, z.H * 4, z.W * 4, dst_nchw=logits_nchw, dst_c8=maps_c8)
         return None, rz
 

@@ -36,6 +36,9 @@ CASES = [
     dict(name="B1 hrnet 48->48 k3 relu 120x160", B=1, H=120, W=160, cins=[48], Cout=48, k=3, act=1),
     dict(name="B1 hrnet 192->192 k3 relu 30x40", B=1, H=30, W=40, cins=[192], Cout=192, k=3, act=1),
     dict(name="B1 16->16 k3 aff+stats 480x640", B=1, H=480, W=640, cins=[16], Cout=16, k=3, stats=True, aff=True),
+    # round 2: residual-as-source 1x1 (h2 enters as a third source with GroupNorm+SiLU on load), statistics without transform
+    dict(name="B24 48->16 k1 (x, skip, silu(GN(h2)))", B=24, H=480, W=640, cins=[16, 16, 16], Cout=16, k=1, aff_last=True),
+    dict(name="B24 16->16 k3 stats", B=24, H=480, W=640, cins=[16], Cout=16, k=3, stats=True),
 ]
 
 
@@ -54,7 +57,7 @@ def run(case, iters):
     for ci in cins:
         t = torch.randn(B, (ci + 7) // 8, H, W, 8, device=dev).to(tdtype)
         a = Act(t, ci)
-        if c.get("aff"):
+        if c.get("aff") or (c.get("aff_last") and len(acts) == len(cins) - 1):
             aff = torch.zeros(B, ((ci + 7) // 8) * 8, 2, device=dev)
             aff[..., 0] = 1.0
             a = a.with_affine(aff)

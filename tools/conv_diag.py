@@ -29,7 +29,7 @@ def from_c8(t, Cc):
 
 
 def run_case(dt, B, H, W, cins, Cout, k, stride=1, pad=None, ups=1, act=0, bias=True, scale=False, residual=False,
-             res_affine=False, src_affine=False, stats=False, head=0, seed=0):
+             res_affine=False, src_affine=False, stats=False, head=0, lo=False, seed=0):
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(seed)
     tdtype = engine._DTYPES[dt][0]
@@ -86,16 +86,19 @@ def run_case(dt, B, H, W, cins, Cout, k, stride=1, pad=None, ups=1, act=0, bias=
         hd = (hw, hb)
     out_nchw = torch.full((B, head or Cout, Ho, Wo), float("nan"), device=dev)
     out, st, info, io = bld.conv("c", acts, w, k, bias=b, scale=sc, stride=stride, pad=pad, upsample=ups, act=act,
-                                 residual=res_act, want_stats=stats, out_nchw=out_nchw, head=hd)
+                                 residual=res_act, want_stats=stats, out_nchw=out_nchw, head=hd, want_lo=lo)
     bld.prog.run()
     torch.cuda.synchronize()
     e_c8 = (from_c8(out.t, Cout) - ref).abs().max().item()
+    e_hilo = (from_c8(out.t, Cout) + from_c8(out.lo.t, Cout) - out_nchw).abs().max().item() if (lo and not head) else None
     if head:
         ref = torch.einsum("nc,bchw->bnhw", hw, ref) + hb[None, :, None, None]
     e_nchw = (out_nchw - ref).abs().max().item()
     res = {"dt": dt, "B": B, "H": H, "W": W, "cins": cins, "Cout": Cout, "k": k, "s": stride, "ups": ups,
            "tile": [info.tile_h, info.tile_w], "R": info.runs, "kst": info.kstages, "nb": info.nb, "nblk": info.nblk,
            "err_nchw": e_nchw, "err_c8": e_c8, "ref_absmax": ref.abs().max().item()}
+    if e_hilo is not None:     # hi + lo planes against the kernel's own fp32 output: ~2^-22 relative
+        res["err_hilo"] = e_hilo
     if stats:
         s = st.double().sum(1)  # [B, cpad, 2]
         rs = torch.stack([ref.double().sum((2, 3)), (ref.double() ** 2).sum((2, 3))], -1)
@@ -136,6 +139,8 @@ CASES = [
     dict(B=2, H=33, W=47, cins=[15], Cout=15, k=3, act=1, scale=True, head=5),
     dict(B=2, H=480, W=640, cins=[15], Cout=15, k=3, act=1, scale=True, head=5),
     dict(B=1, H=64, W=96, cins=[16, 16], Cout=16, k=1, head=3),
+    dict(B=2, H=33, W=47, cins=[25], Cout=25, k=3, act=1, scale=True, lo=True),
+    dict(B=2, H=40, W=56, cins=[16], Cout=16, k=3, lo=True),
 ]
 
 
@@ -160,7 +165,8 @@ def main():
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/conv_diag.json", "w") as f:
         json.dump(out, f, indent=1)
-    bad = [r for r in out if "error" in r or r.get("err_nchw", 1) > 5e-3 * max(1.0, r.get("ref_absmax", 1.0))]
+    bad = [r for r in out if "error" in r or r.get("err_nchw", 1) > 5e-3 * max(1.0, r.get("ref_absmax", 1.0))
+           or r.get("err_hilo", 0.0) > 2e-6 * max(1.0, r.get("ref_absmax", 1.0))]
     print("conv_diag: %d cases, %d bad" % (len(out), len(bad)))
     return 1 if bad else 0
 
