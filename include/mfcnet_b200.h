@@ -380,6 +380,12 @@ int mfc_ingest_depth(const uint8_t* bgr, long long frame_stride_bytes, float* ou
 int mfc_correlation_fwd(const float* first, const float* second, float* out,
                         int B, int C, int H, int W, int max_disp, int stride2, int exact_order,
                         void* stream);
+/* Backward of the cost volume (`_FunctionCorrelation.backward`, models/unflow_correlation.py:339-391; kernels :107-235):
+ *   grad_first [b,c,y,x] = (1/C) sum_d grad_out[b,d,y,x]           * second[b,c,y+dy,x+dx]
+ *   grad_second[b,c,y,x] = (1/C) sum_d grad_out[b,d,y-dy,x-dx]     * first [b,c,y-dy,x-dx]
+ * in the reference's summation order (bit-identical results).  Either gradient pointer may be NULL. */
+int mfc_correlation_bwd(const float* first, const float* second, const float* grad_out, float* grad_first /*or NULL*/,
+                        float* grad_second /*or NULL*/, int B, int C, int H, int W, int max_disp, int stride2, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Key-point extraction (utils/localization_utils_v2.py:5-40).

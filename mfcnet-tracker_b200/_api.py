@@ -1,6 +1,6 @@
 """Public API of the package (re-exported by ``mfcnet_tracker_b200``)."""
 from . import abi, engine
-from .correlation import FunctionCorrelation, ModuleCorrelation, correlation
+from .correlation import FunctionCorrelation, ModuleCorrelation, correlation, correlation_backward
 from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
 from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxima_and_estimate_centroids, gaussian_blur,
                       heatmap_head, predicted_keypoints)
@@ -16,7 +16,7 @@ from .tracking import ToolTracker, class_map, refine_tip_segmentation
 from .train import DataParallelTrainer, autograd_forward, loss_and_grad
 
 __all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic", "HRNetMultiLarge", "TernausNet11", "TernausNet16", "TernausNetMultiBasic", "TernausNetMultiLarge", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
-           "FunctionCorrelation", "ModuleCorrelation", "correlation", "heatmap_head", "create_circular_mask", "calc_centroids",
+           "FunctionCorrelation", "ModuleCorrelation", "correlation", "correlation_backward", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
            "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames", "shard_clips", "segmentation_loss",
            "DataParallelTrainer", "autograd_forward", "loss_and_grad", "ingest_rgb", "ingest_depth", "ToolTracker", "class_map", "refine_tip_segmentation"]

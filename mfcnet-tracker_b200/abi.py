@@ -138,6 +138,7 @@ _SIGNATURES = {
     "mfc_ingest_rgb": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p], c_int),
     "mfc_ingest_depth": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_correlation_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_correlation_bwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_gaussian_blur": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p], c_int),
     "mfc_localmax_mask": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_class_mask": ([c_void_p, c_int, c_void_p, c_ll, c_void_p], c_int),

@@ -213,24 +213,35 @@ EncodeTiledFn encode_tiled_fn() {
 int encode_source_maps(const MfcConvDesc* d, mfc::ConvParams* p) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(MFC_ECUDA, "conv: cuTensorMapEncodeTiled is not available from this driver");
+  static const int no_wide = getenv("MFC_CONV_TMA_WIDE") ? (atoi(getenv("MFC_CONV_TMA_WIDE")) == 0) : 0;  // measurement switch
+  const int box_w = d->upsample == 2 ? p->t.P_lo : p->t.P, box_h = d->upsample == 2 ? p->t.rows_lo : p->t.rows_sub;
+  // Stride 1: a tile row is contiguous in memory (P pixels x 16 bytes).  Described with 16-byte pixels as the innermost
+  // dimension the copy engine walks the box pixel by pixel (measured: ~10 bytes/clk per SM, 2.9 TB/s over the chip); with
+  // 8-byte elements the innermost box dimension is the whole row (up to 256 elements = 128 pixels).
+  p->tma_wide = (!no_wide && d->stride == 1 && box_w * 2 <= 256) ? 1 : 0;
   for (int i = 0; i < d->nsrc; ++i) {
     const cuuint64_t plane = (cuuint64_t)d->Hin * d->Win * 16;
-    cuuint64_t dims[5] = {8, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->src[i].nchunks, (cuuint64_t)d->B};
-    cuuint64_t strides[4] = {16, (cuuint64_t)d->Win * 16, plane,
-                             d->B > 1 ? (cuuint64_t)d->src[i].batch_stride : plane * (cuuint64_t)d->src[i].nchunks};
-    const cuuint32_t st = (cuuint32_t)d->stride;  // stride 2: box extents in tensor elements, every second one is taken
-    cuuint32_t box[5] = {8, (cuuint32_t)p->t.P * st, (cuuint32_t)p->t.rows_sub * st, 1, 1};
-    if (d->upsample == 2) {  // the low-resolution tile; the producer warps expand it x2 in shared memory
-      box[1] = (cuuint32_t)p->t.P_lo;
-      box[2] = (cuuint32_t)p->t.rows_lo;
+    const cuuint64_t bstride = d->B > 1 ? (cuuint64_t)d->src[i].batch_stride : plane * (cuuint64_t)d->src[i].nchunks;
+    CUresult r;
+    if (p->tma_wide) {
+      cuuint64_t dims[4] = {(cuuint64_t)d->Win * 2, (cuuint64_t)d->Hin, (cuuint64_t)d->src[i].nchunks, (cuuint64_t)d->B};
+      cuuint64_t strides[3] = {(cuuint64_t)d->Win * 16, plane, bstride};
+      cuuint32_t box[4] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, 1, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      r = enc(&p->tmap[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(d->src[i].ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[5] = {8, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->src[i].nchunks, (cuuint64_t)d->B};
+      cuuint64_t strides[4] = {16, (cuuint64_t)d->Win * 16, plane, bstride};
+      const cuuint32_t st = (cuuint32_t)d->stride;  // stride 2: box extents in tensor elements, every second one is taken
+      cuuint32_t box[5] = {8, (cuuint32_t)box_w * st, (cuuint32_t)box_h * st, 1, 1};
+      cuuint32_t estr[5] = {1, st, st, 1, 1};
+      r = enc(&p->tmap[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(d->src[i].ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    cuuint32_t estr[5] = {1, st, st, 1, 1};
-    CUresult r = enc(&p->tmap[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(d->src[i].ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
-      return fail(MFC_ECUDA, "conv: cuTensorMapEncodeTiled failed for source %d (CUresult %d; %dx%d, %d chunks, box %dx%d)", i, (int)r,
-                  d->Hin, d->Win, d->src[i].nchunks, p->t.P, p->t.rows_sub);
+      return fail(MFC_ECUDA, "conv: cuTensorMapEncodeTiled failed for source %d (CUresult %d; %dx%d, %d chunks, box %dx%d, wide %d)", i, (int)r,
+                  d->Hin, d->Win, d->src[i].nchunks, box_w, box_h, p->tma_wide);
   }
   return MFC_OK;
 }
@@ -778,6 +789,17 @@ int mfc_correlation_fwd(const float* first, const float* second, float* out, int
       MFC_LAUNCH(mfc::launch_correlation_tma(m1, m2, out, B, C, H, W, stride2, (cudaStream_t)stream), "correlation (tma)");
   }
   MFC_LAUNCH(mfc::launch_correlation(first, second, out, B, C, H, W, max_disp, stride2, exact_order, (cudaStream_t)stream), "correlation");
+}
+
+int mfc_correlation_bwd(const float* first, const float* second, const float* grad_out, float* grad_first, float* grad_second, int B,
+                        int C, int H, int W, int max_disp, int stride2, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!first || !second || !grad_out || (!grad_first && !grad_second) || B < 1 || C < 1 || H < 1 || W < 1)
+    return fail(MFC_EINVAL, "correlation_bwd: bad argument");
+  if (stride2 != 1 && stride2 != 2) return fail(MFC_EINVAL, "correlation_bwd: stride2 %d unsupported (1 or 2)", stride2);
+  if (max_disp < 0 || max_disp > 32 || max_disp % stride2) return fail(MFC_EINVAL, "correlation_bwd: max_disp %d unsupported", max_disp);
+  MFC_LAUNCH(mfc::launch_correlation_bwd(first, second, grad_out, grad_first, grad_second, B, C, H, W, max_disp, stride2, (cudaStream_t)stream),
+             "correlation_bwd");
 }
 
 // ---- key points --------------------------------------------------------------------------------

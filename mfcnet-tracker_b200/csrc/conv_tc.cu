@@ -285,9 +285,15 @@ __device__ __forceinline__ void issue_stage_tma(const ConvParams& p, uint8_t* ab
     }
     uint8_t* plane = abuf + (size_t)q * p.t.plane_bytes;
     if (ups) {  // the low-resolution pixels the upsampled tile maps to: (iy >> 1, ix >> 1), arithmetic shifts (padding rows/columns -> -1)
-      tma_load_5d(abuf + p.t.off_lo + (size_t)q * p.t.lo_plane_bytes, &p.tmap[si], bar, 0, ix_base >> 1, iy_base >> 1, k, b);
+      if (p.tma_wide)
+        tma_load_4d(abuf + p.t.off_lo + (size_t)q * p.t.lo_plane_bytes, &p.tmap[si], bar, (ix_base >> 1) * 2, iy_base >> 1, k, b);
+      else
+        tma_load_5d(abuf + p.t.off_lo + (size_t)q * p.t.lo_plane_bytes, &p.tmap[si], bar, 0, ix_base >> 1, iy_base >> 1, k, b);
     } else if (nsub == 1) {
-      tma_load_5d(plane, &p.tmap[si], bar, 0, ix_base, iy_base, k, b);
+      if (p.tma_wide)
+        tma_load_4d(plane, &p.tmap[si], bar, ix_base * 2, iy_base, k, b);
+      else
+        tma_load_5d(plane, &p.tmap[si], bar, 0, ix_base, iy_base, k, b);
     } else {  // stride 2: sub-plane (py, px) = the pixels (iy_base + 2r + py, ix_base + 2c + px), box traversal stride 2
       for (int sub = 0; sub < 4; ++sub)
         tma_load_5d(plane + (size_t)sub * p.t.slots_sub * 16, &p.tmap[si], bar, 0, ix_base + (sub & 1), iy_base + (sub >> 1), k, b);

@@ -89,6 +89,9 @@ struct ConvParams {
   int head_n;
   int* ovf;       // fp16 outputs only: incremented by every epilogue warp that stored a value beyond +-65504 (or NULL)
   alignas(64) CUtensorMap tmap[MFC_MAX_SRC];  // t.tma: source i as the 5-D tensor (8 ch, W, H, chunk, sample)
+  int tma_wide;   // stride-1 sources are described to TMA as 4-D tensors of 8-byte elements (2 per pixel): the innermost box
+                  // dimension is a whole tile row (P*16 bytes) instead of one 16-byte pixel, i.e. one L2 request stream per
+                  // row instead of one per pixel
   int acc_init;   // slide mode without an epilogue scale: the accumulators are initialised with the per-channel shift (instead of
                   // zeros) at kernel start and whenever the epilogue drains them, so values leave TMEM finished
   int epi_fast;   // NB == 16, one N-block, out_stride 1, and the pixel of (run, lane) is affine in the run index: sliding mode

@@ -213,6 +213,55 @@ static cudaError_t launch_corr_t(const CorrParams& p, int threads, size_t smem, 
   return cudaGetLastError();
 }
 
+// ---- backward ------------------------------------------------------------------------------------------------------
+// kernel_Correlation_updateGradFirst / updateGradSecond (models/unflow_correlation.py:107-235): one thread per input element,
+//   gradFirst [b,c,y,x] = (1/C) sum_{p,o} gradOutput[b,(p,o),y,x]             * second[b,c,y+p*S,x+o*S]
+//   gradSecond[b,c,y,x] = (1/C) sum_{p,o} gradOutput[b,(p,o),y-p*S,x-o*S]     * first [b,c,y-p*S,x-o*S]
+// with the displacement loops in the reference's order (p outer, o inner) and one fused multiply-add per term (nvcc contracts
+// the reference's `sum += a * b` the same way), so the result is bit-identical to the reference kernels'.  Terms that fall
+// outside the image are skipped: the reference multiplies them by the zero padding of its rearranged copies (gradFirst) or
+// skips them too (gradSecond).  gradOutput / the other input are re-read 441 times per element from L1/L2; x is the fastest
+// thread index, so every load is coalesced.
+template <bool SECOND>
+__global__ void __launch_bounds__(256) correlation_bwd_kernel(const float* __restrict__ other, const float* __restrict__ gout,
+                                                             float* __restrict__ grad, int B, int C, int H, int W, int R, int S) {
+  const int D = 2 * R + 1;
+  const long long HW = (long long)H * W;
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const long long bc = i / HW;
+    const int b = (int)(bc / C);
+    const float* oplane = other + bc * HW;
+    const float* g = gout + (long long)b * D * D * HW;
+    float sum = 0.0f;
+    for (int p = -R; p <= R; ++p) {
+      const int yy = SECOND ? y - p * S : y + p * S;
+      if ((unsigned)yy >= (unsigned)H) continue;
+      for (int o = -R; o <= R; ++o) {
+        const int xx = SECOND ? x - o * S : x + o * S;
+        if ((unsigned)xx >= (unsigned)W) continue;
+        const long long op = (long long)((p + R) * D + (o + R)) * HW;
+        const float gv = SECOND ? __ldg(g + op + (long long)yy * W + xx) : __ldg(g + op + (long long)y * W + x);
+        sum = fmaf(gv, __ldg(oplane + (long long)yy * W + xx), sum);
+      }
+    }
+    grad[i] = sum / (float)C;
+  }
+}
+
+cudaError_t launch_correlation_bwd(const float* first, const float* second, const float* grad_out, float* grad_first, float* grad_second,
+                                   int B, int C, int H, int W, int max_disp, int stride2, cudaStream_t st) {
+  const int R = max_disp / stride2;
+  const long long total = (long long)B * C * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kSmCount * 32) blocks = (long long)kSmCount * 32;
+  if (grad_first) correlation_bwd_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(second, grad_out, grad_first, B, C, H, W, R, stride2);
+  if (grad_second) correlation_bwd_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(first, grad_out, grad_second, B, C, H, W, R, stride2);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp,
                                int stride2, int exact_order, cudaStream_t st) {
   const int S = stride2, R = max_disp / stride2, D = 2 * R + 1;

@@ -31,13 +31,6 @@ __device__ __forceinline__ float4 lds_f4s(uint32_t saddr) {
   return v;
 }
 
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
 // Tile = TY output rows x TX = 4*TXG columns; threads = TXG pixel groups x TY/2 row pairs x 10 rows of `second`; NST-deep
 // ring of 8-channel stages.  Narrow tiles (TXG = 8, 16) keep the lanes busy when W is not a multiple of 128 (W = 160 at
 // 1/4 resolution) and run several CTAs per SM.

@@ -59,6 +59,9 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
 cudaError_t launch_correlation(const float* first, const float* second, float* out, int B, int C, int H, int W, int max_disp,
                                int stride2, int exact_order, cudaStream_t st);
 
+cudaError_t launch_correlation_bwd(const float* first, const float* second, const float* grad_out, float* grad_first,
+                                   float* grad_second, int B, int C, int H, int W, int max_disp, int stride2, cudaStream_t st);
+
 // correlation_tma.cu (stride-1, max displacement 4: TMA-fed register-tiled kernel)
 bool correlation_tma_supported(int C, int H, int W, int max_disp, int stride2);
 void correlation_tma_boxes(int H, int W, int stride2, unsigned* box1, unsigned* box2, unsigned* estride);

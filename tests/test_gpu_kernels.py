@@ -108,6 +108,33 @@ def test_correlation_matches_the_reference_kernel_itself(M):
     assert np.array_equal(corr.correlation_c(a, b, 20, 2), ref)
 
 
+def test_correlation_backward_matches_reference_kernel_golden(M):
+    """gradFirst / gradSecond of the reference's own backward kernels (models/unflow_correlation.py:107-235, run through
+    NVRTC on a B200: tests/golden/corr_ref.npz) -- bit for bit, and through torch.autograd (FunctionCorrelation.backward)."""
+    from oracle import make_golden_corr as MG
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "corr_ref.npz"))
+    for tag, B, Cc, H, W in MG.BWD_CASES:
+        a, b = MG.inputs(tag, B, Cc, H, W)
+        g = synth.normal(tag + "/g", (B, 441, H, W), 5)
+        ta = torch.from_numpy(a).cuda().requires_grad_(True)
+        tb = torch.from_numpy(b).cuda().requires_grad_(True)
+        out = M.correlation(ta, tb)
+        out.backward(torch.from_numpy(g).cuda())
+        assert np.array_equal(ta.grad.cpu().numpy(), gold[tag + "/grad_first"]), tag
+        assert np.array_equal(tb.grad.cpu().numpy(), gold[tag + "/grad_second"]), tag
+    # other displacement grids: against autograd of the plain-torch restatement (fp32 rounding only)
+    from oracle import torch_oracle as TO
+    for (B, Cc, H, W, md, s2) in [(2, 16, 12, 14, 4, 1), (1, 8, 9, 20, 6, 2)]:
+        a = torch.randn(B, Cc, H, W, device="cuda")
+        b = torch.randn(B, Cc, H, W, device="cuda")
+        D = 2 * (md // s2) + 1
+        g = torch.randn(B, D * D, H, W, device="cuda")
+        ra, rb = a.clone().double().requires_grad_(True), b.clone().double().requires_grad_(True)
+        TO.correlation(ra, rb, md, s2).backward(g.double())
+        g1, g2 = M.correlation_backward(a, b, g, md, s2)
+        assert float((g1 - ra.grad.float()).abs().max()) <= 2e-6 and float((g2 - rb.grad.float()).abs().max()) <= 2e-6
+
+
 def test_correlation_rejects_cpu(M):
     with pytest.raises(NotImplementedError):
         M.correlation(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8))
