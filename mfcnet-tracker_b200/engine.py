@@ -605,8 +605,9 @@ class WeightPacker:
             self.cache[k] = (scale, shift, args, cb)
         return self.cache[k][0], self.cache[k][1]
 
-    def pack(self, key, prog, desc, info, w_oihw, cmap, scale=None, shift=None):
-        """w_oihw fp32 [Cout][Cin_w][kh][kw] device tensor -> PackedConv for this geometry."""
+    def pack(self, key, prog, desc, info, w_oihw, cmap, scale=None, shift=None, post_scale=None):
+        """w_oihw fp32 [Cout][Cin_w][kh][kw] device tensor -> PackedConv for this geometry.  `scale` is multiplied INTO the
+        weights; `post_scale` (a power of two or None) is applied to the accumulators in the epilogue."""
         k = ("pk", key, info.nb, info.nblk, info.ksteps, info.weight_layout, tuple(cmap) if cmap is not None else None)
         if k not in self.cache:
             w = w_oihw.detach().contiguous().float()
@@ -623,6 +624,8 @@ class WeightPacker:
             if shift is not None:
                 sh = torch.zeros(cpad, dtype=torch.float32, device=self.device)
                 sh[: shift.numel()] = shift.detach().float()
+            if post_scale is not None:
+                sc = torch.full((cpad,), float(post_scale), dtype=torch.float32, device=self.device)
             self.cache[k] = (PackedConv(packed, sc, sh), w, cm, scf)
             # conv_tc_kernel stages weights / scale / shift before its griddepcontrol.wait (they overlap the previous
             # kernel's tail): everything written here must be complete before the first conv launch that uses it
@@ -699,11 +702,21 @@ class Builder:
         cmap = None if identity else chan_map_for(layout)
         if shift is None and bias is not None:
             shift = bias
+        # fp16 has a short exponent: weights below 2^-14 are subnormal (and below 2^-24 vanish).  A layer whose largest
+        # weight is tiny (a down-scaled head) is packed times a power of two and rescaled exactly in the epilogue.
+        post_scale = None
+        if self.prog.dtype_name == "fp16":
+            wmax = float(w_oihw.detach().abs().amax()) * (float(scale.detach().abs().amax()) if scale is not None else 1.0)
+            if 0.0 < wmax < 2.0 ** -6:
+                import math
+                p2 = 2.0 ** min(24, math.floor(-math.log2(wmax)))
+                scale = (scale.detach().float() * p2) if scale is not None else torch.full((Cout,), p2, dtype=torch.float32, device=self.device)
+                post_scale = 1.0 / p2
         if autotune_enabled() and self.device.type == "cuda" and not abi.plan_only():
             self._autotune(d, srcs, w_oihw, cmap, False, shift is not None, residual, want_stats, out_c8, out_nchw, y_c8,
                            None if head is None else head[0].shape[0])
         info = self.prog.query(d)
-        packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift)
+        packed = self.packer.pack(key, self.prog, d, info, w_oihw, cmap, scale, shift, post_scale)
         out, stats, io = self.prog.conv(d, info, srcs, packed, residual=residual, want_stats=want_stats, out_c8=out_c8,
                                         out_nchw=out_nchw, arena=self.arena, y_c8=y_c8, name=key, want_lo=want_lo)
         if want_lo:        # [out, out.lo] as two sources with the same weights = the activation to ~22 bits
