@@ -1143,17 +1143,28 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   if (p.t.slide) {  // every MMA of this mode accumulates: start from initialised accumulators (the epilogue re-initialises
                     // what it drains): zeros, or -- acc_init -- the per-channel shift, column c = [buffer][run][channel c % NB]
     if (warp < 4) {
-      for (uint32_t c = 0; c < p.t.tmem_cols; c += 16) {
-        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + c;
-        if (p.acc_init) {
+      // only the columns the two accumulator buffers use (acc_cols each, a multiple of 16), 32 at a time where possible
+      const uint32_t used = (uint32_t)p.t.nacc * p.t.acc_cols;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+      if (p.acc_init && NB == 16) {  // the same 16 shifts in every 16-column block
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = s_shift[i];
+        uint32_t c = 0;
+        for (; c + 32 <= used; c += 32) tmem_st32v(lane_base + c, v, v);
+        if (c < used) tmem_st16v(lane_base + c, v);
+      } else if (p.acc_init) {
+        for (uint32_t c = 0; c < used; c += 16) {
           float v[16];
           const float* src = s_shift + (c % (uint32_t)NB);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = src[i];
-          tmem_st16v(ta, v);
-        } else {
-          tmem_st16_zero(ta);
+          tmem_st16v(lane_base + c, v);
         }
+      } else {
+        uint32_t c = 0;
+        for (; c + 32 <= used; c += 32) tmem_st32_zero(lane_base + c);
+        if (c < used) tmem_st16_zero(lane_base + c);
       }
       tmem_st_wait();
     }

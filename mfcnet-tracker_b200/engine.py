@@ -34,6 +34,15 @@ def autotune_enabled():
     return os.environ.get("MFC_CONV_TUNE", "0") == "1"
 
 
+def prescale_factor(wmax):
+    """fp16 has a short exponent: values below 2^-14 are subnormal (and below 2^-24 vanish).  A layer whose largest weight is
+    tiny (a down-scaled head) is packed times this power of two and rescaled exactly in the epilogue."""
+    import math
+    if 0.0 < wmax < 2.0 ** -6:
+        return 2.0 ** min(24, math.floor(-math.log2(wmax)))
+    return 1.0
+
+
 def hilo_enabled():
     """MFC_HILO=0: do not carry a network's last hidden activation / last weights as fp16 (hi, lo) pairs (measurement switch)."""
     return os.environ.get("MFC_HILO", "1") != "0"
@@ -47,8 +56,9 @@ def hilo_last_conv(bld, key, x, x_lo, w, bias, **kw):
     straight into the logits -- nothing downstream averages it -- which is why it is worth three K-blocks instead of one."""
     tdtype = bld.tdtype
     wf = w.detach().float()
-    w_lo = wf - wf.to(tdtype).float()
-    wcat = torch.cat([wf, wf, w_lo], 1)
+    p2 = prescale_factor(float(wf.abs().amax())) if bld.prog.dtype_name == "fp16" else 1.0   # what Builder.conv will pack with
+    w_hi = (wf * p2).to(tdtype).float() / p2
+    wcat = torch.cat([wf, wf, wf - w_hi], 1)
     return bld.conv(key, [x, x_lo, x], wcat, 1, bias=bias, **kw)
 
 
@@ -702,14 +712,12 @@ class Builder:
         cmap = None if identity else chan_map_for(layout)
         if shift is None and bias is not None:
             shift = bias
-        # fp16 has a short exponent: weights below 2^-14 are subnormal (and below 2^-24 vanish).  A layer whose largest
-        # weight is tiny (a down-scaled head) is packed times a power of two and rescaled exactly in the epilogue.
+        # tiny-weight layers are packed times a power of two and rescaled exactly in the epilogue (prescale_factor)
         post_scale = None
         if self.prog.dtype_name == "fp16":
             wmax = float(w_oihw.detach().abs().amax()) * (float(scale.detach().abs().amax()) if scale is not None else 1.0)
-            if 0.0 < wmax < 2.0 ** -6:
-                import math
-                p2 = 2.0 ** min(24, math.floor(-math.log2(wmax)))
+            p2 = prescale_factor(wmax)
+            if p2 != 1.0:
                 scale = (scale.detach().float() * p2) if scale is not None else torch.full((Cout,), p2, dtype=torch.float32, device=self.device)
                 post_scale = 1.0 / p2
         if autotune_enabled() and self.device.type == "cuda" and not abi.plan_only():
