@@ -123,7 +123,7 @@ typedef struct MfcConvDesc {
   int Cout;                /* real output channels                                */
   int kh, kw, stride, pad; /* stride 1 or 2                                       */
   int upsample;            /* 1, or 2 = nearest-neighbour x2 fused into the loader */
-  int act;                 /* 0 none, 1 ReLU (after scale/shift and residual)     */
+  int act;                 /* 0 none, 1 ReLU, 2 LeakyReLU(0.1) (after scale/shift and residual) */
   int dtype;               /* MFC_F16 / MFC_BF16 (inputs, weights, C8 outputs)    */
   int nsrc;                /* channel-concat sources, in order                    */
   /* Output-parity mode for ConvTranspose2d(k=4, s=2, p=1) (models/ternausnet.py:35): the transposed conv is
@@ -133,6 +133,8 @@ typedef struct MfcConvDesc {
    * is read as 1) and zero offsets = an ordinary conv. */
   int in_off_y, in_off_x;
   int out_stride, out_off_y, out_off_x;
+  int pad_br;              /* extra zero padding on the bottom and right edges only (nn.ZeroPad2d([l, l+e, t, t+e]) in front of
+                              a pad-0 conv, models/unflow_model.py:85-130: pad = l, pad_br = e); Hout = (Hup + 2 pad + pad_br - kh)/stride + 1 */
   int reserved;            /* flags: MFC_CONV_HAS_RESIDUAL when mfc_conv2d_fwd will be given io->residual (the plan then
                               reserves the shared-memory prefetch rings for it)                                        */
   MfcSrc src[MFC_MAX_SRC];
@@ -369,6 +371,22 @@ int mfc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int mfc_ingest_rgb(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, const float* mean3_host,
                    const float* std3_host, void* stream);
 int mfc_ingest_depth(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * UnFlow network around the correlation (models/unflow_model.py); the convolutions / transposed convolutions /
+ * LeakyReLUs of FlowNetC + 2 x FlowNetS run through mfc_conv2d_fwd (act 2, pad_br, parity mode).
+ *   mfc_unflow_preprocess : UnFlow.forward :253-262 -- RGB -> BGR, minus the per-channel means; fp32 [B][3][H][W] in / out
+ *   mfc_nchw_to_c8        : fp32 NCHW -> C8 planes (the 441-channel cost volume entering moduleCombined, :120-123,165)
+ *   mfc_unflow_warp       : backward(second, flow) (:6-17): grid_sample(bilinear, border, align_corners=False) at
+ *                           linspace(-1,1) + flow/((size-1)/2); optionally also |first - warped| (Simple.forward :224-226)
+ *   mfc_unflow_upscale    : moduleUpscale (:58-61,77): ConvTranspose2d(2,2,k3,s2,p1,bias=False) + ReplicationPad2d([0,1,0,1]),
+ *                           times `scale`; x [B][2][h][w] -> out [B][2][2h][2w], w = the transposed conv's [2][2][3][3] weight
+ * ---------------------------------------------------------------------------------- */
+int mfc_unflow_preprocess(const float* rgb, float* out, int B, int H, int W, void* stream);
+int mfc_nchw_to_c8(const float* src, void* dst, long long dst_bstride_bytes, int B, int C, int H, int W, int dtype, void* stream);
+int mfc_unflow_warp(const float* second, const float* flow, const float* first /*or NULL*/, float* warped, float* absdiff /*or NULL*/,
+                    int B, int C, int H, int W, void* stream);
+int mfc_unflow_upscale(const float* x, const float* w, float* out, int B, int h, int w_in, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * UnFlow correlation cost volume (models/unflow_correlation.py:10-105,282-337).

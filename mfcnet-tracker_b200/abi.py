@@ -41,7 +41,7 @@ class MfcConvDesc(C.Structure):
     _fields_ = [("B", c_int), ("Hin", c_int), ("Win", c_int), ("Hout", c_int), ("Wout", c_int), ("Cout", c_int),
                 ("kh", c_int), ("kw", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int), ("act", c_int),
                 ("dtype", c_int), ("nsrc", c_int), ("in_off_y", c_int), ("in_off_x", c_int), ("out_stride", c_int),
-                ("out_off_y", c_int), ("out_off_x", c_int), ("reserved", c_int), ("src", MfcSrc * MFC_MAX_SRC)]
+                ("out_off_y", c_int), ("out_off_x", c_int), ("pad_br", c_int), ("reserved", c_int), ("src", MfcSrc * MFC_MAX_SRC)]
 
 
 class MfcConvIO(C.Structure):
@@ -137,6 +137,10 @@ _SIGNATURES = {
     "mfc_adam_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p], c_int),
     "mfc_ingest_rgb": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p], c_int),
     "mfc_ingest_depth": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_unflow_preprocess": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_nchw_to_c8": ([c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_unflow_warp": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_unflow_upscale": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p], c_int),
     "mfc_correlation_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_correlation_bwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_gaussian_blur": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p], c_int),

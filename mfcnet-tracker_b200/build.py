@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libmfcnet_b200.so")
-UNITS = ["api", "conv_tc", "pointwise", "fusion_ops", "resample", "loss", "train_ops", "correlation", "correlation_tma", "ingest", "localize"]
+UNITS = ["api", "conv_tc", "pointwise", "fusion_ops", "resample", "loss", "train_ops", "correlation", "correlation_tma", "ingest", "localize", "unflow_ops"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

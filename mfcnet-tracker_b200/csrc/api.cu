@@ -90,12 +90,13 @@ int validate_desc(const MfcConvDesc* d) {
   if (d->kh < 1 || d->kw < 1 || d->kh > 11 || d->kw > 11) return fail(MFC_EINVAL, "conv: kernel %dx%d unsupported", d->kh, d->kw);
   if (d->stride != 1 && d->stride != 2) return fail(MFC_EINVAL, "conv: stride %d unsupported", d->stride);
   if (d->upsample != 1 && d->upsample != 2) return fail(MFC_EINVAL, "conv: upsample %d unsupported", d->upsample);
-  if (d->act != 0 && d->act != 1) return fail(MFC_EINVAL, "conv: act %d unsupported", d->act);
+  if (d->act < 0 || d->act > 2) return fail(MFC_EINVAL, "conv: act %d unsupported", d->act);
+  if (d->pad_br < 0 || d->pad_br > 5) return fail(MFC_EINVAL, "conv: pad_br %d unsupported", d->pad_br);
   if (!dtype_ok(d->dtype)) return fail(MFC_EINVAL, "conv: dtype %d unsupported", d->dtype);
   if (d->nsrc < 1 || d->nsrc > MFC_MAX_SRC) return fail(MFC_EINVAL, "conv: nsrc %d out of range", d->nsrc);
   if (d->pad < 0 || d->pad > 5) return fail(MFC_EINVAL, "conv: pad %d unsupported", d->pad);
   const int Hup = d->Hin * d->upsample, Wup = d->Win * d->upsample;
-  int ho = (Hup + 2 * d->pad - d->kh) / d->stride + 1, wo = (Wup + 2 * d->pad - d->kw) / d->stride + 1;
+  int ho = (Hup + 2 * d->pad + d->pad_br - d->kh) / d->stride + 1, wo = (Wup + 2 * d->pad + d->pad_br - d->kw) / d->stride + 1;
   if (d->out_stride != 0 && d->out_stride != 1 && d->out_stride != 2) return fail(MFC_EINVAL, "conv: out_stride %d unsupported", d->out_stride);
   if ((unsigned)d->in_off_y > 1u || (unsigned)d->in_off_x > 1u || (unsigned)d->out_off_y > 1u || (unsigned)d->out_off_x > 1u)
     return fail(MFC_EINVAL, "conv: parity offsets must be 0 or 1");
@@ -800,6 +801,33 @@ int mfc_correlation_bwd(const float* first, const float* second, const float* gr
   if (max_disp < 0 || max_disp > 32 || max_disp % stride2) return fail(MFC_EINVAL, "correlation_bwd: max_disp %d unsupported", max_disp);
   MFC_LAUNCH(mfc::launch_correlation_bwd(first, second, grad_out, grad_first, grad_second, B, C, H, W, max_disp, stride2, (cudaStream_t)stream),
              "correlation_bwd");
+}
+
+// ---- UnFlow network pieces -----------------------------------------------------------------------
+int mfc_unflow_preprocess(const float* rgb, float* out, int B, int H, int W, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!rgb || !out || B < 1 || H < 1 || W < 1) return fail(MFC_EINVAL, "unflow_preprocess: bad argument");
+  MFC_LAUNCH(mfc::launch_unflow_prep(rgb, out, B, (long long)H * W, (cudaStream_t)stream), "unflow_preprocess");
+}
+
+int mfc_nchw_to_c8(const float* src, void* dst, long long dst_bstride_bytes, int B, int C, int H, int W, int dtype, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!src || !dst || B < 1 || C < 1 || H < 1 || W < 1 || !dtype_ok(dtype) || ((uintptr_t)dst & 15) || (dst_bstride_bytes & 15))
+    return fail(MFC_EINVAL, "nchw_to_c8: bad argument");
+  MFC_LAUNCH(mfc::launch_nchw_to_c8(src, dst, dst_bstride_bytes, B, C, (long long)H * W, dtype == MFC_BF16, (cudaStream_t)stream), "nchw_to_c8");
+}
+
+int mfc_unflow_warp(const float* second, const float* flow, const float* first, float* warped, float* absdiff, int B, int C, int H, int W,
+                    void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!second || !flow || !warped || (absdiff && !first) || B < 1 || C < 1 || H < 2 || W < 2) return fail(MFC_EINVAL, "unflow_warp: bad argument");
+  MFC_LAUNCH(mfc::launch_unflow_warp(second, flow, first, warped, absdiff, B, C, H, W, (cudaStream_t)stream), "unflow_warp");
+}
+
+int mfc_unflow_upscale(const float* x, const float* w, float* out, int B, int h, int w_in, float scale, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!x || !w || !out || B < 1 || h < 1 || w_in < 1) return fail(MFC_EINVAL, "unflow_upscale: bad argument");
+  MFC_LAUNCH(mfc::launch_unflow_upscale(x, w, out, B, h, w_in, scale, (cudaStream_t)stream), "unflow_upscale");
 }
 
 // ---- key points --------------------------------------------------------------------------------

@@ -555,7 +555,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
   // launch_conv_t picks the mode from exactly these pointers: in the specialised modes they are compile-time facts
   const bool has_res = MODE == EPI_RES ? true : (MODE == EPI_GENERIC && p.res != nullptr);
   const bool res_aff = has_res && p.res_aff != nullptr;
-  const bool relu = p.act == 1;
+  const bool relu = p.act == 1, leaky = p.act == 2;
   const bool has_stats = MODE == EPI_STATS ? true : (MODE == EPI_GENERIC && p.stats != nullptr);
   const bool has_nchw = MODE == EPI_NCHW ? true : (MODE == EPI_GENERIC && p.y_nchw != nullptr);
   const bool has_c8 = (MODE != EPI_NCHW && MODE != EPI_GENERIC) || p.y != nullptr;
@@ -674,6 +674,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     if (relu) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+    } else if (leaky) {  // LeakyReLU(0.1): max(v, 0.1 v)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.1f * f[i]);
     }
     if (kStats && has_stats) {
       if (NB16) {
@@ -843,7 +846,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
   const int R = p.t.R;
   int r = 2 * half;
   if (r >= R) return;
-  const bool slide = p.t.slide != 0, acc_init = p.acc_init != 0, relu = p.act == 1;
+  const bool slide = p.t.slide != 0, acc_init = p.acc_init != 0, relu = p.act == 1, leaky = p.act == 2;
   const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
   const int Wout = p.Wout, Cout = p.Cout;
   const uint32_t HWo = (uint32_t)(p.Hout * Wout);
@@ -929,6 +932,9 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
     if (relu) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+    } else if (leaky) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.1f * f[i]);
     }
     if (!valid) return;
     if (kStats) {

@@ -68,6 +68,13 @@ void correlation_tma_boxes(int H, int W, int stride2, unsigned* box1, unsigned* 
 cudaError_t launch_correlation_tma(const CUtensorMap& map1, const CUtensorMap& map2, float* out, int B, int C, int H, int W,
                                    int stride2, cudaStream_t st);
 
+// unflow_ops.cu
+cudaError_t launch_unflow_prep(const float* rgb, float* out, int B, long long pixels, cudaStream_t st);
+cudaError_t launch_nchw_to_c8(const float* src, void* dst, long long dst_bs, int B, int C, long long pixels, bool bf16, cudaStream_t st);
+cudaError_t launch_unflow_warp(const float* second, const float* flow, const float* first, float* warped, float* absdiff, int B, int C,
+                               int H, int W, cudaStream_t st);
+cudaError_t launch_unflow_upscale(const float* x, const float* w, float* out, int B, int h, int wd, float scale, cudaStream_t st);
+
 // ingest.cu
 cudaError_t launch_ingest_rgb(const uint8_t* bgr, long long frame_stride, float* out, int B, long long pixels, const float* mean,
                               const float* stdv, cudaStream_t st);

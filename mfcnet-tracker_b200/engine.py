@@ -362,15 +362,16 @@ class Program:
                                            "bytes": B * H * W * (4 * nreal + 16)})
         return a
 
-    def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act, parity=None):
+    def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act, parity=None, pad_br=0):
         """parity=(py, px): one output parity of ConvTranspose2d(4, 2, 1), a 2x2 conv whose result lands on
         the pixels (2y+py, 2x+px) of a [2H][2W] output (include/mfcnet_b200.h, MfcConvDesc)."""
         d = abi.MfcConvDesc()
         s0 = srcs[0]
         d.B, d.Hin, d.Win = s0.B, s0.H, s0.W
         Hup, Wup = s0.H * upsample, s0.W * upsample
-        d.Hout = (Hup + 2 * pad - k) // stride + 1
-        d.Wout = (Wup + 2 * pad - k) // stride + 1
+        d.Hout = (Hup + 2 * pad + pad_br - k) // stride + 1
+        d.Wout = (Wup + 2 * pad + pad_br - k) // stride + 1
+        d.pad_br = pad_br
         if parity is not None:
             d.Hout, d.Wout = s0.H, s0.W
             d.in_off_y, d.in_off_x, d.out_stride, d.out_off_y, d.out_off_x = parity[0], parity[1], 2, parity[0], parity[1]
@@ -671,7 +672,7 @@ class Builder:
 
     def conv(self, key, srcs, w_oihw, k, *, bias=None, scale=None, shift=None, stride=1, pad=0, upsample=1, act=0,
              residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None, parity=None,
-             head=None, want_lo=False):
+             head=None, want_lo=False, pad_br=0):
         """srcs: list of Act (channel concat in order).  w_oihw: fp32 device weight whose Cin axis
         is the concat of the sources' REAL channels (or, with first_weight_channel=[...], starts
         at the given offsets).  head=(w [Nh, Cout] fp32, bias [Nh] or None): a following 1x1 conv evaluated in fp32 inside this
@@ -695,7 +696,7 @@ class Builder:
                 y_c8 = y_c8.view(y_c8.shape[0], y_c8.shape[1], rows, 128, 8)
             if out_nchw is not None:
                 out_nchw = out_nchw.view(out_nchw.shape[0], out_nchw.shape[1], rows, 128)
-        d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity)
+        d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity, pad_br=pad_br)
         if residual is not None:
             d.reserved |= abi.MFC_CONV_HAS_RESIDUAL
         if want_stats:
