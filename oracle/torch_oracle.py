@@ -343,3 +343,98 @@ def segmentation_loss(output, targets, class_weights=None, w_nll=0.7, w_jaccard=
         jac = jac - torch.log((inter + 1e-15) / (union + 1e-15))
     jac = jac / N
     return float(w_nll * nll + w_jaccard * jac), float(nll), float(jac)
+
+
+# ----------------------------------------------------------------------------
+# UnFlow network around the correlation  (models/unflow_model.py:6-270)
+# ----------------------------------------------------------------------------
+def _lrelu(x):
+    return F.leaky_relu(x, 0.1)
+
+
+def unflow_backward_warp(inp, flow):
+    """`backward()` (models/unflow_model.py:6-17): grid_sample(bilinear, border) at linspace(-1,1) + flow/((size-1)/2),
+    align_corners left at torch's default (False)."""
+    B, _, H, W = flow.shape
+    gx = torch.linspace(-1.0, 1.0, W, dtype=flow.dtype, device=flow.device).view(1, 1, 1, W).expand(B, -1, H, -1)
+    gy = torch.linspace(-1.0, 1.0, H, dtype=flow.dtype, device=flow.device).view(1, 1, H, 1).expand(B, -1, -1, W)
+    grid = torch.cat([gx, gy], 1)
+    fl = torch.cat([flow[:, 0:1] / ((inp.shape[3] - 1.0) / 2.0), flow[:, 1:2] / ((inp.shape[2] - 1.0) / 2.0)], 1)
+    return F.grid_sample(inp, (grid + fl).permute(0, 2, 3, 1), mode="bilinear", padding_mode="border", align_corners=False)
+
+
+def _unflow_upconv(sd, p, o):
+    """Upconv.forward (models/unflow_model.py:64-78)."""
+    def conv(name, x):
+        return F.conv2d(x, sd[p + name + ".weight"], sd[p + name + ".bias"], padding=1)
+
+    def up(name, x):
+        return F.conv_transpose2d(x, sd[p + name + ".weight"], sd[p + name + ".bias"], stride=2, padding=1)
+
+    def nxt(name, x):
+        return _lrelu(F.conv_transpose2d(x, sd[p + name + ".0.weight"], sd[p + name + ".0.bias"], stride=2, padding=1))
+
+    x = o["conv6"]
+    f6 = conv("moduleSixOut", x)
+    x = torch.cat([o["conv5"], nxt("moduleFivNext", x), up("moduleSixUp", f6)], 1)
+    f5 = conv("moduleFivOut", x)
+    x = torch.cat([o["conv4"], nxt("moduleFouNext", x), up("moduleFivUp", f5)], 1)
+    f4 = conv("moduleFouOut", x)
+    x = torch.cat([o["conv3"], nxt("moduleThrNext", x), up("moduleFouUp", f4)], 1)
+    f3 = conv("moduleThrOut", x)
+    x = torch.cat([o["conv2"], nxt("moduleTwoNext", x), up("moduleThrUp", f3)], 1)
+    f2 = conv("moduleTwoOut", x)
+
+    def upscale(t):
+        t = F.conv_transpose2d(t, sd[p + "moduleUpscale.0.weight"], None, stride=2, padding=1)
+        return F.pad(t, [0, 1, 0, 1], mode="replicate")
+    return upscale(upscale(f2)) * 20.0
+
+
+def _unflow_padconv(sd, name, x, pad, k_stride=2):
+    """nn.Sequential(ZeroPad2d(pad), Conv2d(stride 2, padding 0), LeakyReLU(0.1)) -- keys `<name>.1.*`."""
+    return _lrelu(F.conv2d(F.pad(x, pad), sd[name + ".1.weight"], sd[name + ".1.bias"], stride=k_stride))
+
+
+def _unflow_tail(sd, p, o):
+    """moduleFou / moduleFiv / moduleSix (shared by Complex and Simple): pad [0,2,0,2] + conv3 s2 + lrelu + conv3 + lrelu."""
+    for src, dst, name in (("conv3", "conv4", "moduleFou"), ("conv4", "conv5", "moduleFiv"), ("conv5", "conv6", "moduleSix")):
+        x = _unflow_padconv(sd, p + name, o[src], [0, 2, 0, 2])
+        o[dst] = _lrelu(F.conv2d(x, sd[p + name + ".3.weight"], sd[p + name + ".3.bias"], padding=1))
+    return o
+
+
+def unflow_forward(sd, first, second, corr=None):
+    """UnFlow.forward (models/unflow_model.py:253-270) = Complex (FlowNetC, :81-175) then two Simple nets (FlowNetS, :177-245).
+    `corr(a, b)` = the cost volume (default: the torch restatement `correlation`)."""
+    corr = corr or correlation
+    mean = torch.tensor([104.920005 / 255.0, 110.175300 / 255.0, 114.785955 / 255.0], dtype=first.dtype, device=first.device)
+    first = first[:, [2, 1, 0]] - mean.view(1, 3, 1, 1)
+    second = second[:, [2, 1, 0]] - mean.view(1, 3, 1, 1)
+    # ---- Complex
+    p = "moduleFlownets.0."
+
+    def enc(x):
+        c1 = _unflow_padconv(sd, p + "moduleOne", x, [2, 4, 2, 4])
+        c2 = _unflow_padconv(sd, p + "moduleTwo", c1, [1, 3, 1, 3])
+        c3 = _unflow_padconv(sd, p + "moduleThr", c2, [1, 3, 1, 3])
+        return c1, c2, c3
+    o = {}
+    o["conv1"], o["conv2"], o["conv3"] = enc(first)
+    redir = _lrelu(F.conv2d(o["conv3"], sd[p + "moduleRedir.0.weight"], sd[p + "moduleRedir.0.bias"]))
+    other = enc(second)[2]
+    cv = corr(o["conv3"].contiguous(), other.contiguous())
+    o["conv3"] = _lrelu(F.conv2d(torch.cat([redir, cv], 1), sd[p + "moduleCombined.0.weight"], sd[p + "moduleCombined.0.bias"], padding=1))
+    flow = _unflow_upconv(sd, p + "moduleUpconv.", _unflow_tail(sd, p, o))
+    # ---- Simple x 2
+    for n in (1, 2):
+        p = "moduleFlownets.%d." % n
+        warp = unflow_backward_warp(second, flow)
+        x = torch.cat([first, second, flow, warp, (first - warp).abs()], 1)
+        o = {}
+        o["conv1"] = _unflow_padconv(sd, p + "moduleOne", x, [2, 4, 2, 4])
+        o["conv2"] = _unflow_padconv(sd, p + "moduleTwo", o["conv1"], [1, 3, 1, 3])
+        x = _unflow_padconv(sd, p + "moduleThr", o["conv2"], [1, 3, 1, 3])
+        o["conv3"] = _lrelu(F.conv2d(x, sd[p + "moduleThr.3.weight"], sd[p + "moduleThr.3.bias"], padding=1))
+        flow = _unflow_upconv(sd, p + "moduleUpconv.", _unflow_tail(sd, p, o))
+    return flow

@@ -389,6 +389,27 @@ def test_fp16_overflow_is_reported(M):
         assert torch.isfinite(y).all()
 
 
+def test_unflow_matches_reference(M):
+    """UnFlow (FlowNetC + 2 x FlowNetS around the correlation, models/unflow_model.py) against the output of the REAL reference
+    module (tests/golden/unflow_64x128.npz, oracle/make_golden_unflow.py).  Flows are in pixels (the network multiplies by 20
+    three times over); bound: 5e-2 px max-abs, 1e-2 px mean-abs on flows of up to ~2 px."""
+    meta, man, arr = G.load("unflow_64x128")
+    net = M.UnFlow()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    net.load_state_dict(G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"]), strict=True)
+    net = net.cuda().eval()
+    a = torch.from_numpy(synth.uniform("unflow_64x128/first", (meta["B"], 3, meta["H"], meta["W"]), meta["seed"])).cuda()
+    b = torch.from_numpy(synth.uniform("unflow_64x128/second", (meta["B"], 3, meta["H"], meta["W"]), meta["seed"])).cuda()
+    with torch.no_grad():
+        flow = net(a, b)
+        flow2 = net(a, b)
+    assert torch.equal(flow, flow2)
+    d = (flow.cpu().numpy() - arr["flow"])
+    _report(test="unflow/unflow_64x128", dtype="fp16", max_abs_err=float(np.abs(d).max()), mean_abs_err=float(np.abs(d).mean()),
+            argmax_agree=1.0, decidable_frac=1.0, decidable_agree=True, ref_absmax=float(np.abs(arr["flow"]).max()))
+    assert np.abs(d).max() <= 5e-2 and np.abs(d).mean() <= 1e-2, (np.abs(d).max(), np.abs(d).mean())
+
+
 def test_no_cpu_fallback(M):
     net = M.ResUnet_VB(channels=3, dim=8, out_dim=5).eval()
     with pytest.raises(RuntimeError):

@@ -177,6 +177,16 @@ def test_mfcnet_wrapper_keys_and_plan(M, variant):
         net.train()(xs, optflow=[torch.zeros(2, 2, 64, 96)] * 2, depth=[torch.zeros(2, 1, 64, 96)] * 3)
 
 
+def test_unflow_state_dict_keys_and_plan(M):
+    meta, man, _ = G.load("unflow_64x128")
+    net = M.UnFlow().eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s, _ in man]
+    y = net(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
+    assert y.shape == (1, 2, 64, 128)
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 3, 60, 128), torch.zeros(1, 3, 60, 128))
+
+
 def test_hrnet_state_dict_keys_and_plan(M):
     """Checkpoint compatibility of the HRNet-W48 shell (1 839 tensors) and a plan-only forward."""
     meta, man, _ = G.load("hrnet_w48_64x96")

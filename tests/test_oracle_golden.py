@@ -113,3 +113,17 @@ def test_synth_is_stable():
     assert np.array_equal(a, synth.normal("kat", (4,), seed=5))
     assert abs(float(synth.normal("stat", (200000,), 1).std()) - 1.0) < 0.01
     assert abs(float(synth.uniform("stat", (200000,), 1).mean()) - 0.5) < 0.01
+
+
+def test_unflow_oracle_matches_reference_golden():
+    """oracle/torch_oracle.py::unflow_forward against the flow written by the reference's own UnFlow module."""
+    import torch
+    from oracle import synth, torch_oracle as TO
+    from tests import golden_util as G
+    meta, man, arr = G.load("unflow_64x128")
+    sd = G.state_dict(man, meta["seed"], scale_keys=meta["scale_keys"])
+    a = torch.from_numpy(synth.uniform("unflow_64x128/first", (meta["B"], 3, meta["H"], meta["W"]), meta["seed"]))
+    b = torch.from_numpy(synth.uniform("unflow_64x128/second", (meta["B"], 3, meta["H"], meta["W"]), meta["seed"]))
+    with torch.no_grad():
+        flow = TO.unflow_forward(sd, a, b)
+    assert float((flow - torch.from_numpy(arr["flow"])).abs().max()) <= 1e-4
