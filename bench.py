@@ -219,7 +219,7 @@ def secondary_records(args, net, world, rank):
                         "ms_total": ms, "launches_per_step": launches, "gflop_per_frame": gflop,
                         "tensor_tflops": fps * gflop / 1e3, "tensor_frac": fps * gflop / 1e3 / (tf_peak * world),
                         "note": "feature ring: 1 SFC pass + 1 fusion pass per output frame, one CUDA-graph replay per step"}
-    Bc = 4
+    Bc = 16   # measured on B200: 4 / 8 / 16 clips per GPU = 393 / 466-514 / 656 frames/s (HRNet layers are launch- and latency-bound at small batch)
     ms, n_out, launches = bench_stream.run("hrnet", 5, args.video_frames, Bc, H, W, N_CLASSES, world, rank)
     fps = n_out * 1000.0 / ms
     rec["config4"] = {"metric": "output frames/s, HRNet-W48 MFCNet, 5-frame sliding window, %d-frame synthetic video, clips sharded"

@@ -329,17 +329,19 @@ __device__ __forceinline__ float silu_fast(float y) {
   return 0.5f * y * (1.0f + t);
 }
 
-// silu(y) from h = y/2.  Fast form h + h*tanh.approx(h): one MUFU op, |error| <= 2^-11 |h| (the approximation error of
-// tanh.approx.f32 is as large as the fp16 rounding of the result).  Accurate form y / (1 + 2^(-y log2 e)) with ex2.approx +
-// rcp.approx: two MUFU ops, ~1e-7 relative.
-__device__ __forceinline__ float silu_from_half(float h, bool accurate) {
-  if (accurate) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(h * -2.885390081777927f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return (h + h) * r;
-  }
+// silu(y) from h = y/2: h + h*tanh.approx(h), one MUFU op, |error| <= 2^-11 |h|.  The two-MUFU form y / (1 + 2^(-y log2 e))
+// (ex2.approx + rcp.approx, ~1e-7 relative) was measured on the full network (round 2: identical argmax agreement and logit
+// error -- the fp16 storage rounding dominates -- at -5 % frames/s); it is kept behind the compile-time switch
+// -DMFC_SILU_ACCURATE so that the hot loops carry one code path.
+__device__ __forceinline__ float silu_from_half(float h, bool /*unused*/ = false) {
+#ifdef MFC_SILU_ACCURATE
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(h * -2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return (h + h) * r;
+#else
   return fmaf(h, tanh_fast(h), h);
+#endif
 }
 
 // |v| beyond the largest finite fp16 value rounds to +-inf in a C8 fp16 tensor

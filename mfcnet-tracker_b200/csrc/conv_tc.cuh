@@ -101,7 +101,7 @@ struct ConvParams {
   FastDiv div_grid, div_chunk;
   int reverse, total_items;  // reverse: walk the work items from the last sample to the first (see MFC_CONV_REVERSE_ORDER)
   int debug;  // measurement only (MFC_CONV_DEBUG): bit0 skip producer copies, bit1 skip epilogue body, bit2 skip MMAs,
-              // bit3 role timing; bit4 (MFC_SILU_ACCURATE=1): two-MUFU SiLU instead of tanh.approx
+              // bit3 role timing
 };
 
 // host planner

@@ -24,7 +24,7 @@ cudaError_t launch_gn_finalize(const float* stats, int B, int tiles, int cpad, i
                                const float* gamma, const float* beta, float eps, float* affine, cudaStream_t st);
 cudaError_t launch_affine_silu_add(const void* a, const float* affine, const void* r, void* out, int B, int chunks,
                                    long long pixels, bool bf16, int* ovf, cudaStream_t st);
-bool silu_accurate();  // MFC_SILU_ACCURATE=1: two-MUFU SiLU (ex2 + rcp) instead of tanh.approx in every kernel
+bool silu_accurate();  // built with -DMFC_SILU_ACCURATE: two-MUFU SiLU (ex2 + rcp) instead of tanh.approx in every kernel
 
 // fusion_ops.cu
 cudaError_t launch_flow_warp(const MfcWarpArgs& a, cudaStream_t st);

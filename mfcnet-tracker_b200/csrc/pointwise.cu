@@ -8,8 +8,11 @@
 namespace mfc {
 
 bool silu_accurate() {
-  static const bool v = getenv("MFC_SILU_ACCURATE") != nullptr && atoi(getenv("MFC_SILU_ACCURATE")) != 0;
-  return v;
+#ifdef MFC_SILU_ACCURATE
+  return true;
+#else
+  return false;   // compile-time switch (see silu_from_half)
+#endif
 }
 
 // ---- fp32 NCHW planes -> one C8 plane ---------------------------------------------------------

@@ -59,6 +59,33 @@ def main():
             print(json.dumps(r), flush=True)
             out.append(r)
             del net, run
+        # UnFlow (FlowNetC + 2 x FlowNetS) at the reference's operating point: 384x1280 frames -> 48x160 cost volume
+        net = M.UnFlow().cuda().eval()
+        for p_ in net.parameters():                       # random init with a sane scale (LeakyReLU stack)
+            if p_.dim() == 4:
+                torch.nn.init.kaiming_normal_(p_, a=0.1)
+        for n in range(3):
+            net.moduleFlownets[n].moduleUpconv.moduleTwoOut.weight.data.mul_(0.05)
+        a, b = torch.rand(1, 3, 384, 1280, device="cuda"), torch.rand(1, 3, 384, 1280, device="cuda")
+        ms = timeit(lambda: net(a, b), iters)
+        P = net._plans[(1, 384, 1280)]
+        flops = sum(m.get("flops", 0) for pr in P["progs"] for m in pr.meta)
+        r = {"what": "UnFlow 384x1280 (3 stacked nets + correlation)", "batch": 1, "ms": round(ms, 3), "pairs_per_s": round(1000.0 / ms, 1),
+             "launches": sum(pr.n_kernels for pr in P["progs"]) + 10, "conv_TFLOPs": round(flops / ms * 1e-9, 1)}
+        try:   # the same network written with stock torch ops (cuDNN fp32) on this GPU, as an informative library baseline
+            from oracle import torch_oracle as TO
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            sd = {k: v.detach() for k, v in net.state_dict().items()}
+            ms_t = timeit(lambda: TO.unflow_forward(sd, a, b, corr=M.correlation), 3)
+            ref = TO.unflow_forward(sd, a, b, corr=M.correlation)
+            r["ms_torch_ops_fp32_same_gpu"] = round(ms_t, 2)
+            r["max_abs_flow_diff_px"] = float((net(a, b) - ref).abs().max())
+            r["ref_flow_absmax_px"] = float(ref.abs().max())
+        except Exception as e:   # noqa: BLE001
+            r["torch_baseline_error"] = repr(e)[:200]
+        print(json.dumps(r), flush=True)
+        out.append(r)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/bench_models.json", "w") as f:
         json.dump(out, f, indent=1)
