@@ -394,11 +394,11 @@ def run_b200(args):
     achieved = conv["bytes"] / 1e9 / (conv["ms"] / 1e3)
     traffic, traffic_note = None, None
     try:  # dram bytes of the dominant launch shape from the committed `ncu --set full` capture
-        with open(os.path.join(ROOT, "profiles", "r01z_ncu_conv16_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_conv16_summary.json")) as f:
             ncu = json.load(f)
         traffic = (float(ncu["dram__bytes_read.sum"].split()[0]) + float(ncu["dram__bytes_write.sum"].split()[0])) * 1e6
-        traffic_note = ("dram read+write of ONE launch of the most frequent shape (16->16 3x3, GroupNorm+SiLU on load, GN sums, "
-                        "B=24 480x640: 472 MB algorithmic) from profiles/r01z_ncu_conv16_summary.json; reads equal the "
+        traffic_note = ("dram read+write of ONE launch of the most frequent shape (16->16 3x3 + GroupNorm sums, B=24 480x640: "
+                        "472 MB algorithmic) from profiles/r02_ncu_conv16_summary.json (ncu --set full); reads equal the "
                         "algorithmic input bytes (halo re-reads hit L2), part of the output is still in the 126 MB L2 at exit")
     except (OSError, KeyError, ValueError):
         pass

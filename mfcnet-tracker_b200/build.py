@@ -14,7 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libmfcnet_b200.so")
+# MFC_B200_LIB_TAG / MFC_B200_NVCC_DEFS: measurement builds (e.g. TAG=hint DEFS="-DMFC_WAIT_HINT_NS=4000") live next to the product
+_TAG = os.environ.get("MFC_B200_LIB_TAG", "")
+LIB = os.path.join(LIBDIR, "libmfcnet_b200%s.so" % (("_" + _TAG) if _TAG else ""))
+if _TAG:
+    OBJDIR = OBJDIR + "_" + _TAG
 UNITS = ["api", "conv_tc", "pointwise", "fusion_ops", "resample", "loss", "train_ops", "correlation", "correlation_tma", "ingest", "localize", "unflow_ops"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -50,7 +54,7 @@ def build(force=False, verbose=False):
 
     def one(u):
         obj = os.path.join(OBJDIR, u + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, u + ".cu"), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("MFC_B200_NVCC_DEFS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, u + ".cu"), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (u, r.stdout, r.stderr))

@@ -303,10 +303,13 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   p.y_nchw = io->y_nchw;
   p.stats = io->stats;
   p.ovf = io->overflow;
-  p.acc_init = (p.t.slide && io->scale == nullptr && io->shift != nullptr) ? 1 : 0;
   {
     static const int no_fast = getenv("MFC_CONV_EPI_FAST") ? (atoi(getenv("MFC_CONV_EPI_FAST")) == 0) : 0;  // measurement switch
-    p.epi_fast = (tiling_fast_epilogue(d, p.t) && (!no_fast || io->head_w)) ? 1 : 0;
+    // the FAST kernels exist for the statistics mode and the fp32-output (NCHW / fused head) mode (launch_conv_mode)
+    const bool mode_ok = !io->residual && ((io->stats != nullptr) != (io->y_nchw != nullptr));
+    p.epi_fast = (tiling_fast_epilogue(d, p.t) && mode_ok && (!no_fast || io->head_w)) ? 1 : 0;
+    // shift-initialised accumulators: sliding mode, FAST kernels only (the general epilogue keeps its scale/shift pass)
+    p.acc_init = (p.epi_fast && p.t.slide && io->scale == nullptr && io->shift != nullptr) ? 1 : 0;
   }
   if (io->head_w) {
     if (!(d->reserved & MFC_CONV_WANT_HEAD) || !p.epi_fast || !io->y_nchw || io->stats || io->residual || io->head_n < 1 || io->head_n > 8 ||

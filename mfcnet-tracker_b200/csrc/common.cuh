@@ -20,17 +20,28 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// The suspend-time hint lets a waiting warp sleep in hardware (it wakes as soon as the phase completes): without it the
-// idle roles of the conv kernel spin through their poll loops and take ~25 % of the SM's issue slots from the busy ones.
+// -DMFC_WAIT_HINT_NS=<ns> adds a suspend-time hint (a waiting warp may sleep in hardware up to that long): it removes the idle
+// roles' poll loops (~25 % of all executed instructions) but was measured to cost more in hand-off latency than it saves
+// in issue slots, so the default build polls.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef MFC_WAIT_HINT_NS
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)(MFC_WAIT_HINT_NS))
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -146,6 +146,7 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
     // columns past the tile's own halo (slide mode pads the row pitch to 128) are never read for a valid output
     const uint32_t W = (uint32_t)min(p.Win, ix_base + p.t.TW + (p.kw - 1));
     const uint32_t base = smem_u32(plane);
+#ifdef MFC_INCREMENTAL_WALK
     constexpr int U = 4;
     // (row, col) of the thread's U slots, advanced incrementally: one iteration moves every slot by U*NT = step_r rows +
     // step_c columns (one carry), so there is no division in the loop (with the sliding mode's pitch of 128, U*NT = 768 is
@@ -193,6 +194,37 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
         }
       }
     }
+#else
+    constexpr int U = 4;
+    const FastDiv divP = p.divP;
+    for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
+      uint4 v[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = idx0 + u * NT;
+        const int r = (int)fdiv((uint32_t)idx, divP);
+        const int c = idx - r * P;
+        ok[u] = idx < items && (uint32_t)(iy_base + r) < H && (uint32_t)(ix_base + c) < W;  // padding stays zero
+        if (ok[u]) v[u] = lds16_u32(base + (uint32_t)idx * 16u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float f[8];
+        unpack8<BF16>(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = fmaf(f[i], sc[i], sh[i]);
+          f[i] = silu_from_half(h);
+        }
+        v[u] = pack8<BF16>(f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) sts16_u32(base + (uint32_t)(idx0 + u * NT) * 16u, v[u]);
+    }
+#endif
     return;
   }
   const int Hup = p.Hin * p.upsample, Wup = p.Win * p.upsample;
@@ -601,7 +633,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
     return two;
   };
   // scale / shift of one sub-step: accumulators -> fp32 values
-  const bool acc_init = p.acc_init != 0;
+  constexpr bool acc_init = false;   // shift-initialised accumulators exist in the FAST kernels only (api.cu sets p.acc_init there)
   auto scale_shift = [&](const uint32_t* a16, int co0, float (&f)[16]) {
     if (acc_init) {  // the accumulators started from the shift: nothing left to add
 #pragma unroll
@@ -705,10 +737,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tmem
       }
     }
     if (valid) {
+#ifndef MFC_NO_OVF_GUARD
       if (!BF16 && has_c8) {  // fp16 range guard: the largest magnitude this thread stores (checked once, at kernel exit)
 #pragma unroll
         for (int i = 0; i < 16; i += 2) omax = fmaxf(fmaxf(omax, fabsf(f[i])), fabsf(f[i + 1]));
       }
+#endif
       if (has_c8) {
         const uint32_t off0 = (uint32_t)(co0 >> 3) * HWo + pix;  // 16-byte slots from the sample's base: < 2^32
 #pragma unroll
@@ -946,10 +980,12 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
     }
     const uint32_t poff = (uint32_t)rr * pstep;
     if (has_c8) {
+#ifndef MFC_NO_OVF_GUARD
       if (!BF16) {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) omax = fmaxf(fmaxf(omax, fabsf(f[i])), fabsf(f[i + 1]));
       }
+#endif
       uint8_t* q = yp + (size_t)poff * 16;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -1152,14 +1188,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       // only the columns the two accumulator buffers use (acc_cols each, a multiple of 16), 32 at a time where possible
       const uint32_t used = (uint32_t)p.t.nacc * p.t.acc_cols;
       const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-      if (p.acc_init && NB == 16) {  // the same 16 shifts in every 16-column block
+      if (FAST && p.acc_init && NB == 16) {  // the same 16 shifts in every 16-column block
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = s_shift[i];
         uint32_t c = 0;
         for (; c + 32 <= used; c += 32) tmem_st32v(lane_base + c, v, v);
         if (c < used) tmem_st16v(lane_base + c, v);
-      } else if (p.acc_init) {
+      } else if (FAST && p.acc_init) {
         for (uint32_t c = 0; c < used; c += 16) {
           float v[16];
           const float* src = s_shift + (c % (uint32_t)NB);
@@ -1773,7 +1809,9 @@ static cudaError_t launch_conv_inst(const ConvParams& p, cudaStream_t st) {
 
 template <bool BF16, int MODE>
 static cudaError_t launch_conv_mode(const ConvParams& p, cudaStream_t st) {
-  if constexpr (MODE == EPI_PLAIN || MODE == EPI_STATS || MODE == EPI_NCHW) {
+  // the fast epilogue serves the statistics layers and the fp32-output / fused-head layers; plain C8 layers keep the general
+  // path (measured: its convert-then-prefetch loop is faster than the fast path's two alternating accumulator arrays)
+  if constexpr (MODE == EPI_STATS || MODE == EPI_NCHW) {
     if (p.epi_fast) return launch_conv_inst<BF16, MODE, true, true>(p, st);
   }
   return p.t.NB == 16 ? launch_conv_inst<BF16, MODE, true, false>(p, st) : launch_conv_inst<BF16, MODE, false, false>(p, st);

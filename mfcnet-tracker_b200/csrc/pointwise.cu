@@ -159,7 +159,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, int tiles, i
 
 // ---- out = silu(a*scale+shift) + r --------------------------------------------------------------
 template <bool BF16>
-__global__ void affine_silu_add_kernel(const uint8_t* __restrict__ a, const float* __restrict__ affine,
+__global__ void __launch_bounds__(256, 8) affine_silu_add_kernel(const uint8_t* __restrict__ a, const float* __restrict__ affine,
                                        const uint8_t* __restrict__ r, uint8_t* __restrict__ out, int B, int chunks,
                                        long long pixels, bool accurate, int* __restrict__ ovf) {
   pdl_launch_dependents();
@@ -176,8 +176,10 @@ __global__ void affine_silu_add_kernel(const uint8_t* __restrict__ a, const floa
     for (int j = 0; j < 8; ++j) {
       const float2 s = __ldg(af + j);
       fa[j] = silu_from_half(0.5f * fmaf(fa[j], s.x, s.y), accurate) + fr[j];
-      omax = fmaxf(omax, fabsf(fa[j]));
     }
+    // range guard as a tree: one dependent update of `omax` per 16-byte slot, not eight
+    omax = fmaxf(omax, fmaxf(fmaxf(fmaxf(fabsf(fa[0]), fabsf(fa[1])), fmaxf(fabsf(fa[2]), fabsf(fa[3]))),
+                             fmaxf(fmaxf(fabsf(fa[4]), fabsf(fa[5])), fmaxf(fabsf(fa[6]), fabsf(fa[7])))));
     *reinterpret_cast<uint4*>(out + i * 16) = pack8<BF16>(fa);
   }
   if (!BF16 && ovf != nullptr && __any_sync(0xffffffffu, !(omax <= kF16Max)) && (threadIdx.x & 31) == 0) atomicAdd(ovf, 1);
