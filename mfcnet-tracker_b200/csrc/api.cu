@@ -326,6 +326,10 @@ int conv_fwd_tiled(const MfcConvDesc* d, const MfcConvIO* io, const mfc::ConvTil
   if (p.t.tma) {
     rc = encode_source_maps(d, &p);
     if (rc != MFC_OK) return rc;
+    static const int no_direct = getenv("MFC_CONV_DIRECT") ? (atoi(getenv("MFC_CONV_DIRECT")) == 0) : 0;  // measurement switch
+    bool any_aff = false;
+    for (int i = 0; i < d->nsrc; ++i) any_aff = any_aff || d->src[i].affine != nullptr;
+    p.direct = (!no_direct && !any_aff && d->upsample == 1 && !(p.debug & 1)) ? 1 : 0;
   }
   if (p.stats && p.t.NB * p.t.nblk > 256) return fail(MFC_EINVAL, "conv: GroupNorm statistics need Cout <= 256");
   if (((uintptr_t)p.w & 15) || ((uintptr_t)p.y & 15) || ((uintptr_t)p.res & 15) || (p.y_bs & 15) || (p.res_bs & 15))

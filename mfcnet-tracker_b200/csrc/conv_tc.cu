@@ -1256,9 +1256,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
       if (!tma) cp_async_commit();  // one group per pipeline step, empty or not: keeps wait_group(D) exact
     };
+    if (p.direct) {
+      // nothing to transform: the MMA warps consume the stages straight off the TMA barriers; this thread only keeps
+      // the ring full (each issue waits for its slot's MMAs to retire)
+      if (ptid == 0)
+        while (wi < total_items) issue_next();
+      wt = total_items;
+    }
     // Order matters: stage i is handed to the MMA warp BEFORE the copies of stage i+D are issued, because
     // that issue has to wait for the MMAs of stage i-1 to release their slot (D = nstages-1).
-    for (int j = 0; j < D; ++j) issue_next();
+    for (int j = 0; j < D && !p.direct; ++j) issue_next();
     while (wt < total_items) {
       if (D == 0) issue_next();
       const ItemCoord c = decode_item(p, wt);
@@ -1312,7 +1319,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       const uint32_t tmem_acc = tmem_base + (uint32_t)acc_i * p.t.acc_cols;
       int ecount = 0, aset = 0;
       for (int ks = 0; ks < p.t.kstages; ++ks) {
-        mbar_wait_t(&bar_full[stage], phase, timed, wait_a);
+        mbar_wait_t(p.direct ? &bar_tma[stage] : &bar_full[stage], phase, timed, wait_a);
         tc_fence_after();
         if (elect_one_sync()) {
           const int kh_eff = (p.debug & 4) ? 0 : p.kh;

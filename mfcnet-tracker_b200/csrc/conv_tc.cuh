@@ -89,6 +89,9 @@ struct ConvParams {
   int head_n;
   int* ovf;       // fp16 outputs only: incremented by every epilogue warp that stored a value beyond +-65504 (or NULL)
   alignas(64) CUtensorMap tmap[MFC_MAX_SRC];  // t.tma: source i as the 5-D tensor (8 ch, W, H, chunk, sample)
+  int direct;     // no work for the producer warps between the TMA landing and the MMAs (no GroupNorm-on-load, no x2 expansion):
+                  // the MMA warps wait on the TMA barrier themselves and ONE thread keeps the loads issued -- one barrier hop
+                  // and six warps' per-stage hand-off less per work item
   int tma_wide;   // stride-1 sources are described to TMA as 4-D tensors of 8-byte elements (2 per pixel): the innermost box
                   // dimension is a whole tile row (P*16 bytes) instead of one 16-byte pixel, i.e. one L2 request stream per
                   // row instead of one per pixel

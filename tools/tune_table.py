@@ -12,7 +12,7 @@ import sys
 import time
 
 os.environ["MFC_CONV_TUNE"] = "1"
-os.environ.setdefault("MFC_CONV_TUNE_REPS", "5")
+os.environ.setdefault("MFC_CONV_TUNE_REPS", "10")
 if "--fresh" in sys.argv:
     os.environ["MFC_CONV_TABLE"] = "0"
 
