@@ -66,6 +66,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// ---------------------------------------------------------------- bulk stores (shared -> global, bulk async-groups)
+// `bytes` a multiple of 16, both addresses 16-byte aligned.  The issuing thread's earlier shared-memory writes and those of
+// other threads ordered before it by a barrier must have been made visible to the async proxy (fence_async_smem).
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk async-groups of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (their writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA (bulk async copies, completion on an mbarrier)
 // 5-D tiled box load: global tensor described by a CUtensorMap -> dense box in shared memory.  Coordinates are
 // signed; whatever part of the box lies outside the tensor is filled with zeros (this IS the conv zero padding)
@@ -353,6 +365,26 @@ __device__ __forceinline__ float silu_from_half(float h, bool /*unused*/ = false
 #else
   return fmaf(h, tanh_fast(h), h);
 #endif
+}
+
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 -- one instruction, two IEEE fp32 results, same bits as the scalar forms).
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
 
 // |v| beyond the largest finite fp16 value rounds to +-inf in a C8 fp16 tensor

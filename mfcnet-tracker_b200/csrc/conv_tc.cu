@@ -146,85 +146,67 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
     // columns past the tile's own halo (slide mode pads the row pitch to 128) are never read for a valid output
     const uint32_t W = (uint32_t)min(p.Win, ix_base + p.t.TW + (p.kw - 1));
     const uint32_t base = smem_u32(plane);
-#ifdef MFC_INCREMENTAL_WALK
-    constexpr int U = 4;
-    // (row, col) of the thread's U slots, advanced incrementally: one iteration moves every slot by U*NT = step_r rows +
-    // step_c columns (one carry), so there is no division in the loop (with the sliding mode's pitch of 128, U*NT = 768 is
-    // exactly six rows: the columns never change)
-    const FastDiv divP = p.divP;
-    const int step_r = (int)fdiv((uint32_t)(U * NT), divP), step_c = U * NT - step_r * P;
-    int rr[U], cc[U];
+    // COMPACT walk: only the slots inside the image and inside the tile's own halo are dealt out (consecutive lanes =
+    // consecutive valid slots, rows of n_c slots), so every MUFU warp instruction works on 32 live lanes -- the pass is
+    // bound by the SFU (4 results / clk / scheduler, tools/ubench/mufu_rate.cu), and a walk over the padded pitch
+    // (sliding mode: 128 slots per row for 66 .. 109 valid ones) spent 15 .. 30 % of its MUFU issues on dead lanes.
+    // The affine and the final h + h*tanh(h) run as packed fp32 pairs (FFMA2: same IEEE results as the scalar FFMAs).
+    constexpr int U = 4;    // slots in flight per thread
+    const int r_lo = max(0, -iy_base), r_hi = min(p.t.rows_sub, (int)H - iy_base);
+    const int c_lo = max(0, -ix_base), c_hi = min(P, (int)W - ix_base);
+    const int n_c = c_hi - c_lo;
+    if (n_c <= 0 || r_hi <= r_lo) return;
+    const int n_items = (r_hi - r_lo) * n_c;
+    const uint32_t mdiv = n_c > 1 ? (uint32_t)(0xFFFFFFFFu / (uint32_t)n_c) + 1u : 0u;   // exact quotients for idx < 2^16
+    const uint32_t base0 = base + (uint32_t)(r_lo * P + c_lo) * 16u;
+    const uint32_t row_skip = (uint32_t)(P - n_c);
+#ifndef MFC_SILU_ACCURATE
+    uint64_t sc2[4], sh2[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = tid + u * NT;
-      rr[u] = (int)fdiv((uint32_t)idx, divP);
-      cc[u] = idx - rr[u] * P;
-      rr[u] += iy_base;
-      cc[u] += ix_base;
-    }
-    const int c_wrap = ix_base + P;
-    for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
-      uint4 v[U];
-      bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        ok[u] = idx0 + u * NT < items && (uint32_t)rr[u] < H && (uint32_t)cc[u] < W;  // padding stays zero
-        if (ok[u]) v[u] = lds16_u32(base + (uint32_t)(idx0 + u * NT) * 16u);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        float f[8];
-        unpack8<BF16>(v[u], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float h = fmaf(f[i], sc[i], sh[i]);
-          f[i] = silu_from_half(h, accurate);
-        }
-        v[u] = pack8<BF16>(f);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (ok[u]) sts16_u32(base + (uint32_t)(idx0 + u * NT) * 16u, v[u]);
-        rr[u] += step_r;
-        cc[u] += step_c;
-        if (cc[u] >= c_wrap) {
-          cc[u] -= P;
-          ++rr[u];
-        }
-      }
-    }
-#else
-    constexpr int U = 4;
-    const FastDiv divP = p.divP;
-    for (int idx0 = tid; idx0 < items; idx0 += U * NT) {
-      uint4 v[U];
-      bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int idx = idx0 + u * NT;
-        const int r = (int)fdiv((uint32_t)idx, divP);
-        const int c = idx - r * P;
-        ok[u] = idx < items && (uint32_t)(iy_base + r) < H && (uint32_t)(ix_base + c) < W;  // padding stays zero
-        if (ok[u]) v[u] = lds16_u32(base + (uint32_t)idx * 16u);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        float f[8];
-        unpack8<BF16>(v[u], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float h = fmaf(f[i], sc[i], sh[i]);
-          f[i] = silu_from_half(h);
-        }
-        v[u] = pack8<BF16>(f);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (ok[u]) sts16_u32(base + (uint32_t)(idx0 + u * NT) * 16u, v[u]);
+    for (int i = 0; i < 4; ++i) {
+      sc2[i] = f32x2_pack(sc[2 * i], sc[2 * i + 1]);
+      sh2[i] = f32x2_pack(sh[2 * i], sh[2 * i + 1]);
     }
 #endif
+    auto slot_addr = [&](uint32_t idx) {
+      const uint32_t r = n_c > 1 ? __umulhi(idx, mdiv) : idx;
+      return base0 + (idx + r * row_skip) * 16u;
+    };
+    auto silu8 = [&](uint4 v) {
+      float f[8];
+      unpack8<BF16>(v, f);
+#ifdef MFC_SILU_ACCURATE
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = silu_from_half(fmaf(f[i], sc[i], sh[i]));
+#else
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint64_t h = f32x2_fma(f32x2_pack(f[2 * i], f[2 * i + 1]), sc2[i], sh2[i]);
+        float h0, h1;
+        f32x2_unpack(h, h0, h1);
+        f32x2_unpack(f32x2_fma(h, f32x2_pack(tanh_fast(h0), tanh_fast(h1)), h), f[2 * i], f[2 * i + 1]);
+      }
+#endif
+      return pack8<BF16>(f);
+    };
+    int idx0 = tid;
+    for (; idx0 + (U - 1) * NT < n_items; idx0 += U * NT) {   // U slots per thread in flight, no predicates
+      uint4 v[U];
+      uint32_t a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u] = slot_addr((uint32_t)(idx0 + u * NT));
+        v[u] = lds16_u32(a[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = silu8(v[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) sts16_u32(a[u], v[u]);
+    }
+    for (; idx0 < n_items; idx0 += NT) {   // the last, partial group
+      const uint32_t a = slot_addr((uint32_t)idx0);
+      sts16_u32(a, silu8(lds16_u32(a)));
+    }
     return;
   }
   const int Hup = p.Hin * p.upsample, Wup = p.Win * p.upsample;
@@ -1067,6 +1049,125 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, uint32_t
   if (slide) tmem_st_wait();
 }
 
+// The epilogue of the layers that dominate ResUNet-16, cut down to what they need: sliding mode, all output channels in one
+// 16-column block, shift-initialised accumulators (values leave TMEM finished), no activation, C8 output, GroupNorm sums.
+// The general fast epilogue re-tests its run-time switches in every sub-step (constant-bank loads, branches, the instruction
+// fetch bubbles behind them: ~125 executed instructions per 16-channel sub-step); this one is straight-line: per run pair one
+// tcgen05.ld.x32, four LDS.128 of the shifts, two tcgen05.st.x16 from the same registers, and per pixel 8 FADD2 + 8 FFMA2 (packed
+// fp32 pairs -- the same IEEE operations, the same order, the same bits), 8 FMNMX3, 8 F2FP and two 16-byte stores.
+template <bool BF16, bool STAGED>
+__device__ __forceinline__ void epilogue_slide16_stats(const ConvParams& p, uint32_t tmem_acc, uint32_t s_shift_addr, float (&d1)[16],
+                                                       float (&d2)[16], int b, int oy0, int ox0, int lq, int half, int lane,
+                                                       float& omax, uint32_t ring, uint32_t& on) {
+  const int R = p.t.R;
+  int r = 2 * half;
+  if (r >= R) return;
+  const int Wout = p.Wout;
+  const int rows_valid = min(p.t.TH, p.Hout - oy0);
+  const int col = lq * 32 + lane;
+  const int cols_valid = min(p.t.TW, Wout - ox0);
+  const bool col_ok = col < cols_valid;
+  const size_t rowb = (size_t)Wout * 16;
+  const size_t plane = (size_t)p.Hout * rowb;
+  const bool two_planes = p.Cout > 8;
+  // STAGED: the row pair is written to shared memory ([row][plane][128 pixels] x 16 bytes, two buffers per warp group) and
+  // leaves the SM as up to four bulk copies (cp.async.bulk shared -> global, one per (row, plane): a tile row of one plane is
+  // contiguous in the C8 tensor), issued by four lanes of ONE warp of the group after a 128-thread barrier.  The warps never
+  // wait for the store path: per-thread 16-byte st.global kept the load/store unit's queue full and the epilogue warps
+  // stalled behind it (measured: 48 of 132 us of a 16->16 3x3 layer at batch 24).  Buffer reuse: the issuing role rotates
+  // over the four warps; the issuer of pair n waits for ITS copies' shared-memory reads one iteration later, before the
+  // barrier of pair n+1 -- which every warp passes before it writes pair n+2 into the same buffer.
+  uint8_t* q = p.y + (size_t)b * p.y_bs + ((size_t)oy0 * Wout + (size_t)(ox0 + (STAGED ? 0 : col))) * 16 + (size_t)r * rowb;
+  uint32_t c = tmem_acc + ((uint32_t)(lq * 32) << 16) + (uint32_t)(r * 16);
+  uint64_t s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s1[i] = f32x2_pack(d1[2 * i], d1[2 * i + 1]);
+    s2[i] = f32x2_pack(d2[2 * i], d2[2 * i + 1]);
+  }
+  const bool no_store = (p.debug & 64) != 0, no_math = (p.debug & 128) != 0;   // measurement switches
+  // dst: global address (direct) or shared-memory address (staged) of this thread's pixel in plane 0
+  auto pixel = [&](const uint32_t* a, uint8_t* gdst, uint32_t sdst) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(a[i]);
+    if (!no_math) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint64_t x = f32x2_pack(f[2 * i], f[2 * i + 1]);
+        s1[i] = f32x2_add(s1[i], x);
+        s2[i] = f32x2_fma(x, x, s2[i]);
+      }
+    }
+#ifndef MFC_NO_OVF_GUARD
+    if (!BF16) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) omax = fmaxf(fmaxf(omax, fabsf(f[i])), fabsf(f[i + 1]));
+    }
+#endif
+    uint4 o, o2;
+    o.x = pack2<BF16>(f[0], f[1]); o.y = pack2<BF16>(f[2], f[3]); o.z = pack2<BF16>(f[4], f[5]); o.w = pack2<BF16>(f[6], f[7]);
+    o2.x = pack2<BF16>(f[8], f[9]); o2.y = pack2<BF16>(f[10], f[11]); o2.z = pack2<BF16>(f[12], f[13]); o2.w = pack2<BF16>(f[14], f[15]);
+    if (no_store) return;
+    if constexpr (STAGED) {
+      sts16_u32(sdst, o);
+      sts16_u32(sdst + 128u * 16u, o2);
+    } else {
+      *reinterpret_cast<uint4*>(gdst) = o;
+      if (two_planes) *reinterpret_cast<uint4*>(gdst + plane) = o2;
+    }
+  };
+  while (true) {
+    const bool pair = r + 1 < R;   // warp-uniform
+    const uint32_t buf = ring + (on & 1u) * (2u * 2u * 128u * 16u);
+    const uint32_t sdst = buf + (uint32_t)col * 16u;
+    // one row (16 columns) at a time: 16 accumulator registers live instead of 32 -- with shared memory at 227 KB the L1 is
+    // a few KB and a spill inside this loop is an L2 round trip (measured: 25 spilled registers per pair = 3x the layer time)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (j == 1 && !pair) break;
+      uint32_t A[16];
+      tmem_ld16(c + (uint32_t)(j * 16), A);
+      float v[16];   // the drained columns start the next item from the shifts again
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 t = lds_f4(s_shift_addr + i * 4);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+      }
+      tmem_ld_wait();
+      tmem_st16v(c + (uint32_t)(j * 16), v);
+      if (col_ok && r + j < rows_valid) pixel(A, q + (size_t)j * rowb, sdst + (uint32_t)j * (2u * 128u * 16u));
+    }
+    if constexpr (STAGED) {
+      if (!(p.debug & 512)) fence_async_smem();   // this thread's generic-proxy writes -> visible to the bulk copy (async proxy)
+      const bool issuer = (on & 3u) == (uint32_t)lq;
+      if (((on - 1u) & 3u) == (uint32_t)lq && !(p.debug & 2048)) bulk_wait_read0();   // my copies of the previous pair have left shared memory
+      if (p.debug & 1024) {
+      } else if (half)
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+      else
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (issuer && lane < 4 && !no_store) {
+        const int j = lane >> 1, h = lane & 1;
+        if (r + j < rows_valid && (j == 0 || pair) && (h == 0 || two_planes))
+          bulk_store(q + (size_t)j * rowb + (h ? plane : 0), buf + (uint32_t)((j * 2 + h) * 128 * 16), (uint32_t)cols_valid * 16u);
+      }
+      if (issuer && !(p.debug & 2048)) bulk_commit();
+      ++on;
+    }
+    r += 4;
+    if (r >= R) break;
+    c += 64;
+    q += 4 * rowb;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f32x2_unpack(s1[i], d1[2 * i], d1[2 * i + 1]);
+    f32x2_unpack(s2[i], d2[2 * i], d2[2 * i + 1]);
+  }
+  tmem_st_wait();
+}
+
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 // Writes this CTA's GroupNorm partial record of one sample ([cpad][2] floats) and clears the accumulators.
@@ -1097,6 +1198,17 @@ __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_stats,
   epi_barrier();
 }
 
+// measurement only (MFC_CONV_DEBUG bit 12): clock stamps of CTA 0's roles for its items 8..15
+// (compiled in with -DMFC_TRACE only: the switch costs the role loops a live register)
+#ifdef MFC_TRACE
+__device__ long long g_trace[3][8][4];
+__device__ __forceinline__ void trace_stamp(bool on, int role, int item, int k) {
+  if (on && item >= 8 && item < 16) g_trace[role][item - 8][k] = clock64();
+}
+#else
+__device__ __forceinline__ void trace_stamp(bool, int, int, int) {}
+#endif
+
 // measurement only (MFC_CONV_DEBUG bit 3): cycles a role spends blocked on each of its barriers
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
   if (!timed) {
@@ -1108,7 +1220,9 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
   acc += clock64() - t0;
 }
 
-template <bool BF16, int MODE, bool NB16, bool FAST>
+// FAST: 0 general epilogue, 1 fast epilogue, 2 fast epilogue + register re-distribution towards the epilogue warps (direct-mode
+// layers only: their producer warps have nothing to transform)
+template <bool BF16, int MODE, bool NB16, int FAST>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -1153,7 +1267,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     }
     if (p.stats)
       for (int i = tid; i < kEpiWarps * cpad * 2; i += kConvThreads) s_stats[i] = 0.0f;
-    if (FAST && MODE == EPI_NCHW && p.head_w != nullptr) {
+    if (FAST != 0 && MODE == EPI_NCHW && p.head_w != nullptr) {
       // fused head: [8][16] weights then [8] biases, parked in the statistics scratch (1 KB at cpad 16; no stats in this mode)
       for (int i = tid; i < 8 * 16; i += kConvThreads) s_stats[i] = i < p.head_n * 16 ? __ldg(p.head_w + i) : 0.0f;
       for (int i = tid; i < 8; i += kConvThreads) s_stats[128 + i] = (p.head_b != nullptr && i < p.head_n) ? __ldg(p.head_b + i) : 0.0f;
@@ -1188,14 +1302,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       // only the columns the two accumulator buffers use (acc_cols each, a multiple of 16), 32 at a time where possible
       const uint32_t used = (uint32_t)p.t.nacc * p.t.acc_cols;
       const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-      if (FAST && p.acc_init && NB == 16) {  // the same 16 shifts in every 16-column block
+      if (FAST != 0 && p.acc_init && NB == 16) {  // the same 16 shifts in every 16-column block
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = s_shift[i];
         uint32_t c = 0;
         for (; c + 32 <= used; c += 32) tmem_st32v(lane_base + c, v, v);
         if (c < used) tmem_st16v(lane_base + c, v);
-      } else if (FAST && p.acc_init) {
+      } else if (FAST != 0 && p.acc_init) {
         for (uint32_t c = 0; c < used; c += 16) {
           float v[16];
           const float* src = s_shift + (c % (uint32_t)NB);
@@ -1218,8 +1332,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   pdl_wait();  // from here on the previous kernel's outputs (activations, GroupNorm affines) are read
   const long long t_setup = clock64();
   const bool timed = (p.debug & 8) != 0;
+#ifdef MFC_TRACE
+  const bool traced = (p.debug & 4096) != 0 && blockIdx.x == 0 && lane == 0;
+#else
+  constexpr bool traced = false;
+#endif
   long long wait_a = 0, wait_b = 0;  // per role: blocked on its input barrier / on its output (back-pressure) barrier
 
+  // Register re-distribution (setmaxnreg acts on warpgroups = 4 consecutive warps; the CTA is launched with 512 x 128): the MMA
+  // and producer warpgroups (warps 8..15) give up 16 registers per thread, the two epilogue warpgroups (warps 0..7) take them.
+  // The statistics epilogue keeps 32 GroupNorm accumulators live across its whole item loop; at 128 registers it spills loop
+  // state, and with 227 KB of shared memory carved out the L1 is too small for the CTA's local frames -- every reload is an L2
+  // round trip (ncu: ~15 % of the epilogue warps' time on `long scoreboard` behind LDL; 16->16 3x3 + statistics at batch 24:
+  // 121 -> 99 us).  Only for direct-mode layers (FAST == 2): with 112 registers the SiLU pass of the producers spills instead.
+  if constexpr (FAST == 2) {
+    if (warp >= kMmaWarp0)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    else
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+  }
   if (warp >= kProdWarp0) {
     // =========================================================== producers
     // Software pipeline: the raw copies of stage i+D are in flight (cp.async) while stage i is
@@ -1236,6 +1367,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         if (!tma || ptid == 0 || (p.debug & 1)) {
           const ItemCoord c = decode_item(p, wi);
           mbar_wait_t(&bar_empty[slot_i], phase_i ^ 1u, timed, wait_b);  // the MMAs that read this slot have drained
+          trace_stamp(traced && ptid == 0, 2, (wi - (int)blockIdx.x) / (int)gridDim.x, 0);
           uint8_t* abuf = stage0 + (size_t)slot_i * p.t.stage_bytes;
           const int iy_base = c.oy0 * p.stride - p.pad + p.in_off_y, ix_base = c.ox0 * p.stride - p.pad + p.in_off_x;
           if (!(p.debug & 1)) {
@@ -1244,6 +1376,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             else
               issue_stage<kProdThreads>(p, abuf, c.b, c.nbk, ksi, iy_base, ix_base, ptid);
           }
+          trace_stamp(traced && ptid == 0, 2, (wi - (int)blockIdx.x) / (int)gridDim.x, 1);
         }
         if (++ksi == p.t.kstages) {
           ksi = 0;
@@ -1285,9 +1418,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         transform_stage<BF16, kProdThreads>(p, stage0 + (size_t)slot_t * p.t.stage_bytes, c.b, kst,
                                             c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x, ptid, aff0);
       }
+      trace_stamp(traced && ptid == 0, 2, (wt - (int)blockIdx.x) / (int)gridDim.x, 2);
       fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[slot_t]);
+      trace_stamp(traced && ptid == 0, 2, (wt - (int)blockIdx.x) / (int)gridDim.x, 3);
       if (++kst == p.t.kstages) {
         kst = 0;
         wt += gridDim.x;
@@ -1316,11 +1451,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       const uint32_t use = p.t.nacc == 2 ? (uint32_t)(item >> 1) : (uint32_t)item;
       mbar_wait_t(&bar_tempty[acc_i], (use & 1u) ^ 1u, timed, wait_b);  // the epilogue has drained this accumulator buffer
       tc_fence_after();
+      trace_stamp(traced && mw == 0, 1, item, 0);
       const uint32_t tmem_acc = tmem_base + (uint32_t)acc_i * p.t.acc_cols;
       int ecount = 0, aset = 0;
       for (int ks = 0; ks < p.t.kstages; ++ks) {
         mbar_wait_t(p.direct ? &bar_tma[stage] : &bar_full[stage], phase, timed, wait_a);
         tc_fence_after();
+        trace_stamp(traced && mw == 0, 1, item, 1);
         if (elect_one_sync()) {
           const int kh_eff = (p.debug & 4) ? 0 : p.kh;
           const uint8_t* abuf = stage0 + (size_t)stage * p.t.stage_bytes;
@@ -1412,6 +1549,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
           if (ks == p.t.kstages - 1) umma_commit(&bar_tfull[acc_i]);   // accumulators complete
         }
         __syncwarp();
+        trace_stamp(traced && mw == 0, 1, item, 2);
         if (++stage == p.t.nstages) {
           stage = 0;
           phase ^= 1u;
@@ -1431,8 +1569,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       d1[i] = d2[i] = 0.0f;
-      sc[i] = (NB16 && !FAST) ? s_scale[i] : 1.0f;
-      sh[i] = (NB16 && !FAST) ? s_shift[i] : 0.0f;
+      sc[i] = (NB16 && FAST == 0) ? s_scale[i] : 1.0f;
+      sh[i] = (NB16 && FAST == 0) ? s_shift[i] : 0.0f;
     }
     // stats layout: [B][grid][cpad][2]; this CTA owns record blockIdx.x of every sample
     const size_t rec_stride = (size_t)cpad * 2;
@@ -1443,6 +1581,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         for (int i = warp * 32 + lane; i < cpad * 2; i += kEpiWarps * 32) my_rec[(size_t)bb * img_stride + i] = 0.0f;
     }
     int cur_b = -1, aff_b = -1;
+    static_assert(kEpiWarps == 8, "epilogue_slide16_stats: two warps per TMEM lane quarter");
+    const bool slide16 = FAST != 0 && MODE == EPI_STATS && p.t.slide && p.acc_init && p.act == 0 && has_stats && p.y != nullptr &&
+                         p.y_lo == nullptr && !(p.debug & 32);
+    // output staging ring of this warp group (half): bulk-copy stores (epilogue_slide16_stats<STAGED>)
+    const uint32_t out_ring = (slide16 && p.t.off_ostage != 0 && !(p.debug & 256))
+                                  ? smem_u32(smem + p.t.off_ostage) + (uint32_t)half * (uint32_t)(kOutStageBytes / 2) : 0u;
+    uint32_t out_n = 0;
     const bool res_aff_smem = (MODE == EPI_RES || MODE == EPI_GENERIC) && p.res != nullptr && p.res_aff != nullptr && !has_stats && cpad <= 256;
     ResPrefetch rp;
     rp.ring = smem_u32(smem + p.t.off_resring) + (uint32_t)warp * (kResDepth * 1024u);
@@ -1462,8 +1607,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
       const int acc_i = p.t.nacc == 2 ? (item & 1) : 0;
       const uint32_t use = p.t.nacc == 2 ? (uint32_t)(item >> 1) : (uint32_t)item;
+      trace_stamp(traced && warp == 0, 0, item, 0);
       mbar_wait_t(&bar_tfull[acc_i], use & 1u, timed, wait_a);
       tc_fence_after();
+      trace_stamp(traced && warp == 0, 0, item, 1);
       if (res_aff_smem && c.b != aff_b) {  // park (s/2, t/2) of this sample's residual affine in the warp's smem slot
         aff_b = c.b;
         const int nch = ((p.Cout + 7) >> 3) << 3;
@@ -1476,18 +1623,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         __syncwarp();
       }
       if (!(p.debug & 2)) {
-        if constexpr (FAST)
+        if constexpr (FAST != 0 && MODE == EPI_STATS) {
+          if (slide16 && out_ring != 0)
+            epilogue_slide16_stats<BF16, true>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_shift), d1, d2, c.b, c.oy0, c.ox0,
+                                               lq, half, lane, omax, out_ring, out_n);
+          else if (slide16)
+            epilogue_slide16_stats<BF16, false>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_shift), d1, d2, c.b, c.oy0, c.ox0,
+                                                lq, half, lane, omax, 0u, out_n);
+          else
+            epilogue_tile_fast<BF16, MODE>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_shift), smem_u32(s_stats), d1,
+                                                  d2, c.b, c.oy0, c.ox0, lq, half, lane, omax);
+        } else if constexpr (FAST != 0)
           epilogue_tile_fast<BF16, MODE>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_shift), smem_u32(s_stats), d1, d2, c.b,
                                          c.oy0, c.ox0, lq, half, lane, omax);
         else
           epilogue_tile<BF16, MODE, NB16>(p, tmem_base + (uint32_t)acc_i * p.t.acc_cols, smem_u32(s_scale), my_stats, d1, d2, sc, sh,
                                           c.b, c.oy0, c.ox0, c.nbk, lq, half, lane, res_aff_smem, rp, total_items, omax);
       }
+      trace_stamp(traced && warp == 0, 0, item, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc_i]);
     }
     if (has_stats && cur_b >= 0) flush_stats(p, s_stats, warp, d1, d2, my_rec + (size_t)cur_b * img_stride, lane);
+    if (out_ring != 0) bulk_wait_all();   // the bulk copies issued by this thread have been written
     // a stored value beyond the fp16 range became +-inf: count it where the host can see it (MfcConvIO.overflow)
     if (!BF16 && p.ovf != nullptr && __any_sync(0xffffffffu, !(omax <= kF16Max)) && lane == 0) atomicAdd(p.ovf, 1);
   }
@@ -1499,6 +1658,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
            (total_items + (int)gridDim.x - 1) / (int)gridDim.x, t_alloc - t_entry, t_prewait - t_alloc, t_setup - t_prewait);
   tc_fence_before();
   __syncthreads();
+#ifdef MFC_TRACE
+  if ((p.debug & 4096) && blockIdx.x == 0 && tid == 0) {
+    const long long t0 = g_trace[2][0][0];
+    for (int i = 0; i < 8; ++i)
+      printf("trace item %2d: load[slot free %6lld issued %6lld | landed/xf done %6lld handed %6lld]  mma[acc free %6lld data %6lld issued %6lld]  "
+             "epi[ready %6lld acc full %6lld done %6lld]\n", i + 8, g_trace[2][i][0] - t0, g_trace[2][i][1] - t0, g_trace[2][i][2] - t0,
+             g_trace[2][i][3] - t0, g_trace[1][i][0] - t0, g_trace[1][i][1] - t0, g_trace[1][i][2] - t0, g_trace[0][i][0] - t0,
+             g_trace[0][i][1] - t0, g_trace[0][i][2] - t0);
+  }
+#endif
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.t.tmem_cols);
@@ -1620,18 +1789,27 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
   const bool slide_ok = s == 1 && d.kh > 1 && nblk == 1 && d.kh * NB <= 256 && d.out_stride != 2 && force_slide != 0;
   // evaluates one tile shape; slide = sliding-accumulate mode (P must be 128: one MMA run per input row)
   auto consider = [&](int TH, int TW, int nx, bool slide) -> bool {  // false: TH too large for this TW (stop growing it)
+    const uint32_t tmem_cap = 512u;
+    const uint64_t smem_cap = (uint64_t)kSmemPerCtaMax;
+    const int sm_ctas = kSmCount;
     const int P = slide ? 128 : TW + hx;
+    // statistics layers in sliding mode with one 16-column block: the epilogue stages its output rows in shared memory and
+    // stores them with bulk copies (epilogue_slide16_stats); the ring sits where a residual layer has its prefetch ring
+    // (measurement switch, off by default: the staged stores were measured SLOWER than direct 16-byte stores)
+    static const int want_ostage = getenv("MFC_CONV_OSTAGE") ? atoi(getenv("MFC_CONV_OSTAGE")) : 0;
+    const bool ostage = want_ostage != 0 && slide && NB == 16 && nblk == 1 && (d.reserved & MFC_CONV_WANT_STATS) && !has_res &&
+                        d.out_stride != 2;
     const int entries = slide ? (pair ? (d.kw + 1) / 2 : d.kw) : (pair ? d.kh * ((d.kw + 1) / 2) : d.kh * d.kw);  // B blocks per K step
     const int nrows_b = slide ? d.kh * NB : NB;
     const uint64_t w_bytes_nblk = (uint64_t)ksteps * entries * 2 * nrows_b * 16;  // one N-block's packed weights
     const int R = slide ? TH : ceil_div((TH - 1) * P + TW, 128);  // accumulator runs ([run][NB] column blocks)
-    if ((uint32_t)(R * NB) > 512) return false;
+    if ((uint32_t)(R * NB) > tmem_cap) return false;
     // a dependent accumulate costs ~167 cycles, an independent N<=32 MMA ~39: every issuing warp wants
     // >= 4 accumulators to rotate over.  Tiles with few runs split K over kacc accumulator sets.
     int kacc = 1;
     if (!slide)
-      while (kacc < 4 && ceil_div(R * kacc, kMmaWarps) < 4 && R * NB * kacc * 2 <= 512 && kacc * 2 <= entries * ksteps) kacc *= 2;
-    const int nacc = (2 * R * NB * kacc <= 512) ? 2 : 1;
+      while (kacc < 4 && ceil_div(R * kacc, kMmaWarps) < 4 && R * NB * kacc * 2 <= (int)tmem_cap && kacc * 2 <= entries * ksteps) kacc *= 2;
+    const int nacc = (2 * R * NB * kacc <= (int)tmem_cap) ? 2 : 1;
     const uint32_t tmem = pow2_at_least((uint32_t)(nacc * R * NB * kacc), 32);
     const int rows_sub = TH + hy;
     int slots_sub = slide ? rows_sub * P + hx + 1 : std::max(R * 128 + hy * P + hx, rows_sub * P);
@@ -1654,9 +1832,9 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
       const uint32_t lo_plane_bytes = ups_tma ? ((uint32_t)(P_lo * rows_lo) * 16u + 127u) & ~127u : 0u;
       const uint64_t off_lo = ((uint64_t)a_stage + (resident ? 0 : b_stage) + 127) & ~(uint64_t)127;
       const uint64_t stage_bytes = (off_lo + (uint64_t)CBc * lo_plane_bytes + 127) & ~(uint64_t)127;
-      const uint64_t off_stage = ((uint64_t)off_bres + (resident ? w_bytes_nblk : 0) + 127) & ~(uint64_t)127;
-      if (off_stage + stage_bytes + 128 > (uint64_t)kSmemPerCtaMax) continue;
-      int nstages = (int)(((uint64_t)kSmemPerCtaMax - 128 - off_stage) / stage_bytes);
+      const uint64_t off_stage = ((uint64_t)off_bres + (ostage ? kOutStageBytes : 0) + (resident ? w_bytes_nblk : 0) + 127) & ~(uint64_t)127;
+      if (off_stage + stage_bytes + 128 > smem_cap) continue;
+      int nstages = (int)((smem_cap - 128 - off_stage) / stage_bytes);
       nstages = std::min(nstages, kstages > 1 ? 6 : 4);
       nstages = std::min(nstages, kMaxStages);
       if (nstages < 1) continue;
@@ -1700,7 +1878,7 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
         M = 500.0 + (double)entries * ksteps * per_entry;
       }
       const double E = 400.0 + (double)((R + 1) / 2) * (NB / 16) * (475.0 + 120.0 * (kacc - 1) + (slide ? 30.0 : 0.0));
-      const int G = (int)std::min<long long>(items, kSmCount);
+      const int G = (int)std::min<long long>(items, sm_ctas);
       const double rounds = std::ceil((double)items / G);
       double per_item;
       if (nstages >= 2) {
@@ -1722,7 +1900,9 @@ static void conv_enumerate(const MfcConvDesc& d, std::vector<std::pair<double, C
         best.plane_bytes = plane_bytes; best.a_stage_bytes = a_stage; best.b_stage_bytes = (uint32_t)b_stage;
         best.stage_bytes = (uint32_t)stage_bytes;
         best.smem_bytes = smem; best.tmem_cols = tmem; best.acc_cols = (uint32_t)(R * NB * kacc);
-        best.off_scale = off_scale; best.off_stats = off_stats; best.off_resring = off_resring; best.off_bres = off_bres; best.off_stage = (uint32_t)off_stage;
+        best.off_scale = off_scale; best.off_stats = off_stats; best.off_resring = off_resring;
+        best.off_bres = off_bres + (ostage ? (uint32_t)kOutStageBytes : 0u); best.off_stage = (uint32_t)off_stage;
+        best.off_ostage = ostage ? off_bres : 0u;
         best.grid = G;
         all.emplace_back(cost, best);
       }
@@ -1789,7 +1969,7 @@ void conv_shortlist(const MfcConvDesc& d, int per_bucket, std::vector<ConvTiling
   }
 }
 
-template <bool BF16, int MODE, bool NB16, bool FAST>
+template <bool BF16, int MODE, bool NB16, int FAST>
 static cudaError_t launch_conv_inst(const ConvParams& p, cudaStream_t st) {
   static int configured_for = -1;
   int dev = 0;
@@ -1818,10 +1998,15 @@ template <bool BF16, int MODE>
 static cudaError_t launch_conv_mode(const ConvParams& p, cudaStream_t st) {
   // the fast epilogue serves the statistics layers and the fp32-output / fused-head layers; plain C8 layers keep the general
   // path (measured: its convert-then-prefetch loop is faster than the fast path's two alternating accumulator arrays)
-  if constexpr (MODE == EPI_STATS || MODE == EPI_NCHW) {
-    if (p.epi_fast) return launch_conv_inst<BF16, MODE, true, true>(p, st);
+  if constexpr (MODE == EPI_STATS) {
+    // direct-mode statistics layers: the kernel that hands 16 registers per thread from the idle producers to the epilogue
+    static const int no_smr = getenv("MFC_CONV_SETMAXNREG") ? (atoi(getenv("MFC_CONV_SETMAXNREG")) == 0) : 0;
+    if (p.epi_fast && p.direct && !no_smr) return launch_conv_inst<BF16, MODE, true, 2>(p, st);
   }
-  return p.t.NB == 16 ? launch_conv_inst<BF16, MODE, true, false>(p, st) : launch_conv_inst<BF16, MODE, false, false>(p, st);
+  if constexpr (MODE == EPI_STATS || MODE == EPI_NCHW) {
+    if (p.epi_fast) return launch_conv_inst<BF16, MODE, true, 1>(p, st);
+  }
+  return p.t.NB == 16 ? launch_conv_inst<BF16, MODE, true, 0>(p, st) : launch_conv_inst<BF16, MODE, false, 0>(p, st);
 }
 
 template <bool BF16>

@@ -8,6 +8,7 @@
 namespace mfc {
 
 // warp roles of conv_tc_kernel (one persistent CTA per SM)
+constexpr int kOutStageBytes = 2 * 2 * 2 * 2 * 128 * 16;   // [warp group][buffer][row of the pair][plane][128 pixels] x 16 bytes
 constexpr int kEpiWarps = 8;                       // warps 0..7 : TMEM -> registers -> global (lane quarter = warp % 4)
 constexpr int kMmaWarp0 = kEpiWarps;               // warps 8..9  : tcgen05.mma issue (one elected lane each; warp i
 constexpr int kMmaWarps = 2;                       //               issues the runs r = i, i+2, ...: a single thread
@@ -58,6 +59,7 @@ struct ConvTiling {
   uint32_t acc_cols;       // kacc * R * NB, columns of one accumulator buffer
   uint32_t off_resring;    // residual prefetch rings of the epilogue warps (only with MFC_CONV_HAS_RESIDUAL)
   uint32_t off_scale, off_stats, off_bres, off_stage;  // smem carve-up (bytes from the 128B-aligned base)
+  uint32_t off_ostage;     // != 0: output staging ring of the slide16 statistics epilogue (kOutStageBytes; bulk-copy stores)
   int grid;                // persistent CTAs
 };
 
