@@ -1245,16 +1245,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   const int total_items = p.B * p.t.tiles_x * p.t.tiles_y * p.t.nblk;
   const int ksteps_per_stage = p.t.CBc / 2;
 
+  // Sliding mode issues all MMAs from warp 8; warp 9 then is the LOADER: one lane keeps the TMA ring full (wait for a free
+  // slot, issue the stage's box loads), so that no producer warp's share of the transform waits behind the 1 400 - 1 800
+  // cycles an issue costs (per-item trace), and a slot is refilled the moment its MMAs retire.
+  // (not in the FAST == 2 kernels: their layers are direct-mode, the ring is kept full by an otherwise idle producer lane,
+  // and a fourth role inside the register-reduced warpgroup made ptxas spill 650 instead of 130 bytes in the epilogue)
+  const bool loader9 = FAST != 2 && p.t.tma != 0 && p.t.slide != 0 && !(p.debug & (1 | 16384));
+  const int n_mma = loader9 ? 1 : kMmaWarps;   // warps committing MMAs (arrivals on bar_empty / bar_tfull)
+
   // ---- one-time setup (independent of the previous kernel's output: overlaps its tail under PDL)
   pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < p.t.nstages; ++i) {
       mbar_init(&bar_full[i], kProdWarps);
-      mbar_init(&bar_empty[i], kMmaWarps);
+      mbar_init(&bar_empty[i], n_mma);
       mbar_init(&bar_tma[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_tfull[i], kMmaWarps);
+      mbar_init(&bar_tfull[i], n_mma);
       mbar_init(&bar_tempty[i], kEpiWarps);
     }
     fence_mbar_init();
@@ -1363,6 +1371,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     const bool tma = p.t.tma != 0;
     uint32_t phase_t = 0;
     auto issue_next = [&]() {
+      if (loader9) return;   // warp 9 issues
       if (wi < total_items) {
         if (!tma || ptid == 0 || (p.debug & 1)) {
           const ItemCoord c = decode_item(p, wi);
@@ -1392,7 +1401,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     if (p.direct) {
       // nothing to transform: the MMA warps consume the stages straight off the TMA barriers; this thread only keeps
       // the ring full (each issue waits for its slot's MMAs to retire)
-      if (ptid == 0)
+      if (ptid == 0 && !loader9)
         while (wi < total_items) issue_next();
       wt = total_items;
     }
@@ -1434,6 +1443,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       if (D > 0) issue_next();
     }
     cp_async_wait_group<0>();
+  } else if (loader9 && warp == kMmaWarp0 + 1) {
+    // =========================================================== loader (sliding mode): the TMA ring
+    if (lane == 0) {
+      int slot = 0, ksi = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_items;) {
+        const ItemCoord c = decode_item(p, w);
+        mbar_wait_t(&bar_empty[slot], phase ^ 1u, timed, wait_b);  // the MMAs that read this slot have retired
+        issue_stage_tma(p, stage0 + (size_t)slot * p.t.stage_bytes, &bar_tma[slot], c.b, c.nbk, ksi,
+                        c.oy0 * p.stride - p.pad + p.in_off_y, c.ox0 * p.stride - p.pad + p.in_off_x);
+        if (++ksi == p.t.kstages) {
+          ksi = 0;
+          w += gridDim.x;
+        }
+        if (++slot == p.t.nstages) {
+          slot = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp >= kMmaWarp0) {
     // =========================================================== MMA issue (warp i: runs r = i, i+kMmaWarps, ...)
     const int mw = warp - kMmaWarp0;
