@@ -389,6 +389,54 @@ int mfc_unflow_warp(const float* second, const float* flow, const float* first /
 int mfc_unflow_upscale(const float* x, const float* w, float* out, int B, int h, int w_in, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * RAFT-large, the online optical-flow provider of the video loop (scripts/test_multiframe_segmentation_on_videos_v3.py:264-271,
+ * 342-350 and src/engine.py:39-53 call torchvision.models.optical_flow.raft_large -- a third-party dependency of the reference,
+ * torchvision 0.26 `models/optical_flow/raft.py`).  Its convolutions run through mfc_conv2d_fwd; these are the other pieces.
+ *   mfc_pointwise : element-wise glue on dense C8 tensors [B][chunks][pixels][8] (kind below)
+ *   mfc_raft_op   : correlation volume / pyramid pooling / pyramid lookup / flow update / convex upsampling (kind below)
+ * ---------------------------------------------------------------------------------- */
+#define MFC_PW_AFFINE_ADD 0  /* out = [relu_out]( [relu_a](a*s_a + t_a) + (r*s_r + t_r) ); a_aff / r / r_aff may be NULL
+                                (ResidualBlock.forward with InstanceNorm: relu(x + relu(norm(conv(.))))); affines [B][chunks*8][2] */
+#define MFC_PW_CTX_SPLIT 1   /* a has 2*chunks planes: out = tanh(a[:, :chunks]), out2 = relu(a[:, chunks:]) (RAFT.forward)  */
+#define MFC_PW_GRU_RH 2      /* a = fused z|r pre-activations (2*chunks planes), r = h: out = sigmoid(a[:, chunks:]) * h      */
+#define MFC_PW_GRU_UPDATE 3  /* a = z|r, r = q pre-activation, out = h IN PLACE: h = (1-sigmoid(z))*h + sigmoid(z)*tanh(q)   */
+typedef struct MfcPointwiseArgs {
+  const void* a;
+  const float* a_aff;
+  const void* r;
+  const float* r_aff;
+  void* out;
+  void* out2;
+  long long pixels;
+  int kind, B, chunks, dtype, relu_a, relu_out;
+} MfcPointwiseArgs;
+int mfc_pointwise(const MfcPointwiseArgs* a, void* stream);
+
+#define MFC_RAFT_CORR_VOLUME 0 /* p0 = fmap1, p1 = fmap2 (fp32 [B][C][h*w]), p2 = out fp32 [B][h*w][h*w] = <f1_i, f2_j> * scale
+                                  (CorrBlock._compute_corr_volume: scale = 1/sqrt(C))                                           */
+#define MFC_RAFT_POOL 1        /* p0 = in fp32 [B][h][w] (B = all leading dimensions), p1 = out [B][h/2][w/2]: avg_pool2d(2, 2)  */
+#define MFC_RAFT_LOOKUP 2      /* p0..p3 = pyramid levels ([B*h*w][h>>l][w>>l]), p4 = flow fp32 [B][2][h][w] (coords1 - coords0),
+                                  p5 = out C8 [B][ceil(levels*(2r+1)^2 / 8)][h][w][8]  (CorrBlock.index_pyramid)                 */
+#define MFC_RAFT_FLOW_ADD 3    /* p0 = flow fp32 [B][2][h][w] += p1 = delta_flow                                                */
+#define MFC_RAFT_UPSAMPLE 4    /* p0 = flow fp32 [B][2][h][w], p1 = mask fp32 [B][576][h][w] (before the multiplier `scale`),
+                                  p2 = out fp32 [B][2][8h][8w]  (upsample_flow with up_mask)                                     */
+#define MFC_RAFT_RESIZE_AC 5   /* p0 = in fp32 [B][C][h][w], p2 = out fp32 [B][C][levels][radius] (levels = Hout, radius = Wout):
+                                  F.interpolate(in * scale, size, mode='bilinear', align_corners=True) -- the video script's resize
+                                  of flow / 0.5 to the frame size (scripts/test_multiframe_segmentation_on_videos_v3.py:269)      */
+typedef struct MfcRaftArgs {
+  const void* p0;
+  const void* p1;
+  const void* p2;
+  const void* p3;
+  const void* p4;
+  void* p5;
+  int kind, B, C, h, w, levels, radius, dtype;
+  float scale;
+  int reserved;
+} MfcRaftArgs;
+int mfc_raft_op(const MfcRaftArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * UnFlow correlation cost volume (models/unflow_correlation.py:10-105,282-337).
  * first/second: fp32 NCHW contiguous; out: fp32 [B][D*D][H][W], D = 2*(max_disp/stride2)+1,
  * out[b,(iy*D+ix),y,x] = mean_c first[b,c,y,x]*second[b,c,y+dy,x+dx], zero outside.
@@ -481,6 +529,8 @@ int mfc_refine_tip_mask(const uint8_t* mask, int H, int W, const int* labels, co
 #define MFC_OP_RESIZE 7          /* a = MfcResizeArgs*                */
 #define MFC_OP_MAXPOOL2 8        /* a = MfcPoolArgs*                  */
 #define MFC_OP_HEATMAP 9         /* a = MfcHeatmapArgs*               */
+#define MFC_OP_POINTWISE 10      /* a = MfcPointwiseArgs*             */
+#define MFC_OP_RAFT 11           /* a = MfcRaftArgs*                  */
 
 typedef struct MfcGnArgs {
   const float* stats;

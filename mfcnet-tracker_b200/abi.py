@@ -18,6 +18,9 @@ MFC_CONV_WANT_STATS = 4
 MFC_CONV_WANT_HEAD = 8
 OP_FORK, OP_JOIN, MFC_MAX_LANES = 100, 101, 4
 OP_CONV, OP_GN_FINALIZE, OP_AFFINE_SILU_ADD, OP_GATHER, OP_WARP, OP_FUSE_SUM, OP_RESIZE, OP_MAXPOOL2, OP_HEATMAP = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OP_POINTWISE, OP_RAFT = 10, 11
+PW_AFFINE_ADD, PW_CTX_SPLIT, PW_GRU_RH, PW_GRU_UPDATE = 0, 1, 2, 3
+RAFT_CORR_VOLUME, RAFT_POOL, RAFT_LOOKUP, RAFT_FLOW_ADD, RAFT_UPSAMPLE, RAFT_RESIZE_AC = 0, 1, 2, 3, 4, 5
 
 c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -101,6 +104,17 @@ class MfcHeatmapArgs(C.Structure):
                 ("B", c_int), ("N", c_int)]
 
 
+class MfcPointwiseArgs(C.Structure):
+    _fields_ = [("a", c_void_p), ("a_aff", c_void_p), ("r", c_void_p), ("r_aff", c_void_p), ("out", c_void_p), ("out2", c_void_p),
+                ("pixels", c_ll), ("kind", c_int), ("B", c_int), ("chunks", c_int), ("dtype", c_int), ("relu_a", c_int), ("relu_out", c_int)]
+
+
+class MfcRaftArgs(C.Structure):
+    _fields_ = [("p0", c_void_p), ("p1", c_void_p), ("p2", c_void_p), ("p3", c_void_p), ("p4", c_void_p), ("p5", c_void_p),
+                ("kind", c_int), ("B", c_int), ("C", c_int), ("h", c_int), ("w", c_int), ("levels", c_int), ("radius", c_int),
+                ("dtype", c_int), ("scale", c_float), ("reserved", c_int)]
+
+
 class MfcCmd(C.Structure):
     _fields_ = [("op", c_int), ("lane", c_int), ("a", c_void_p), ("b", c_void_p)]
 
@@ -124,6 +138,8 @@ _SIGNATURES = {
     "mfc_gn_finalize": ([c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p], c_int),
     "mfc_affine_silu_add": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_void_p], c_int),
     "mfc_flow_warp": ([C.POINTER(MfcWarpArgs), c_void_p], c_int),
+    "mfc_pointwise": ([C.POINTER(MfcPointwiseArgs), c_void_p], c_int),
+    "mfc_raft_op": ([C.POINTER(MfcRaftArgs), c_void_p], c_int),
     "mfc_maxpool2": ([c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_fuse_sum": ([C.POINTER(MfcFuseArgs), c_void_p], c_int),
     "mfc_bilinear_resize": ([C.POINTER(MfcResizeArgs), c_void_p], c_int),

@@ -19,7 +19,7 @@ _TAG = os.environ.get("MFC_B200_LIB_TAG", "")
 LIB = os.path.join(LIBDIR, "libmfcnet_b200%s.so" % (("_" + _TAG) if _TAG else ""))
 if _TAG:
     OBJDIR = OBJDIR + "_" + _TAG
-UNITS = ["api", "conv_tc", "pointwise", "fusion_ops", "resample", "loss", "train_ops", "correlation", "correlation_tma", "ingest", "localize", "unflow_ops"]
+UNITS = ["api", "conv_tc", "pointwise", "fusion_ops", "resample", "loss", "train_ops", "correlation", "correlation_tma", "ingest", "localize", "unflow_ops", "raft_ops"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

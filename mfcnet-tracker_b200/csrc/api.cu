@@ -837,6 +837,55 @@ int mfc_unflow_upscale(const float* x, const float* w, float* out, int B, int h,
   MFC_LAUNCH(mfc::launch_unflow_upscale(x, w, out, B, h, w_in, scale, (cudaStream_t)stream), "unflow_upscale");
 }
 
+// ---- RAFT pieces ---------------------------------------------------------------------------------
+int mfc_pointwise(const MfcPointwiseArgs* a, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!a || !a->a || !a->out || a->B < 1 || a->chunks < 1 || a->pixels < 1 || !dtype_ok(a->dtype) || a->kind < 0 || a->kind > 3)
+    return fail(MFC_EINVAL, "pointwise: bad argument");
+  if ((a->kind == MFC_PW_CTX_SPLIT && !a->out2) || ((a->kind == MFC_PW_GRU_RH || a->kind == MFC_PW_GRU_UPDATE) && !a->r))
+    return fail(MFC_EINVAL, "pointwise: kind %d misses an operand", a->kind);
+  MFC_LAUNCH(mfc::launch_pointwise(a->kind, a->a, a->a_aff, a->r, a->r_aff, a->out, a->out2, a->B, a->chunks, a->pixels, a->relu_a,
+                                   a->relu_out, a->dtype == MFC_BF16, (cudaStream_t)stream), "pointwise");
+}
+
+int mfc_raft_op(const MfcRaftArgs* a, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!a || a->B < 1 || a->h < 1 || a->w < 1) return fail(MFC_EINVAL, "raft_op: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->kind) {
+    case MFC_RAFT_CORR_VOLUME:
+      if (!a->p0 || !a->p1 || !a->p2 || a->C < 1) return fail(MFC_EINVAL, "raft_op: corr_volume needs p0, p1, p2, C");
+      MFC_LAUNCH(mfc::launch_raft_corr_volume((const float*)a->p0, (const float*)a->p1, (float*)a->p2, a->B, a->C, a->h * a->w, a->scale, st),
+                 "raft corr_volume");
+    case MFC_RAFT_POOL:
+      if (!a->p0 || !a->p1 || a->h < 2 || a->w < 2) return fail(MFC_EINVAL, "raft_op: pool needs p0, p1 and h, w >= 2");
+      MFC_LAUNCH(mfc::launch_raft_corr_pool((const float*)a->p0, (float*)a->p1, (long long)a->B, a->h, a->w, st), "raft pool");
+    case MFC_RAFT_LOOKUP: {
+      if (!a->p0 || !a->p4 || !a->p5 || a->levels < 1 || a->levels > 4 || a->radius < 0 || a->radius > 8 || !dtype_ok(a->dtype))
+        return fail(MFC_EINVAL, "raft_op: lookup needs 1..4 levels, flow, out");
+      if ((a->h >> (a->levels - 1)) < 2 || (a->w >> (a->levels - 1)) < 2) return fail(MFC_EINVAL, "raft_op: feature map too small for %d levels", a->levels);
+      const float* lvl[4] = {(const float*)a->p0, (const float*)a->p1, (const float*)a->p2, (const float*)a->p3};
+      for (int i = 0; i < a->levels; ++i)
+        if (!lvl[i]) return fail(MFC_EINVAL, "raft_op: lookup level %d missing", i);
+      const int side = 2 * a->radius + 1, chunks = (a->levels * side * side + 7) / 8;
+      MFC_LAUNCH(mfc::launch_raft_lookup(lvl, (const float*)a->p4, a->p5, a->B, a->h, a->w, a->levels, a->radius, chunks, a->dtype == MFC_BF16, st),
+                 "raft lookup");
+    }
+    case MFC_RAFT_FLOW_ADD:
+      if (!a->p0 || !a->p1) return fail(MFC_EINVAL, "raft_op: flow_add needs p0, p1");
+      MFC_LAUNCH(mfc::launch_raft_flow_add((float*)a->p0, (const float*)a->p1, (long long)a->B * 2 * a->h * a->w, st), "raft flow_add");
+    case MFC_RAFT_UPSAMPLE:
+      if (!a->p0 || !a->p1 || !a->p2) return fail(MFC_EINVAL, "raft_op: upsample needs p0, p1, p2");
+      MFC_LAUNCH(mfc::launch_raft_upsample((const float*)a->p0, (const float*)a->p1, (float*)a->p2, a->B, a->h, a->w, a->scale, st), "raft upsample");
+    case MFC_RAFT_RESIZE_AC:
+      if (!a->p0 || !a->p2 || a->C < 1 || a->levels < 1 || a->radius < 1) return fail(MFC_EINVAL, "raft_op: resize needs p0, p2, C, Hout, Wout");
+      MFC_LAUNCH(mfc::launch_raft_resize_ac((const float*)a->p0, (float*)a->p2, a->B * a->C, a->h, a->w, a->levels, a->radius, a->scale, st),
+                 "raft resize");
+    default:
+      return fail(MFC_EINVAL, "raft_op: kind %d unknown", a->kind);
+  }
+}
+
 // ---- key points --------------------------------------------------------------------------------
 int mfc_gaussian_blur(const float* heat, float* tmp, float* out, int B, int H, int W, const double* weights_dev, int radius, void* stream) {
   MFC_REQUIRE_ARCH();
@@ -971,6 +1020,12 @@ int run_list_impl(const MfcCmd* cmds, int n, void* main_stream, bool use_lanes) 
       }
       case MFC_OP_WARP:
         rc = mfc_flow_warp((const MfcWarpArgs*)c.a, stream);
+        break;
+      case MFC_OP_POINTWISE:
+        rc = mfc_pointwise((const MfcPointwiseArgs*)c.a, stream);
+        break;
+      case MFC_OP_RAFT:
+        rc = mfc_raft_op((const MfcRaftArgs*)c.a, stream);
         break;
       case MFC_OP_FUSE_SUM:
         rc = mfc_fuse_sum((const MfcFuseArgs*)c.a, stream);

@@ -75,6 +75,17 @@ cudaError_t launch_unflow_warp(const float* second, const float* flow, const flo
                                int H, int W, cudaStream_t st);
 cudaError_t launch_unflow_upscale(const float* x, const float* w, float* out, int B, int h, int wd, float scale, cudaStream_t st);
 
+// raft_ops.cu
+cudaError_t launch_pointwise(int kind, const void* a, const float* a_aff, const void* r, const float* r_aff, void* out, void* out2, int B,
+                             int chunks, long long pixels, int relu_a, int relu_out, bool bf16, cudaStream_t st);
+cudaError_t launch_raft_corr_volume(const float* f1, const float* f2, float* out, int B, int C, int HW, float scale, cudaStream_t st);
+cudaError_t launch_raft_corr_pool(const float* in, float* out, long long N, int h, int w, cudaStream_t st);
+cudaError_t launch_raft_lookup(const float* const* lvl, const float* flow, void* out, int B, int h, int w, int levels, int radius, int chunks,
+                               bool bf16, cudaStream_t st);
+cudaError_t launch_raft_flow_add(float* flow, const float* delta, long long n, cudaStream_t st);
+cudaError_t launch_raft_resize_ac(const float* in, float* out, int BC, int h, int w, int H, int W, float mult, cudaStream_t st);
+cudaError_t launch_raft_upsample(const float* flow, const float* mask, float* out, int B, int h, int w, float mult, cudaStream_t st);
+
 // ingest.cu
 cudaError_t launch_ingest_rgb(const uint8_t* bgr, long long frame_stride, float* out, int B, long long pixels, const float* mean,
                               const float* stdv, cudaStream_t st);

@@ -539,6 +539,28 @@ class Program:
         self._push(abi.OP_HEATMAP, a, meta={"kind": "heatmap_head", "name": "", "flops": 0, "bytes": B * N * a.pixels * 8})
         return a
 
+    def pointwise(self, kind, a, out, a_aff=None, r=None, r_aff=None, out2=None, relu_a=False, relu_out=False, chunks=None):
+        """Element-wise glue on dense C8 tensors (MfcPointwiseArgs; kinds abi.PW_*).  `chunks` = planes of the OUTPUT."""
+        g = abi.MfcPointwiseArgs()
+        g.a, g.a_aff, g.r, g.r_aff = a.data_ptr(), abi.ptr(a_aff), abi.ptr(r), abi.ptr(r_aff)
+        g.out, g.out2 = out.data_ptr(), abi.ptr(out2)
+        g.B, g.chunks, g.pixels = out.shape[0], (chunks or out.shape[1]), out.shape[2] * out.shape[3]
+        g.kind, g.dtype, g.relu_a, g.relu_out = kind, self.cdtype, int(relu_a), int(relu_out)
+        for t in (a, r, out, out2):
+            if t is not None and not t.is_contiguous():
+                raise ValueError("pointwise needs dense C8 tensors")
+        self.keep += [t for t in (a, a_aff, r, r_aff, out, out2) if t is not None]
+        self._push(abi.OP_POINTWISE, g, meta={"kind": "pointwise", "name": "", "flops": 0, "bytes": 2 * out.numel() * out.element_size()})
+
+    def raft(self, kind, ptrs, B, h, w, C_=0, levels=0, radius=0, scale=0.0):
+        """One RAFT piece (MfcRaftArgs; kinds abi.RAFT_*); `ptrs` = up to six tensors p0..p5 (None = NULL)."""
+        g = abi.MfcRaftArgs()
+        ptrs = list(ptrs) + [None] * (6 - len(ptrs))
+        g.p0, g.p1, g.p2, g.p3, g.p4, g.p5 = [abi.ptr(t) for t in ptrs]
+        g.kind, g.B, g.C, g.h, g.w, g.levels, g.radius, g.dtype, g.scale = kind, B, C_, h, w, levels, radius, self.cdtype, scale
+        self.keep += [t for t in ptrs if t is not None]
+        self._push(abi.OP_RAFT, g, meta={"kind": "raft%d" % kind, "name": "", "flops": 0, "bytes": 0})
+
     def warp(self, args, nbytes=0):
         self._push(abi.OP_WARP, args, meta={"kind": "flow_warp", "name": "", "flops": 0, "bytes": nbytes})
 

@@ -51,7 +51,7 @@ def test_struct_sizes_match_header():
         pytest.skip("gcc not available")
     names = ["MfcGather", "MfcConvInfo", "MfcSrc", "MfcConvDesc", "MfcConvIO", "MfcWarpArgs", "MfcGnArgs", "MfcAddArgs",
              "MfcFuseTerm", "MfcFuseArgs", "MfcResizeArgs", "MfcPoolArgs", "MfcHeatmapArgs",
-             "MfcGatherArgs", "MfcCmd"]
+             "MfcGatherArgs", "MfcCmd", "MfcPointwiseArgs", "MfcRaftArgs"]
     prog = '#include <stdio.h>\n#include "mfcnet_b200.h"\nint main(){' + "".join(
         'printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
