@@ -131,7 +131,9 @@ typedef struct MfcConvDesc {
    * (input row = oy*stride - pad + in_off_y + ky); out_stride 2 makes the epilogue store pixel (oy,ox) at
    * (oy*2 + out_off_y, ox*2 + out_off_x) of a [2*Hout][2*Wout] output tensor.  out_stride 1 (default, 0
    * is read as 1) and zero offsets = an ordinary conv. */
-  int in_off_y, in_off_x;
+  int in_off_y, in_off_x;  /* ordinary convs (out_stride 0 / 1): REDUCE the padding of that axis, 0 <= in_off <= pad -- rectangular
+                              kernels such as RAFT's ConvGRU (1x5 with padding (0, 2): kh 1, kw 5, pad 2, in_off_y 2);
+                              Hout = (Hup + 2 (pad - in_off_y) + pad_br - kh)/stride + 1                                 */
   int out_stride, out_off_y, out_off_x;
   int pad_br;              /* extra zero padding on the bottom and right edges only (nn.ZeroPad2d([l, l+e, t, t+e]) in front of
                               a pad-0 conv, models/unflow_model.py:85-130: pad = l, pad_br = e); Hout = (Hup + 2 pad + pad_br - kh)/stride + 1 */

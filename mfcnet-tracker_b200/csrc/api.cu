@@ -96,17 +96,25 @@ int validate_desc(const MfcConvDesc* d) {
   if (d->nsrc < 1 || d->nsrc > MFC_MAX_SRC) return fail(MFC_EINVAL, "conv: nsrc %d out of range", d->nsrc);
   if (d->pad < 0 || d->pad > 5) return fail(MFC_EINVAL, "conv: pad %d unsupported", d->pad);
   const int Hup = d->Hin * d->upsample, Wup = d->Win * d->upsample;
-  int ho = (Hup + 2 * d->pad + d->pad_br - d->kh) / d->stride + 1, wo = (Wup + 2 * d->pad + d->pad_br - d->kw) / d->stride + 1;
+  // ordinary convs: in_off_{y,x} REDUCE the padding of one axis (rectangular kernels: a 1x5 conv with padding (0, 2) is
+  // pad = 2, in_off_y = 2); the input window of output row oy starts at oy*stride - pad + in_off_y either way
+  const bool parity_mode = d->out_stride == 2;
+  const int pv = d->pad - (parity_mode ? 0 : d->in_off_y), ph = d->pad - (parity_mode ? 0 : d->in_off_x);
+  int ho = (Hup + 2 * pv + d->pad_br - d->kh) / d->stride + 1, wo = (Wup + 2 * ph + d->pad_br - d->kw) / d->stride + 1;
   if (d->out_stride != 0 && d->out_stride != 1 && d->out_stride != 2) return fail(MFC_EINVAL, "conv: out_stride %d unsupported", d->out_stride);
-  if ((unsigned)d->in_off_y > 1u || (unsigned)d->in_off_x > 1u || (unsigned)d->out_off_y > 1u || (unsigned)d->out_off_x > 1u)
+  if (parity_mode && ((unsigned)d->in_off_y > 1u || (unsigned)d->in_off_x > 1u || (unsigned)d->out_off_y > 1u || (unsigned)d->out_off_x > 1u))
     return fail(MFC_EINVAL, "conv: parity offsets must be 0 or 1");
+  if (!parity_mode && (d->in_off_y < 0 || d->in_off_x < 0 || d->in_off_y > d->pad || d->in_off_x > d->pad))
+    return fail(MFC_EINVAL, "conv: in_off (%d, %d) must lie in [0, pad]", d->in_off_y, d->in_off_x);
   if (d->out_stride == 2) {  // one output parity of ConvTranspose2d(4,2,1): a 2x2 pad-1 conv restricted to Hin x Win outputs
     if (d->kh != 2 || d->kw != 2 || d->stride != 1 || d->pad != 1 || d->upsample != 1)
       return fail(MFC_EINVAL, "conv: out_stride 2 is the k4 s2 p1 transposed-conv parity mode (k=2, s=1, p=1)");
     ho = d->Hin;
     wo = d->Win;
-  } else if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) {
-    return fail(MFC_EINVAL, "conv: parity offsets need out_stride 2");
+  } else if (d->out_off_y || d->out_off_x) {
+    return fail(MFC_EINVAL, "conv: output offsets need out_stride 2");
+  } else if ((d->in_off_y || d->in_off_x) && (d->stride != 1 || d->upsample != 1)) {
+    return fail(MFC_EINVAL, "conv: per-axis padding (in_off) needs stride 1 and no upsampling");
   }
   if (ho != d->Hout || wo != d->Wout)
     return fail(MFC_EINVAL, "conv: Hout/Wout %dx%d inconsistent with input %dx%d (expected %dx%d)", d->Hout, d->Wout, Hup, Wup, ho, wo);

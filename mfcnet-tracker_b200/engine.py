@@ -362,20 +362,25 @@ class Program:
                                            "bytes": B * H * W * (4 * nreal + 16)})
         return a
 
-    def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act, parity=None, pad_br=0):
+    def conv_desc(self, srcs, Cout, k, stride, pad, upsample, act, parity=None, pad_br=0, kw=None, pad_yx=None):
         """parity=(py, px): one output parity of ConvTranspose2d(4, 2, 1), a 2x2 conv whose result lands on
         the pixels (2y+py, 2x+px) of a [2H][2W] output (include/mfcnet_b200.h, MfcConvDesc)."""
         d = abi.MfcConvDesc()
         s0 = srcs[0]
         d.B, d.Hin, d.Win = s0.B, s0.H, s0.W
         Hup, Wup = s0.H * upsample, s0.W * upsample
-        d.Hout = (Hup + 2 * pad + pad_br - k) // stride + 1
-        d.Wout = (Wup + 2 * pad + pad_br - k) // stride + 1
+        kw = k if kw is None else kw          # rectangular kernel k x kw with paddings pad_yx = (py, px): pad = max, in_off = pad - p
+        if pad_yx is not None:
+            pad = max(pad_yx)
+            d.in_off_y, d.in_off_x = pad - pad_yx[0], pad - pad_yx[1]
+        py, px = pad - d.in_off_y, pad - d.in_off_x
+        d.Hout = (Hup + 2 * py + pad_br - k) // stride + 1
+        d.Wout = (Wup + 2 * px + pad_br - kw) // stride + 1
         d.pad_br = pad_br
         if parity is not None:
             d.Hout, d.Wout = s0.H, s0.W
             d.in_off_y, d.in_off_x, d.out_stride, d.out_off_y, d.out_off_x = parity[0], parity[1], 2, parity[0], parity[1]
-        d.Cout, d.kh, d.kw, d.stride, d.pad, d.upsample, d.act = Cout, k, k, stride, pad, upsample, act
+        d.Cout, d.kh, d.kw, d.stride, d.pad, d.upsample, d.act = Cout, k, kw, stride, pad, upsample, act
         d.dtype = self.cdtype
         if len(srcs) > abi.MFC_MAX_SRC:
             raise ValueError("too many concat sources")
@@ -694,7 +699,7 @@ class Builder:
 
     def conv(self, key, srcs, w_oihw, k, *, bias=None, scale=None, shift=None, stride=1, pad=0, upsample=1, act=0,
              residual=None, want_stats=False, out_c8=True, out_nchw=None, y_c8=None, first_weight_channel=None, parity=None,
-             head=None, want_lo=False, pad_br=0):
+             head=None, want_lo=False, pad_br=0, kw=None, pad_yx=None):
         """srcs: list of Act (channel concat in order).  w_oihw: fp32 device weight whose Cin axis
         is the concat of the sources' REAL channels (or, with first_weight_channel=[...], starts
         at the given offsets).  head=(w [Nh, Cout] fp32, bias [Nh] or None): a following 1x1 conv evaluated in fp32 inside this
@@ -705,7 +710,7 @@ class Builder:
         # consecutive pixels, one contiguous TMA box per plane (R*2 KB) instead of TH short row segments, and the epilogue's
         # pixel addresses are affine in the run index.  Pure re-interpretation: same bytes, same arithmetic.
         H0, W0 = srcs[0].H, srcs[0].W
-        flat = (k == 1 and stride == 1 and upsample == 1 and pad == 0 and parity is None and W0 != 128 and (H0 * W0) % 128 == 0
+        flat = (k == 1 and kw in (None, 1) and stride == 1 and upsample == 1 and pad == 0 and parity is None and W0 != 128 and (H0 * W0) % 128 == 0
                 and os.environ.get("MFC_CONV_FLAT", "1") != "0")
         if flat:
             rows = H0 * W0 // 128
@@ -718,7 +723,7 @@ class Builder:
                 y_c8 = y_c8.view(y_c8.shape[0], y_c8.shape[1], rows, 128, 8)
             if out_nchw is not None:
                 out_nchw = out_nchw.view(out_nchw.shape[0], out_nchw.shape[1], rows, 128)
-        d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity, pad_br=pad_br)
+        d = self.prog.conv_desc(srcs, Cout, k, stride, pad, upsample, act, parity=parity, pad_br=pad_br, kw=kw, pad_yx=pad_yx)
         if residual is not None:
             d.reserved |= abi.MFC_CONV_HAS_RESIDUAL
         if want_stats:

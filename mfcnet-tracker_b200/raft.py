@@ -11,7 +11,7 @@ keep the Sequential indices).  The modules below only HOLD parameters; the arith
   * every convolution = one fused tensor-core conv (`mfc_conv2d_fwd`): eval BatchNorm folded into scale / shift (context
     encoder), InstanceNorm as per-channel GroupNorm statistics in the conv epilogue + `mfc_gn_finalize` (feature encoder), the
     z and r gates of a ConvGRU as ONE conv with 256 output channels, channel concats as multi-source convs (never
-    materialised), the 1x5 / 5x1 GRU kernels embedded in 5x5 ones (the conv descriptor has one padding for both axes);
+    materialised), the 1x5 / 5x1 GRU kernels as rectangular convs with per-axis padding (MfcConvDesc.in_off);
   * the element-wise glue (norm + ReLU + residual add, tanh / ReLU split of the context, GRU gates) = `mfc_pointwise`;
   * all-pairs correlation volume, its 4-level pyramid, the 9x9 x 4 bilinear lookup (written straight into the C8 planes the
     motion encoder reads), the flow update and the convex upsampling = `mfc_raft_op`.
@@ -99,17 +99,6 @@ class _MaskPredictor(nn.Module):
     def __init__(self):
         super().__init__()
         self.convrelu, self.conv = _cna(128, 256, 3), nn.Conv2d(256, 8 * 8 * 9, 1)
-
-
-def _embed5(w):
-    """(O, I, 1, 5) or (O, I, 5, 1) -> (O, I, 5, 5) with the taps on the middle row / column."""
-    O, I, kh, kw = w.shape
-    out = torch.zeros(O, I, 5, 5, dtype=torch.float32, device=w.device)
-    if kh == 1:
-        out[:, :, 2, :] = w[:, :, 0, :]
-    else:
-        out[:, :, :, 2] = w[:, :, :, 0]
-    return out
 
 
 class RAFT(nn.Module):
@@ -222,12 +211,14 @@ class RAFT(nn.Module):
         mot = cv("conv", me.conv, [corr, flo])
         for gn, gru in (("convgru1", rb.convgru1), ("convgru2", rb.convgru2)):
             p = "update_block.recurrent_block.%s." % gn
-            wzr = _embed5(torch.cat([gru.convz.weight.detach(), gru.convr.weight.detach()], 0).float())
+            kh, kw = gru.convz.kernel_size
+            rect = dict(kw=kw, pad_yx=tuple(gru.convz.padding))      # 1x5 / 5x1 kernels, padding (0, 2) / (2, 0)
+            wzr = torch.cat([gru.convz.weight.detach(), gru.convr.weight.detach()], 0).float()
             bzr = torch.cat([gru.convz.bias.detach(), gru.convr.bias.detach()], 0).float()
-            zr = bu.conv(p + "convzr", [hA, cA, mot, fl], wzr, 5, bias=bzr, pad=2)[0]
+            zr = bu.conv(p + "convzr", [hA, cA, mot, fl], wzr, kh, bias=bzr, **rect)[0]
             rh = bu.arena.alloc(tuple(P["h"].shape), tdt)
             bu.prog.pointwise(abi.PW_GRU_RH, zr.t, rh, r=P["h"], chunks=16)
-            q = bu.conv(p + "convq", [Act(rh, 128), cA, mot, fl], _embed5(gru.convq.weight.detach().float()), 5, bias=gru.convq.bias, pad=2)[0]
+            q = bu.conv(p + "convq", [Act(rh, 128), cA, mot, fl], gru.convq.weight, kh, bias=gru.convq.bias, **rect)[0]
             bu.prog.pointwise(abi.PW_GRU_UPDATE, zr.t, P["h"], r=q.t, chunks=16)
         f1 = bu.conv("update_block.flow_head.conv1", [hA], fh.conv1.weight, 3, bias=fh.conv1.bias, pad=1, act=1)[0]
         bu.conv("update_block.flow_head.conv2", [f1], fh.conv2.weight, 3, bias=fh.conv2.bias, pad=1, out_c8=False, out_nchw=P["delta"])

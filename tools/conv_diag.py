@@ -29,7 +29,7 @@ def from_c8(t, Cc):
 
 
 def run_case(dt, B, H, W, cins, Cout, k, stride=1, pad=None, ups=1, act=0, bias=True, scale=False, residual=False,
-             res_affine=False, src_affine=False, stats=False, head=0, lo=False, seed=0):
+             res_affine=False, src_affine=False, stats=False, head=0, lo=False, seed=0, kw=None, pad_yx=None):
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(seed)
     tdtype = engine._DTYPES[dt][0]
@@ -52,14 +52,15 @@ def run_case(dt, B, H, W, cins, Cout, k, stride=1, pad=None, ups=1, act=0, bias=
         acts.append(a)
         ref_in.append(r)
     cin = sum(cins)
-    w = (torch.randn(Cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+    kw_ = k if kw is None else kw
+    w = (torch.randn(Cout, cin, k, kw_, generator=g) / (cin * k * kw_) ** 0.5).to(dev)
     b = (0.1 * torch.randn(Cout, generator=g)).to(dev) if bias else None
     sc = (1.0 + 0.2 * torch.randn(Cout, generator=g)).to(dev) if scale else None
     xin = torch.cat(ref_in, 1)
     if ups == 2:
         xin = F.interpolate(xin, scale_factor=2, mode="nearest")
     wq = w.to(tdtype).float()
-    ref = F.conv2d(xin, wq, None, stride=stride, padding=pad)
+    ref = F.conv2d(xin, wq, None, stride=stride, padding=pad if pad_yx is None else pad_yx)
     if sc is not None:
         ref = ref * sc[None, :, None, None]
     if b is not None:
@@ -86,7 +87,7 @@ def run_case(dt, B, H, W, cins, Cout, k, stride=1, pad=None, ups=1, act=0, bias=
         hd = (hw, hb)
     out_nchw = torch.full((B, head or Cout, Ho, Wo), float("nan"), device=dev)
     out, st, info, io = bld.conv("c", acts, w, k, bias=b, scale=sc, stride=stride, pad=pad, upsample=ups, act=act,
-                                 residual=res_act, want_stats=stats, out_nchw=out_nchw, head=hd, want_lo=lo)
+                                 residual=res_act, want_stats=stats, out_nchw=out_nchw, head=hd, want_lo=lo, kw=kw, pad_yx=pad_yx)
     bld.prog.run()
     torch.cuda.synchronize()
     e_c8 = (from_c8(out.t, Cout) - ref).abs().max().item()
@@ -141,6 +142,12 @@ CASES = [
     dict(B=1, H=64, W=96, cins=[16, 16], Cout=16, k=1, head=3),
     dict(B=2, H=33, W=47, cins=[25], Cout=25, k=3, act=1, scale=True, lo=True),
     dict(B=2, H=40, W=56, cins=[16], Cout=16, k=3, lo=True),
+    # rectangular kernels with per-axis padding (RAFT's ConvGRU: 1x5 / 5x1 over a four-source concat)
+    dict(B=2, H=30, W=40, cins=[128, 128, 126, 2], Cout=256, k=1, kw=5, pad_yx=(0, 2)),
+    dict(B=2, H=30, W=40, cins=[128, 128, 126, 2], Cout=128, k=5, kw=1, pad_yx=(2, 0)),
+    dict(B=1, H=17, W=23, cins=[16], Cout=16, k=1, kw=5, pad_yx=(0, 2), act=1),
+    dict(B=1, H=17, W=23, cins=[24], Cout=40, k=5, kw=1, pad_yx=(2, 0)),
+    dict(B=1, H=16, W=20, cins=[128], Cout=64, k=1, stride=2, pad=0),
 ]
 
 
