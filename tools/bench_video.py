@@ -37,19 +37,33 @@ def main():
         flows.append([4 * torch.randn(1, 2, H, W, device="cuda", generator=g) for _ in range(K - 1)])
     out = torch.empty(1, N, H, W, device="cuda")
     depth_ring = []
+    # --online-flow: the K-1 flow fields of every frame come from RAFT-large on the engine, as in the video script
+    # (scripts/test_multiframe_segmentation_on_videos_v3.py:264-271: half-size frames, flow / 0.5 resized back), one batched call
+    online = "--online-flow" in sys.argv
+    raft = M.raft_large().cuda().eval() if online else None
+    frame_ring = []
+
+    def flows_for(t, x):
+        if not online:
+            return flows[t % pool]
+        frame_ring.insert(0, x)
+        del frame_ring[K:]
+        prev = (frame_ring + frame_ring[-1:] * K)[1:K]
+        f = M.video_flow(raft, x.expand(K - 1, -1, -1, -1), torch.cat(prev, 0))
+        return [f[i:i + 1] for i in range(K - 1)]
 
     def forward(t):
         x = M.ingest_rgb(bgr[t % pool])
         depth_ring.insert(0, M.ingest_depth(gray[t % pool]))
         del depth_ring[K:]
-        y = run.step(x, flows[t % pool], (depth_ring + depth_ring[-1:] * K)[:K], out=out)
+        y = run.step(x, flows_for(t, x), (depth_ring + depth_ring[-1:] * K)[:K], out=out)
         return None if y is None else M.heatmap_head(y, want_logp=False, want_argmax=False)[1]
 
     def frame(t, track):
         x = M.ingest_rgb(bgr[t % pool])
         depth_ring.insert(0, M.ingest_depth(gray[t % pool]))
         del depth_ring[K:]
-        y = run.step(x, flows[t % pool], (depth_ring + depth_ring[-1:] * K)[:K], out=out)
+        y = run.step(x, flows_for(t, x), (depth_ring + depth_ring[-1:] * K)[:K], out=out)
         if y is None or track is None:
             return None
         _, prob, _ = M.heatmap_head(y, want_logp=False, want_argmax=False)
@@ -60,6 +74,7 @@ def main():
         for name, mk in (("model_only", lambda: None), ("model_head_tracking", lambda: M.ToolTracker(10, 40, 0.0))):
             run.reset()
             del depth_ring[:]
+            del frame_ring[:]
             tr = mk()
             for t in range(3 * K):
                 frame(t, tr)
@@ -74,6 +89,7 @@ def main():
         # one frame in flight: frame t's tracking is submitted, frame t+1's forward is launched, then frame t's row is collected
         run.reset()
         del depth_ring[:]
+        del frame_ring[:]
         tr = M.ToolTracker(10, 40, 0.0)
         for t in range(3 * K):
             frame(t, tr)
@@ -90,10 +106,11 @@ def main():
         dt = time.perf_counter() - t0
         res["model_head_tracking_pipelined"] = {"frames_per_s": round(F / dt, 1), "ms_per_frame": round(dt / F * 1e3, 3),
                                                 "last_row_identical": bool(all((a == b) or (a != a and b != b) for a, b in zip(rows[-1], row)))}
-    line = {"what": "video loop, %s MFCNet K=%d, 480x640, batch 1, ingest + streaming forward + head + tracking" % (model, K), "frames": F, **res}
+    line = {"what": "video loop, %s MFCNet K=%d, 480x640, batch 1, ingest + %sstreaming forward + head + tracking"
+                    % (model, K, "online RAFT-large flow (K-1 fields per frame, one batched call) + " if online else ""), "frames": F, **res}
     print(json.dumps(line))
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(line, open("gpurun_out/bench_video_%s.json" % model, "w"), indent=1)
+    json.dump(line, open("gpurun_out/bench_video_%s%s.json" % (model, "_online_flow" if online else ""), "w"), indent=1)
 
 
 if __name__ == "__main__":
