@@ -227,7 +227,38 @@ def secondary_records(args, net, world, rank):
                       "value": fps, "unit": "frames/s", "clips_per_gpu": Bc, "n_gpus": world, "frames": args.video_frames,
                       "outputs": n_out, "ms_total": ms, "launches_per_step": launches, "scaling": "strong",
                       "gflop_per_frame": 296.2, "tensor_frac": fps * 296.2 / 1e3 / (tf_peak * world)}
+    rec["online_flow"] = raft_record(world)
     return rec
+
+
+def raft_record(world, B=8, Hh=240, Wh=320, calls=20):
+    """RAFT-large, the video loop's online flow provider, at the video script's operating point (half-size
+    frames): B frame pairs per GPU per call, 12 updates, device-timed, max over ranks.  Random-init weights (timing only)."""
+    import torch
+    import torch.distributed as dist
+    import mfcnet_tracker_b200 as m
+    torch.manual_seed(0)
+    net = m.raft_large().cuda().eval()
+    x = torch.randn(B, 3, Hh, Wh, device="cuda").clamp_(-2, 2)
+    y = torch.randn(B, 3, Hh, Wh, device="cuda").clamp_(-2, 2)
+    with torch.no_grad():
+        for _ in range(3):
+            net(x, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(calls):
+            net(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / calls], device="cuda")
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    P = net._plans[(B, Hh, Wh)]
+    return {"metric": "flow fields/s, RAFT-large (12 updates) on %dx%d half-size frames, %d frame pairs per GPU per call" % (Hh, Wh, B),
+            "value": B * world * 1e3 / ms, "unit": "fields/s", "batch_per_gpu": B, "ms_per_call": ms,
+            "launches_per_call": P["E"].n_kernels + 12 * P["U"].n_kernels + P["M"].n_kernels, "n_gpus": world, "scaling": "weak"}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -373,6 +373,13 @@ int mfc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int mfc_ingest_rgb(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, const float* mean3_host,
                    const float* std3_host, void* stream);
 int mfc_ingest_depth(const uint8_t* bgr, long long frame_stride_bytes, float* out, int B, int H, int W, void* stream);
+/* cv2.resize(frame, (W, H)) (default INTER_LINEAR, 8-bit; scripts/test_multiframe_segmentation_on_videos_v3.py:253,257) on the
+ * device, bit-exact with OpenCV's fixed-point scheme: src uint8 [B][h][w][C] (C = 1 or 3, `frame_stride_bytes` between
+ * frames) -> dst uint8 [B][H][W][C], dense.  mfc_bgr2gray_u8 = cvtColor(BGR2GRAY) (:244, at the source size, before the
+ * resize); mfc_ingest_gray = astype(float32)/255 of a gray frame (:258): uint8 [n] -> fp32 [n]. */
+int mfc_resize_u8(const uint8_t* src, long long frame_stride_bytes, int h, int w, int C, uint8_t* dst, int B, int H, int W, void* stream);
+int mfc_bgr2gray_u8(const uint8_t* bgr, long long frame_stride_bytes, uint8_t* gray, int B, int H, int W, void* stream);
+int mfc_ingest_gray(const uint8_t* gray, float* out, long long n, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * UnFlow network around the correlation (models/unflow_model.py); the convolutions / transposed convolutions /

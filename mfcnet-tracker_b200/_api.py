@@ -5,7 +5,7 @@ from .fusion import MultiFrameNetBasic, MultiFrameNetLarge
 from .heatmap import (calc_centroids, create_circular_mask, determine_local_maxima_and_estimate_centroids, gaussian_blur,
                       heatmap_head, predicted_keypoints)
 from .hrnet import HighResolutionNet
-from .ingest import ingest_depth, ingest_rgb
+from .ingest import ingest_depth, ingest_rgb, resize_u8
 from .loss import segmentation_loss
 from .multiframe import (HRNetMultiBasic, HRNetMultiLarge, ResUNetMultiBasic, ResUNetMultiLarge, TernausNetMultiBasic,
                          TernausNetMultiLarge)
@@ -21,7 +21,7 @@ __all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic"
            "FunctionCorrelation", "ModuleCorrelation", "correlation", "correlation_backward", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
            "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames", "shard_clips", "segmentation_loss",
-           "UnFlow", "RAFT", "raft_large", "video_flow", "DataParallelTrainer", "autograd_forward", "loss_and_grad", "ingest_rgb", "ingest_depth", "ToolTracker", "class_map", "refine_tip_segmentation"]
+           "UnFlow", "RAFT", "raft_large", "video_flow", "DataParallelTrainer", "autograd_forward", "loss_and_grad", "ingest_rgb", "ingest_depth", "resize_u8", "ToolTracker", "class_map", "refine_tip_segmentation"]
 
 
 def get_tooltip_segmentation_model(args):

@@ -153,6 +153,9 @@ _SIGNATURES = {
     "mfc_adam_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p], c_int),
     "mfc_ingest_rgb": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p], c_int),
     "mfc_ingest_depth": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_resize_u8": ([c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_bgr2gray_u8": ([c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "mfc_ingest_gray": ([c_void_p, c_void_p, c_ll, c_void_p], c_int),
     "mfc_unflow_preprocess": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_nchw_to_c8": ([c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "mfc_unflow_warp": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),

@@ -845,6 +845,23 @@ int mfc_unflow_upscale(const float* x, const float* w, float* out, int B, int h,
   MFC_LAUNCH(mfc::launch_unflow_upscale(x, w, out, B, h, w_in, scale, (cudaStream_t)stream), "unflow_upscale");
 }
 
+int mfc_resize_u8(const uint8_t* src, long long frame_stride_bytes, int h, int w, int C, uint8_t* dst, int B, int H, int W, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!src || !dst || B < 1 || h < 1 || w < 1 || H < 1 || W < 1 || (C != 1 && C != 3) || frame_stride_bytes < (long long)h * w * C)
+    return fail(MFC_EINVAL, "resize_u8: bad argument");
+  MFC_LAUNCH(mfc::launch_resize_u8(src, frame_stride_bytes, h, w, C, dst, B, H, W, (cudaStream_t)stream), "resize_u8");
+}
+int mfc_bgr2gray_u8(const uint8_t* bgr, long long frame_stride_bytes, uint8_t* gray, int B, int H, int W, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!bgr || !gray || B < 1 || H < 1 || W < 1 || frame_stride_bytes < (long long)H * W * 3) return fail(MFC_EINVAL, "bgr2gray_u8: bad argument");
+  MFC_LAUNCH(mfc::launch_bgr2gray_u8(bgr, frame_stride_bytes, gray, B, (long long)H * W, (cudaStream_t)stream), "bgr2gray_u8");
+}
+int mfc_ingest_gray(const uint8_t* gray, float* out, long long n, void* stream) {
+  MFC_REQUIRE_ARCH();
+  if (!gray || !out || n < 1) return fail(MFC_EINVAL, "ingest_gray: bad argument");
+  MFC_LAUNCH(mfc::launch_ingest_gray(gray, out, n, (cudaStream_t)stream), "ingest_gray");
+}
+
 // ---- RAFT pieces ---------------------------------------------------------------------------------
 int mfc_pointwise(const MfcPointwiseArgs* a, void* stream) {
   MFC_REQUIRE_ARCH();

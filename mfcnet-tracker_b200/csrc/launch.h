@@ -75,6 +75,11 @@ cudaError_t launch_unflow_warp(const float* second, const float* flow, const flo
                                int H, int W, cudaStream_t st);
 cudaError_t launch_unflow_upscale(const float* x, const float* w, float* out, int B, int h, int wd, float scale, cudaStream_t st);
 
+cudaError_t launch_resize_u8(const uint8_t* src, long long frame_stride, int h, int w, int C, uint8_t* dst, int B, int H, int W,
+                             cudaStream_t st);
+cudaError_t launch_bgr2gray_u8(const uint8_t* bgr, long long frame_stride, uint8_t* out, int B, long long pixels, cudaStream_t st);
+cudaError_t launch_ingest_gray(const uint8_t* gray, float* out, long long n, cudaStream_t st);
+
 // raft_ops.cu
 cudaError_t launch_pointwise(int kind, const void* a, const float* a_aff, const void* r, const float* r_aff, void* out, void* out2, int B,
                              int chunks, long long pixels, int relu_a, int relu_out, bool bf16, cudaStream_t st);
