@@ -15,7 +15,7 @@ keep the Sequential indices).  The modules below only HOLD parameters; the arith
   * the element-wise glue (norm + ReLU + residual add, tanh / ReLU split of the context, GRU gates) = `mfc_pointwise`;
   * all-pairs correlation volume, its 4-level pyramid, the 9x9 x 4 bilinear lookup (written straight into the C8 planes the
     motion encoder reads), the flow update and the convex upsampling = `mfc_raft_op`.
-One update iteration is one command list, captured into a CUDA graph and replayed `num_flow_updates` times.  Only the last
+The whole forward (encoders, `num_flow_updates` update iterations, upsampling) is captured into ONE CUDA graph per input shape.  Only the last
 prediction is computed (torchvision returns one per iteration; the reference takes ``[-1]``): forward returns ``[flow]``.
 Inference only.
 """
@@ -189,11 +189,18 @@ class RAFT(nn.Module):
         arena = engine.Arena(dev)
         # ---- program E: both encoders, context split, correlation pyramid
         be = engine.Builder(dev, dt, self._packer, arena)
+        lanes = os.environ.get("MFC_RAFT_GRAPH", "1") == "0" and os.environ.get("MFC_LANES", "1") != "0"   # eager mode only: the
+        if lanes:                                            # two encoders on concurrent streams (measured: no gain, the host issues)
+            be.prog.fork()
+            be.prog.lane = 1
         x2 = be.gather_channels([Ext("img", P["img"])], 2 * B, H, W)
         self._encoder(be, "feature_encoder", self.feature_encoder, x2, ident, out_c8=False, out_nchw=P["fmaps"])
+        be.prog.lane = 0
         x1 = be.gather_channels([Ext("img1", P["img"][:B])], B, H, W)
         ctx = self._encoder(be, "context_encoder", self.context_encoder, x1, ident)
         be.prog.pointwise(abi.PW_CTX_SPLIT, ctx.t, P["h"], out2=P["ctx"], chunks=16)
+        if lanes:
+            be.prog.join()
         be.prog.raft(abi.RAFT_CORR_VOLUME, [P["fmaps"][:B], P["fmaps"][B:], P["vol"][0]], B, h, w, C_=256, scale=1.0 / 16.0)
         for l in range(self.LEVELS - 1):
             be.prog.raft(abi.RAFT_POOL, [P["vol"][l], P["vol"][l + 1]], B * hw, h >> l, w >> l)
@@ -231,7 +238,7 @@ class RAFT(nn.Module):
         bm.conv("mask_predictor.conv", [m1], mp.conv.weight, 1, bias=mp.conv.bias, out_c8=False, out_nchw=P["mask"])
         bm.prog.raft(abi.RAFT_UPSAMPLE, [P["flow"], P["mask"], P["out"]], B, h, w, scale=self.MULT)
         bm.prog.finalize()
-        P.update(E=be.prog, U=bu.prog, M=bm.prog, graphU=None, arena=arena, ident=ident)
+        P.update(E=be.prog, U=bu.prog, M=bm.prog, graphs={}, arena=arena, ident=ident, dt=dt)
         return P
 
     def forward(self, image1, image2, num_flow_updates=12):
@@ -251,19 +258,25 @@ class RAFT(nn.Module):
             P["img"][:B].copy_(image1)
             P["img"][B:].copy_(image2)
             P["flow"].zero_()
-            P["E"].run()
-            if P["graphU"] is None and os.environ.get("MFC_RAFT_GRAPH", "1") != "0":
-                P["U"].run()                      # first iteration eagerly (settles the packed weights), then capture
-                P["graphU"] = P["U"].capture()
-                first = 1
-            else:
-                first = 0
-            for _ in range(first, num_flow_updates):
-                if P["graphU"] is not None:
-                    P["graphU"].launch()
-                else:
+            n = int(num_flow_updates)
+            if os.environ.get("MFC_RAFT_GRAPH", "1") == "0":
+                P["E"].run()
+                for _ in range(n):
                     P["U"].run()
-            P["M"].run()
+                P["M"].run()
+            elif n in P["graphs"]:
+                P["graphs"][n].launch()               # the whole forward -- encoders, n updates, upsampling -- is ONE graph launch
+            else:
+                P["E"].run()                          # first call eagerly (settles the packed weights), then capture
+                for _ in range(n):
+                    P["U"].run()
+                P["M"].run()
+                whole = engine.Program(dev, P["dt"])
+                whole.extend(P["E"])
+                for _ in range(n):
+                    whole.extend(P["U"])
+                whole.extend(P["M"])
+                P["graphs"][n] = whole.capture()
             out = P["out"].clone()
         engine.record_stream(image1)
         engine.record_stream(image2)
