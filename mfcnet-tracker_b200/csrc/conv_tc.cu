@@ -1250,7 +1250,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   // cycles an issue costs (per-item trace), and a slot is refilled the moment its MMAs retire.
   // (not in the FAST == 2 kernels: their layers are direct-mode, the ring is kept full by an otherwise idle producer lane,
   // and a fourth role inside the register-reduced warpgroup made ptxas spill 650 instead of 130 bytes in the epilogue)
-  const bool loader9 = FAST != 2 && p.t.tma != 0 && p.t.slide != 0 && !(p.debug & (1 | 16384));
+  // Also in the per-tap mode when the MMA work of an item is small (narrow 1x1 / 2x2 layers: a handful of MMAs per run):
+  // one issuing warp is enough there, and their multi-stage items cost the issuing producer lane 3 x 1 500 cycles each.
+  const bool light_mma = p.t.slide == 0 && p.t.nblk == 1 && p.t.NB <= 32 && p.t.entries * p.t.ksteps <= 16 && !(p.debug & 32768);
+  const bool loader9 = FAST != 2 && p.t.tma != 0 && (p.t.slide != 0 || light_mma) && !(p.debug & (1 | 16384));
   const int n_mma = loader9 ? 1 : kMmaWarps;   // warps committing MMAs (arrivals on bar_empty / bar_tfull)
 
   // ---- one-time setup (independent of the previous kernel's output: overlaps its tail under PDL)
@@ -1558,13 +1561,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 // (set, run) pairs q = set*R + r with q % kMmaWarps == mw
                 const uint32_t acc = ecount >= p.t.kacc ? 1u : 0u;
                 const int q0 = aset * p.t.R;
-                const int r0 = (mw - q0) & (kMmaWarps - 1);
+                const int r0 = (mw - q0) & (n_mma - 1);      // n_mma = 1 (loader warp active): this warp issues every run
                 uint32_t a_lo = a_sk + 128u * (uint32_t)r0;
                 uint32_t d_tmem = tmem_acc + (uint32_t)((q0 + r0) * NB);
-                for (int r = r0; r < p.t.R; r += kMmaWarps) {
+                for (int r = r0; r < p.t.R; r += n_mma) {
                   umma_f16_ss(d_tmem, ((uint64_t)da_hi << 32) | a_lo, ((uint64_t)db_hi << 32) | b_lo, idesc, acc);
-                  a_lo += 128u * kMmaWarps;
-                  d_tmem += (uint32_t)(NB * kMmaWarps);
+                  a_lo += 128u * (uint32_t)n_mma;
+                  d_tmem += (uint32_t)(NB * n_mma);
                 }
                 ++ecount;
                 if (++aset == p.t.kacc) aset = 0;

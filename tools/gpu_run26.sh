@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-T=r03e
+T=r05e
 rm -f gpurun_out/parity_report.jsonl
 MFC_CONV_TUNE=0 MFC_CONV_TABLE=0 timeout 600 python tools/conv_diag.py fp16 2>&1 | tail -1 > gpurun_out/${T}_conv_diag.log
 timeout 1500 python tools/tune_table.py --fresh > gpurun_out/${T}_tune.log 2>&1
