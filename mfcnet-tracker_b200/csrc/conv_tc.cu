@@ -203,9 +203,22 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
 #pragma unroll
       for (int u = 0; u < U; ++u) sts16_u32(a[u], v[u]);
     }
-    for (; idx0 < n_items; idx0 += NT) {   // the last, partial group
-      const uint32_t a = slot_addr((uint32_t)idx0);
-      sts16_u32(a, silu8(lds16_u32(a)));
+    if (idx0 < n_items) {   // the last, partial group: the same U-slot pipeline with predicates (one slot at a time would
+      uint4 v[U];            // serialise LDS -> FFMA2 -> MUFU -> FFMA2 -> STS chains: ~20 % of a 10-slot-per-thread plane)
+      uint32_t a[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ok[u] = idx0 + u * NT < n_items;
+        a[u] = slot_addr((uint32_t)(idx0 + u * NT));
+        if (ok[u]) v[u] = lds16_u32(a[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) v[u] = silu8(v[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) sts16_u32(a[u], v[u]);
     }
     return;
   }

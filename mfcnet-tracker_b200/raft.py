@@ -21,12 +21,16 @@ Inference only.
 """
 import ctypes as C
 import os
+import threading
 
 import torch
 from torch import nn
 
 from . import abi, engine
 from .engine import Act, Ext
+
+
+_FORWARD_LOCK = threading.Lock()   # a plan's buffers are shared state: one RAFT forward at a time per process
 
 
 def _cna(cin, cout, k, stride=1, norm=None, act=True):
@@ -249,12 +253,12 @@ class RAFT(nn.Module):
             raise ValueError("input images should have the same shape (B, 3, H, W), instead got %s and %s" % (tuple(image1.shape), tuple(image2.shape)))
         B, _, H, W = image1.shape
         dev = image1.device
-        dt = self._check_weights(dev)
-        key = (B, H, W)
-        if key not in self._plans:
-            self._plans[key] = self._build(B, H, W, dev, dt)
-        P = self._plans[key]
-        with engine.device_guard(dev):
+        with _FORWARD_LOCK, engine.device_guard(dev):
+            dt = self._check_weights(dev)
+            key = (B, H, W)
+            if key not in self._plans:
+                self._plans[key] = self._build(B, H, W, dev, dt)
+            P = self._plans[key]
             P["img"][:B].copy_(image1)
             P["img"][B:].copy_(image2)
             P["flow"].zero_()
