@@ -21,8 +21,10 @@ def arg(name, default):
     return type(default)(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
 
 
-def run(model="hrnet", K=5, F=9000, B=4, H=480, W=640, N=5, world=1, rank=0, net=None, variant="large"):
-    """Streams the rank's clips; returns (device ms, outputs produced, launches per step).  All ranks must call it."""
+def run(model="hrnet", K=5, F=9000, B=4, H=480, W=640, N=5, world=1, rank=0, net=None, variant="large", online_flow=False):
+    """Streams the rank's clips; returns (device ms, outputs produced, launches per step).  All ranks must call it.
+    online_flow: the K-1 flow fields of every clip and step come from RAFT-large on the engine (the video script's call site,
+    scripts/test_multiframe_segmentation_on_videos_v3.py:264-271: half-size frames), B x (K-1) frame pairs in one call."""
     dev = torch.device("cuda", torch.cuda.current_device())
     if net is None:
         torch.manual_seed(0)
@@ -49,14 +51,27 @@ def run(model="hrnet", K=5, F=9000, B=4, H=480, W=640, N=5, world=1, rank=0, net
     def indices(i):   # frame index of every clip at step i (finished / empty clips repeat their last frame, output discarded)
         return torch.tensor([max(0, min(c["enc_lo"] + i, c["hi"] - 1)) % pool for c in clips], device=dev)
 
+    raft = M.raft_large().to(dev).eval() if online_flow else None
+    ring = []   # the clips' previous frames (step i-1, i-2, ...), each (B, 3, H, W)
+
     def step(i):
         idx = indices(i)
-        return runner.step(frames[idx], [f[idx] for f in flows], [d[idx] for d in depths], out=out)
+        x = frames[idx]
+        if raft is None:
+            fl = [f[idx] for f in flows]
+        else:
+            prev = (ring + [x] * K)[:K - 1]            # a clip's first steps see its own frame (zero motion) for missing history
+            f = M.video_flow(raft, x.repeat(K - 1, 1, 1, 1), torch.cat(prev, 0))
+            fl = [f[j * B:(j + 1) * B] for j in range(K - 1)]
+            ring.insert(0, x)
+            del ring[K - 1:]
+        return runner.step(x, fl, [d[idx] for d in depths], out=out)
 
     with torch.no_grad():
         for i in range(min(3 * K, steps)):   # warm-up (plans, graphs)
             step(i)
         runner.reset()
+        del ring[:]
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -86,9 +101,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F, K, model, B = arg("--frames", 9000), arg("--k", 5), arg("--model", "hrnet"), arg("--clips", 4)
-    ms, tot, launches = run(model, K, F, B, world=world, rank=rank)
+    online = "--online-flow" in sys.argv
+    ms, tot, launches = run(model, K, F, B, world=world, rank=rank, online_flow=online)
     if rank == 0:
-        print(json.dumps({"metric": "output frames/sec, %s MFCNet K=%d sliding window, 480x640, clips sharded across GPUs" % (model, K),
+        print(json.dumps({"metric": "output frames/sec, %s MFCNet K=%d sliding window%s, 480x640, clips sharded across GPUs"
+                                    % (model, K, " with online RAFT-large flow" if online else ""),
                           "value": tot * 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "frames": F, "clips_per_gpu": B,
                           "outputs": tot, "halo_frames_per_clip": K - 1, "ms_total": ms, "scaling": "strong",
                           "launches_per_step": launches}))
