@@ -123,6 +123,9 @@ __device__ __forceinline__ void load_aff(AffRegs& r, const float* __restrict__ a
   for (int i = 0; i < 8; ++i) r.a[i] = __ldg(reinterpret_cast<const float2*>(aff) + i);
 }
 
+#ifndef MFC_XF_U
+#define MFC_XF_U 4
+#endif
 template <bool BF16, int NT>
 __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* plane, const AffRegs& ar, int iy_base, int ix_base,
                                                 int tid) {
@@ -151,7 +154,7 @@ __device__ __forceinline__ void transform_plane(const ConvParams& p, uint8_t* pl
     // bound by the SFU (4 results / clk / scheduler, tools/ubench/mufu_rate.cu), and a walk over the padded pitch
     // (sliding mode: 128 slots per row for 66 .. 109 valid ones) spent 15 .. 30 % of its MUFU issues on dead lanes.
     // The affine and the final h + h*tanh(h) run as packed fp32 pairs (FFMA2: same IEEE results as the scalar FFMAs).
-    constexpr int U = 4;    // slots in flight per thread
+    constexpr int U = MFC_XF_U;    // slots in flight per thread
     const int r_lo = max(0, -iy_base), r_hi = min(p.t.rows_sub, (int)H - iy_base);
     const int c_lo = max(0, -ix_base), c_hi = min(P, (int)W - ix_base);
     const int n_c = c_hi - c_lo;
