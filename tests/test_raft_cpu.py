@@ -31,7 +31,8 @@ def test_oracle_matches_golden():
     assert float(np.abs(f12 - g["flow12"].astype(np.float32)).max()) <= 2e-2
 
 
-def test_cpu_call_fails_loudly():
+def test_cpu_call_fails_loudly(monkeypatch):
+    monkeypatch.delenv("MFC_B200_PLAN_ONLY", raising=False)    # (the host-logic tests' plan-only mode records plans on the CPU)
     net = m.raft_large().eval()
     x = torch.zeros(1, 3, 128, 160)
     try:

@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-T=r05a
+T=r06a
 rm -f gpurun_out/parity_report.jsonl
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/${T}_pytest.log
 python __graft_entry__.py smoke > gpurun_out/${T}_smoke.log 2>&1
