@@ -14,14 +14,14 @@ from .ternausnet import TernausNet11, TernausNet16
 from .stream import HostPipeline, StreamingMFCNet, shard_clips, shard_frames
 from .tracking import ToolTracker, class_map, refine_tip_segmentation
 from .unflow import UnFlow
-from .raft import RAFT, raft_large, video_flow
+from .raft import RAFT, StreamingFlow, raft_large, video_flow
 from .train import DataParallelTrainer, autograd_forward, loss_and_grad
 
 __all__ = ["abi", "engine", "ResUnet_VB", "HighResolutionNet", "HRNetMultiBasic", "HRNetMultiLarge", "TernausNet11", "TernausNet16", "TernausNetMultiBasic", "TernausNetMultiLarge", "MultiFrameNetBasic", "MultiFrameNetLarge", "ResUNetMultiBasic", "ResUNetMultiLarge",
            "FunctionCorrelation", "ModuleCorrelation", "correlation", "correlation_backward", "heatmap_head", "create_circular_mask", "calc_centroids",
            "determine_local_maxima_and_estimate_centroids", "gaussian_blur", "predicted_keypoints",
            "get_tooltip_segmentation_model", "get_multiframe_segmentation_model", "HostPipeline", "StreamingMFCNet", "shard_frames", "shard_clips", "segmentation_loss",
-           "UnFlow", "RAFT", "raft_large", "video_flow", "DataParallelTrainer", "autograd_forward", "loss_and_grad", "ingest_rgb", "ingest_depth", "resize_u8", "ToolTracker", "class_map", "refine_tip_segmentation"]
+           "UnFlow", "RAFT", "StreamingFlow", "raft_large", "video_flow", "DataParallelTrainer", "autograd_forward", "loss_and_grad", "ingest_rgb", "ingest_depth", "resize_u8", "ToolTracker", "class_map", "refine_tip_segmentation"]
 
 
 def get_tooltip_segmentation_model(args):

@@ -175,6 +175,45 @@ class RAFT(nn.Module):
                 y = self._block(bld, "%s.%s.%d" % (name, ln, i), blk, y, norm, ident)
         return bld.conv(name + ".conv", [y], enc.conv.weight, 1, bias=enc.conv.bias, **final_kw)[0]
 
+    def _record_update(self, P, B, h, w, dev, dt, arena):
+        """Records program U (one update iteration on B frame pairs) and program M (mask predictor + convex upsampling) over
+        the buffers of P: vol (pyramid), flow, delta, corr, h, ctx, mask, out."""
+        tdt = engine._DTYPES[dt][0]
+        # ---- program U: one update iteration (lookup, motion encoder, two ConvGRUs, flow head, flow += delta)
+        bu = engine.Builder(dev, dt, self._packer, arena)
+        ub, me, rb, fh = self.update_block, self.update_block.motion_encoder, self.update_block.recurrent_block, self.update_block.flow_head
+        bu.prog.raft(abi.RAFT_LOOKUP, P["vol"] + [P["flow"], P["corr"]], B, h, w, levels=self.LEVELS, radius=self.RADIUS)
+        hA, cA = Act(P["h"], 128), Act(P["ctx"], 128)
+        fl = bu.gather_channels([Ext("flow", P["flow"])], B, h, w)
+        cv = lambda nm, seq, srcs: bu.conv("update_block.motion_encoder." + nm, srcs, seq[0].weight, seq[0].kernel_size[0], bias=seq[0].bias,
+                                           pad=seq[0].padding[0], act=1)[0]
+        corr = cv("convcorr2", me.convcorr2, [cv("convcorr1", me.convcorr1, [Act(P["corr"], self.LEVELS * (2 * self.RADIUS + 1) ** 2)])])
+        flo = cv("convflow2", me.convflow2, [cv("convflow1", me.convflow1, [fl])])
+        mot = cv("conv", me.conv, [corr, flo])
+        for gn, gru in (("convgru1", rb.convgru1), ("convgru2", rb.convgru2)):
+            p = "update_block.recurrent_block.%s." % gn
+            kh, kw = gru.convz.kernel_size
+            rect = dict(kw=kw, pad_yx=tuple(gru.convz.padding))      # 1x5 / 5x1 kernels, padding (0, 2) / (2, 0)
+            wzr = torch.cat([gru.convz.weight.detach(), gru.convr.weight.detach()], 0).float()
+            bzr = torch.cat([gru.convz.bias.detach(), gru.convr.bias.detach()], 0).float()
+            zr = bu.conv(p + "convzr", [hA, cA, mot, fl], wzr, kh, bias=bzr, **rect)[0]
+            rh = bu.arena.alloc(tuple(P["h"].shape), tdt)
+            bu.prog.pointwise(abi.PW_GRU_RH, zr.t, rh, r=P["h"], chunks=16)
+            q = bu.conv(p + "convq", [Act(rh, 128), cA, mot, fl], gru.convq.weight, kh, bias=gru.convq.bias, **rect)[0]
+            bu.prog.pointwise(abi.PW_GRU_UPDATE, zr.t, P["h"], r=q.t, chunks=16)
+        f1 = bu.conv("update_block.flow_head.conv1", [hA], fh.conv1.weight, 3, bias=fh.conv1.bias, pad=1, act=1)[0]
+        bu.conv("update_block.flow_head.conv2", [f1], fh.conv2.weight, 3, bias=fh.conv2.bias, pad=1, out_c8=False, out_nchw=P["delta"])
+        bu.prog.raft(abi.RAFT_FLOW_ADD, [P["flow"], P["delta"]], B, h, w)
+        bu.prog.finalize()
+        # ---- program M: mask predictor on the final hidden state + convex upsampling
+        bm = engine.Builder(dev, dt, self._packer, arena)
+        mp = self.mask_predictor
+        m1 = bm.conv("mask_predictor.convrelu", [hA], mp.convrelu[0].weight, 3, bias=mp.convrelu[0].bias, pad=1, act=1)[0]
+        bm.conv("mask_predictor.conv", [m1], mp.conv.weight, 1, bias=mp.conv.bias, out_c8=False, out_nchw=P["mask"])
+        bm.prog.raft(abi.RAFT_UPSAMPLE, [P["flow"], P["mask"], P["out"]], B, h, w, scale=self.MULT)
+        bm.prog.finalize()
+        return bu.prog, bm.prog
+
     def _build(self, B, H, W, dev, dt):
         if H % 8 or W % 8:
             raise ValueError("input image H and W should be divisible by 8, instead got %d (h) and %d (w)" % (H, W))
@@ -209,40 +248,8 @@ class RAFT(nn.Module):
         for l in range(self.LEVELS - 1):
             be.prog.raft(abi.RAFT_POOL, [P["vol"][l], P["vol"][l + 1]], B * hw, h >> l, w >> l)
         be.prog.finalize()
-        # ---- program U: one update iteration (lookup, motion encoder, two ConvGRUs, flow head, flow += delta)
-        bu = engine.Builder(dev, dt, self._packer, arena)
-        ub, me, rb, fh = self.update_block, self.update_block.motion_encoder, self.update_block.recurrent_block, self.update_block.flow_head
-        bu.prog.raft(abi.RAFT_LOOKUP, P["vol"] + [P["flow"], P["corr"]], B, h, w, levels=self.LEVELS, radius=self.RADIUS)
-        hA, cA = Act(P["h"], 128), Act(P["ctx"], 128)
-        fl = bu.gather_channels([Ext("flow", P["flow"])], B, h, w)
-        cv = lambda nm, seq, srcs: bu.conv("update_block.motion_encoder." + nm, srcs, seq[0].weight, seq[0].kernel_size[0], bias=seq[0].bias,
-                                           pad=seq[0].padding[0], act=1)[0]
-        corr = cv("convcorr2", me.convcorr2, [cv("convcorr1", me.convcorr1, [Act(P["corr"], self.LEVELS * (2 * self.RADIUS + 1) ** 2)])])
-        flo = cv("convflow2", me.convflow2, [cv("convflow1", me.convflow1, [fl])])
-        mot = cv("conv", me.conv, [corr, flo])
-        for gn, gru in (("convgru1", rb.convgru1), ("convgru2", rb.convgru2)):
-            p = "update_block.recurrent_block.%s." % gn
-            kh, kw = gru.convz.kernel_size
-            rect = dict(kw=kw, pad_yx=tuple(gru.convz.padding))      # 1x5 / 5x1 kernels, padding (0, 2) / (2, 0)
-            wzr = torch.cat([gru.convz.weight.detach(), gru.convr.weight.detach()], 0).float()
-            bzr = torch.cat([gru.convz.bias.detach(), gru.convr.bias.detach()], 0).float()
-            zr = bu.conv(p + "convzr", [hA, cA, mot, fl], wzr, kh, bias=bzr, **rect)[0]
-            rh = bu.arena.alloc(tuple(P["h"].shape), tdt)
-            bu.prog.pointwise(abi.PW_GRU_RH, zr.t, rh, r=P["h"], chunks=16)
-            q = bu.conv(p + "convq", [Act(rh, 128), cA, mot, fl], gru.convq.weight, kh, bias=gru.convq.bias, **rect)[0]
-            bu.prog.pointwise(abi.PW_GRU_UPDATE, zr.t, P["h"], r=q.t, chunks=16)
-        f1 = bu.conv("update_block.flow_head.conv1", [hA], fh.conv1.weight, 3, bias=fh.conv1.bias, pad=1, act=1)[0]
-        bu.conv("update_block.flow_head.conv2", [f1], fh.conv2.weight, 3, bias=fh.conv2.bias, pad=1, out_c8=False, out_nchw=P["delta"])
-        bu.prog.raft(abi.RAFT_FLOW_ADD, [P["flow"], P["delta"]], B, h, w)
-        bu.prog.finalize()
-        # ---- program M: mask predictor on the final hidden state + convex upsampling
-        bm = engine.Builder(dev, dt, self._packer, arena)
-        mp = self.mask_predictor
-        m1 = bm.conv("mask_predictor.convrelu", [hA], mp.convrelu[0].weight, 3, bias=mp.convrelu[0].bias, pad=1, act=1)[0]
-        bm.conv("mask_predictor.conv", [m1], mp.conv.weight, 1, bias=mp.conv.bias, out_c8=False, out_nchw=P["mask"])
-        bm.prog.raft(abi.RAFT_UPSAMPLE, [P["flow"], P["mask"], P["out"]], B, h, w, scale=self.MULT)
-        bm.prog.finalize()
-        P.update(E=be.prog, U=bu.prog, M=bm.prog, graphs={}, arena=arena, ident=ident, dt=dt)
+        U, M = self._record_update(P, B, h, w, dev, dt, arena)
+        P.update(E=be.prog, U=U, M=M, graphs={}, arena=arena, ident=ident, dt=dt)
         return P
 
     def forward(self, image1, image2, num_flow_updates=12):
@@ -301,6 +308,106 @@ def video_flow(net, frame0, frame_i):
     with engine.device_guard(frame0.device):
         abi.check(abi.load().mfc_raft_op(C.byref(g), torch.cuda.current_stream(frame0.device).cuda_stream))
     return out
+
+
+class StreamingFlow:
+    """The video loop's flow provider with the per-frame work done once (scripts/test_multiframe_segmentation_on_videos_v3.py:
+    264-271 calls RAFT on (current, i frames earlier) for i = 1..K-1, every frame): B clips advance in lock step; per step the
+    feature and context encoders run on the B NEW half-size frames only -- the feature maps of the K-1 earlier frames are kept
+    in a ring -- then the correlation pyramids of the B (K-1) pairs are built and the update iterations run on all pairs at
+    once.  `step(frames)` -> list of K-1 tensors (B, 2, H, W): flow(current -> i frames earlier), i = 1..K-1, resized as the
+    script does (flow / 0.5, bilinear, align_corners=True).  A clip's first steps see its own frame for the missing history."""
+
+    def __init__(self, net, num_frames, H, W, batch=1, num_flow_updates=12, device=None):
+        if H % 16 or W % 16:
+            raise ValueError("StreamingFlow: H and W must be multiples of 16 (half-size frames, 1/8-resolution feature maps)")
+        self.net, self.K, self.H, self.W, self.B, self.n = net, int(num_frames), H, W, int(batch), int(num_flow_updates)
+        self.dev = engine.canonical_device(device if device is not None else next(net.parameters()).device)
+        self.P, self.t = None, 0
+
+    def reset(self):
+        self.t = 0
+
+    def _build(self):
+        net, B, K, dev = self.net, self.B, self.K, self.dev
+        dt = net._check_weights(dev)
+        Hh, Wh = self.H // 2, self.W // 2
+        h, w = Hh // 8, Wh // 8
+        hw, NP = h * w, B * (K - 1)
+        tdt = engine._DTYPES[dt][0]
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        c8 = lambda b, c: torch.zeros((b, (c + 7) // 8, h, w, 8), dtype=tdt, device=dev)
+        P = {"img": f32(B, 3, Hh, Wh), "fm_new": f32(B, 256, h, w), "ring": [f32(B, 256, h, w) for _ in range(K - 1)],
+             "h0": c8(B, 128), "ctx0": c8(B, 128), "h": c8(NP, 128), "ctx": c8(NP, 128),
+             "flow": f32(NP, 2, h, w), "delta": f32(NP, 2, h, w), "mask": f32(NP, 576, h, w), "out": f32(NP, 2, Hh, Wh),
+             "full": f32(NP, 2, self.H, self.W), "corr": c8(NP, net.LEVELS * (2 * net.RADIUS + 1) ** 2),
+             "vol": [f32(NP * hw, h >> l, w >> l) for l in range(net.LEVELS)]}
+        ident = (torch.ones(256, dtype=torch.float32, device=dev), torch.zeros(256, dtype=torch.float32, device=dev))
+        arena = engine.Arena(dev)
+        b1 = engine.Builder(dev, dt, net._packer, arena)          # E1: the two encoders on the new frames
+        x = b1.gather_channels([Ext("img", P["img"])], B, Hh, Wh)
+        net._encoder(b1, "feature_encoder", net.feature_encoder, x, ident, out_c8=False, out_nchw=P["fm_new"])
+        ctx = net._encoder(b1, "context_encoder", net.context_encoder, x, ident)
+        b1.prog.pointwise(abi.PW_CTX_SPLIT, ctx.t, P["h0"], out2=P["ctx0"], chunks=16)
+        b1.prog.finalize()
+        b2 = engine.Builder(dev, dt, net._packer, arena)          # E2: pyramids of the B (K-1) pairs
+        for j in range(K - 1):
+            b2.prog.raft(abi.RAFT_CORR_VOLUME, [P["fm_new"], P["ring"][j], P["vol"][0][j * B * hw:(j + 1) * B * hw]], B, h, w, C_=256,
+                         scale=1.0 / 16.0)
+        for l in range(net.LEVELS - 1):
+            b2.prog.raft(abi.RAFT_POOL, [P["vol"][l], P["vol"][l + 1]], NP * hw, h >> l, w >> l)
+        U, M = net._record_update(P, NP, h, w, dev, dt, arena)
+        M.raft(abi.RAFT_RESIZE_AC, [P["out"], None, P["full"]], NP, Hh, Wh, C_=2, levels=self.H, radius=self.W, scale=2.0)
+        M.finalize()
+        P.update(E1=b1.prog, E2=b2.prog, U=U, M=M, graph1=None, graph2=None, arena=arena, ident=ident, dt=dt, fp=net._fingerprint)
+        return P
+
+    def step(self, frames):
+        engine.require_cuda(frames, "StreamingFlow.step")
+        B, K, net = self.B, self.K, self.net
+        if tuple(frames.shape) != (B, 3, self.H, self.W):
+            raise ValueError("StreamingFlow.step: expected frames of shape %s, got %s" % ((B, 3, self.H, self.W), tuple(frames.shape)))
+        with _FORWARD_LOCK, engine.device_guard(self.dev):
+            net._check_weights(self.dev)
+            if self.P is None or self.P["fp"] != net._fingerprint:
+                self.P, self.t = self._build(), 0
+            P = self.P
+            P["img"].copy_(frames[:, :, ::2, ::2])                  # F.interpolate(scale_factor=0.5, mode='nearest')
+            graphs = os.environ.get("MFC_RAFT_GRAPH", "1") != "0"
+            if P["graph1"] is not None:
+                P["graph1"].launch()
+            else:
+                P["E1"].run()
+                if graphs:
+                    P["graph1"] = P["E1"].capture()
+            if self.t == 0:                                         # no history yet: every earlier frame = this frame
+                for r in P["ring"]:
+                    r.copy_(P["fm_new"])
+            for j in range(K - 1):                                  # hidden state / context of pair (j, b) = those of frame b
+                P["h"][j * B:(j + 1) * B].copy_(P["h0"])
+                P["ctx"][j * B:(j + 1) * B].copy_(P["ctx0"])
+            P["flow"].zero_()
+            if P["graph2"] is not None:
+                P["graph2"].launch()
+            else:
+                P["E2"].run()
+                for _ in range(self.n):
+                    P["U"].run()
+                P["M"].run()
+                if graphs:
+                    whole = engine.Program(self.dev, P["dt"])
+                    whole.extend(P["E2"])
+                    for _ in range(self.n):
+                        whole.extend(P["U"])
+                    whole.extend(P["M"])
+                    P["graph2"] = whole.capture()
+            for j in range(K - 2, 0, -1):                           # age the ring: slot j <- slot j-1, slot 0 <- the new frame
+                P["ring"][j].copy_(P["ring"][j - 1])
+            P["ring"][0].copy_(P["fm_new"])
+            self.t += 1
+            out = P["full"].clone()
+        engine.record_stream(frames)
+        return [out[j * B:(j + 1) * B] for j in range(K - 1)]
 
 
 def raft_large(**_ignored):

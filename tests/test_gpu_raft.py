@@ -94,3 +94,23 @@ def test_rejects_bad_sizes():
         mine(torch.zeros(1, 3, 100, 160, device="cuda"), torch.zeros(1, 3, 100, 160, device="cuda"))
     with pytest.raises(ValueError):
         mine(torch.zeros(1, 3, 64, 64, device="cuda"), torch.zeros(1, 3, 64, 64, device="cuda"))
+
+
+def test_streaming_flow_matches_the_per_pair_calls():
+    """StreamingFlow (encoders once per new frame, feature-map ring) against video_flow on every (current, earlier) pair."""
+    tv, mine, _ = _pair(1, 128, 160)
+    B, K, H, W = 2, 3, 256, 320
+    seq = [RO.frames(B, H, W, seed=10 + t)[0].cuda() for t in range(4)]
+    sf = m.StreamingFlow(mine, K, H, W, batch=B)
+    with torch.no_grad():
+        for t, x in enumerate(seq):
+            got = sf.step(x)
+            assert len(got) == K - 1 and got[0].shape == (B, 2, H, W)
+            for j in range(K - 1):
+                prev = seq[max(0, t - 1 - j)] if t > 0 else x
+                ref = m.video_flow(mine, x, prev)
+                err = (got[j] - ref).abs()
+                assert float(err.max()) <= 8e-2 and float(err.mean()) <= 1e-2, (t, j, float(err.max()), float(err.mean()))
+        ref_tv = RO.video_flow(tv, seq[3].cpu(), seq[1].cpu())        # and against torchvision itself for one pair
+        err = (got[1].cpu() - ref_tv).abs()
+        assert float(err.max()) <= 1.5e-1 and float(err.mean()) <= 3e-2, (float(err.max()), float(err.mean()))

@@ -52,13 +52,17 @@ def run(model="hrnet", K=5, F=9000, B=4, H=480, W=640, N=5, world=1, rank=0, net
         return torch.tensor([max(0, min(c["enc_lo"] + i, c["hi"] - 1)) % pool for c in clips], device=dev)
 
     raft = M.raft_large().to(dev).eval() if online_flow else None
-    ring = []   # the clips' previous frames (step i-1, i-2, ...), each (B, 3, H, W)
+    reuse = online_flow and os.environ.get("MFC_FLOW_REUSE", "1") != "0"
+    sflow = M.StreamingFlow(raft, K, H, W, batch=B) if reuse else None     # encoders once per new frame, feature-map ring
+    ring = []   # (without reuse) the clips' previous frames (step i-1, i-2, ...), each (B, 3, H, W)
 
     def step(i):
         idx = indices(i)
         x = frames[idx]
         if raft is None:
             fl = [f[idx] for f in flows]
+        elif sflow is not None:
+            fl = sflow.step(x)
         else:
             prev = (ring + [x] * K)[:K - 1]            # a clip's first steps see its own frame (zero motion) for missing history
             f = M.video_flow(raft, x.repeat(K - 1, 1, 1, 1), torch.cat(prev, 0))
@@ -72,6 +76,8 @@ def run(model="hrnet", K=5, F=9000, B=4, H=480, W=640, N=5, world=1, rank=0, net
             step(i)
         runner.reset()
         del ring[:]
+        if sflow is not None:
+            sflow.reset()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
