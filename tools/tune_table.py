@@ -57,6 +57,22 @@ def sfc(net, B, h=H, w=W):
     torch.cuda.synchronize()
 
 
+def raft(h, w, B):
+    net = M.raft_large().cuda().eval()
+    with torch.no_grad():
+        net(torch.randn(B, 3, h, w, device="cuda").clamp_(-2, 2), torch.randn(B, 3, h, w, device="cuda").clamp_(-2, 2))
+    torch.cuda.synchronize()
+
+
+def sflow(K, B):
+    net = M.raft_large().cuda().eval()
+    sf = M.StreamingFlow(net, K, H, W, batch=B)
+    with torch.no_grad():
+        for _ in range(2):
+            sf.step(torch.randn(B, 3, H, W, device="cuda").clamp_(-2, 2))
+    torch.cuda.synchronize()
+
+
 WORK = {
     # BASELINE configs[1] (bench.py headline) and its Basic variant: 24-frame SFC sub-batch + 8 fusion windows
     "bench": lambda: [window(M.ResUNetMultiLarge, 3, 8), window(M.ResUNetMultiBasic, 3, 8)],
@@ -67,6 +83,10 @@ WORK = {
     # BASELINE configs[3]: HRNet MFCNet K=5 streaming
     "hrnet": lambda: [stream(M.HRNetMultiLarge, 5, b) for b in (1, 4)] + [sfc(M.HighResolutionNet(num_classes=N), 1)],
     "ternaus": lambda: [sfc(M.TernausNet16(num_classes=N, num_filters=64), b) for b in (1, 2)],
+    # RAFT-large at the video script's operating point (half-size frames), pair batches of bench.py / tools/bench_raft.py, the
+    # streaming form (encoders on B new frames, updates on B (K-1) pairs) and the shapes of tests/test_gpu_raft.py
+    "raft": lambda: [raft(240, 320, b) for b in (1, 2, 8)] + [sflow(3, b) for b in (1, 8, 16)] + [raft(128, 160, b) for b in (1, 2)] +
+                    [raft(480, 640, 1)],
     # the shapes of smoke() and of the full-size parity tests
     "tests": lambda: [window(M.ResUNetMultiBasic, 3, 1, 96, 128), window(M.ResUNetMultiLarge, 3, 1), window(M.ResUNetMultiLarge, 3, 2, 96, 128),
                       window(M.HRNetMultiLarge, 5, 1)],
