@@ -1,6 +1,10 @@
+#!/bin/bash
+# The round's verification recipe on a B200 box:  gpurun --timeout 2400 -- 'bash tools/gpu_verify.sh r02z'
+# GPU test suite, smoke, the bench line (both arms), the ncu launch list and one full capture of the most frequent conv
+# shape, the correlation bench.  Everything lands in gpurun_out/<tag>_*; copy what should be judged into profiles/.
 set -x
 mkdir -p gpurun_out
-T=r06a
+T=${1:-verify}
 rm -f gpurun_out/parity_report.jsonl
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/${T}_pytest.log
 python __graft_entry__.py smoke > gpurun_out/${T}_smoke.log 2>&1
