@@ -39,6 +39,9 @@ CASES = [
     # round 2: residual-as-source 1x1 (h2 enters as a third source with GroupNorm+SiLU on load), statistics without transform
     dict(name="B24 48->16 k1 (x, skip, silu(GN(h2)))", B=24, H=480, W=640, cins=[16, 16, 16], Cout=16, k=1, aff_last=True),
     dict(name="B24 16->16 k3 stats", B=24, H=480, W=640, cins=[16], Cout=16, k=3, stats=True),
+    # tensor-bound shapes (TernausNet16's widest layers): the ncu tensor-pipe captures of profiles/r02_ncu_kernels_summary.json
+    dict(name="B2 ternaus 768->512 k3 relu 120x160", B=2, H=120, W=160, cins=[512, 256], Cout=512, k=3, act=1),
+    dict(name="B2 ternaus 256->256 k3 relu 240x320", B=2, H=240, W=320, cins=[256], Cout=256, k=3, act=1),
 ]
 
 
