@@ -42,6 +42,10 @@ CASES = [
     # tensor-bound shapes (TernausNet16's widest layers): the ncu tensor-pipe captures of profiles/r02_ncu_kernels_summary.json
     dict(name="B2 ternaus 768->512 k3 relu 120x160", B=2, H=120, W=160, cins=[512, 256], Cout=512, k=3, act=1),
     dict(name="B2 ternaus 256->256 k3 relu 240x320", B=2, H=240, W=320, cins=[256], Cout=256, k=3, act=1),
+    # the low-resolution GroupNorm-on-load layers WITHOUT the transform (direct mode): what materialising silu(GN(.)) first would buy
+    dict(name="B24 128->128 k3 stats (direct)", B=24, H=60, W=80, cins=[128], Cout=128, k=3, stats=True),
+    dict(name="B24 64->64 k3 stats (direct)", B=24, H=120, W=160, cins=[64], Cout=64, k=3, stats=True),
+    dict(name="B24 32->32 k3 stats (direct)", B=24, H=240, W=320, cins=[32], Cout=32, k=3, stats=True),
 ]
 
 
