@@ -146,89 +146,115 @@ __global__ void __launch_bounds__(CtCfg<TXG, TY, NST>::Threads, (CtCfg<TXG, TY, 
 // Stride-2 variant (the reference's own operating point: max displacement 20, stride 2, D = 21, 441 output channels).
 // Vertical displacements are even, so an output row only meets rows of `second` with its own parity: a CTA works on ONE row
 // parity and its TMA boxes traverse H with stride 2 (elementStrides; TMA has no traversal stride on the innermost dimension,
-// so columns stay interleaved).  A thread owns 4 ADJACENT image pixels x 21 dx for one (row, dy): its 44-float window of
-// `second` (11 LDS.128) serves both column parities -- pixel a, displacement d reads window[a + 2d] -- so no loaded value is
-// wasted: 12 LDS.128 per 84 FMAs, float4 stores.  Tile = TY2 rows (parity space) x 32 columns; threads = 8 x TY2 x 21.
+// so columns stay interleaved: pixel a, displacement index d reads window[a + 2d], both column parities of a loaded window
+// are used).  Tile = 2 rows (parity space) x 32 columns.
 constexpr int kC2R = 10, kC2D = 21, kC2TXG = 8, kC2TX = 32, kC2TY = 2, kC2CK = 8, kC2NST = 2;
 constexpr int kC2F2Rows = kC2TY + 2 * kC2R, kC2F2Cols = kC2TX + 4 * kC2R;     // 22 x 72 (columns in image space)
-constexpr int kC2Threads = kC2TXG * kC2TY * kC2D;                             // 336
 constexpr int kC2F1Stage = kC2CK * kC2TY * kC2TX, kC2F2Stage = kC2CK * kC2F2Rows * kC2F2Cols;
 constexpr int kC2F1Bytes = (kC2F1Stage * 4 + 127) / 128 * 128;
 constexpr int kC2StageBytes = kC2F1Bytes + (kC2F2Stage * 4 + 127) / 128 * 128;
 constexpr int kC2Smem = kC2NST * kC2StageBytes + 1024;
 
-__global__ void __launch_bounds__(kC2Threads, 1) correlation_tma_s2_kernel(const __grid_constant__ CUtensorMap map1,
-                                                                           const __grid_constant__ CUtensorMap map2,
-                                                                           float* __restrict__ out, int B, int C, int H, int W,
-                                                                           int tiles_x, int tiles_y) {
+// Register tile: a thread = 4 adjacent pixels x HALF of the horizontal displacements (11 of 21: d = 10h .. 10h+10, the two halves
+// share d = 10 and the upper one does not store it) x BOTH output rows of the tile that meet row r of `second` (row j = 0 with dy
+// index r, row j = 1 with dy index r - 1: the pair trick of the stride-1 kernel).  Its window is 24 floats (6 LDS.128 at column
+// 4g + 20h), shared by the two output rows: 8 LDS.128 per 88 FMAs.  The kernel is bound by that ratio (shared-memory wavefronts):
+// round 1's tile -- 4 pixels x all 21 displacements of ONE output row, a 44-float window, 12 LDS.128 per 84 FMAs -- took 81 us at
+// C = 256, 48 x 160 and 547 us at batch 8; this one 68 and 457 us (two channels unrolled: 74 / 495 without).  Threads = 8 pixel
+// groups x 22 rows of `second` x 2 halves = 352.  Per output value the same sequential FMA chain over the channels as every other
+// fast kernel here: results bit-identical to round 1's.
+constexpr int kC2hD = 11, kC2hUnr = 2, kC2hNST = kC2NST, kC2hSmem = kC2Smem;
+constexpr int kC2hThreads = kC2TXG * kC2F2Rows * 2;   // 352
+static_assert(kC2TY == 2, "the pair mapping below is written for two-row tiles");
+
+__global__ void __launch_bounds__(kC2hThreads, 1) correlation_tma_s2_kernel(const __grid_constant__ CUtensorMap map1,
+                                                                             const __grid_constant__ CUtensorMap map2,
+                                                                             float* __restrict__ out, int B, int C, int H, int W,
+                                                                             int tiles_x, int tiles_y) {
   extern __shared__ uint8_t ct_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ct_smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full[kC2NST];
+  __shared__ uint64_t full[kC2hNST];
   int bid = blockIdx.x;
   const int py = bid & 1; bid >>= 1;
   const int tx = bid % tiles_x; bid /= tiles_x;
   const int ty = bid % tiles_y;
   const int b = bid / tiles_y;
-  const int x0 = tx * kC2TX, yp0 = ty * kC2TY;          // columns in image space, rows in parity space (y = 2 yp + py)
+  const int x0 = tx * kC2TX, yp0 = ty * kC2TY;
   const int t = threadIdx.x;
   const int g = t % kC2TXG, k = t / kC2TXG;
-  const int j = k / kC2D, iy = k - j * kC2D;             // output row of the tile, vertical displacement index (dy = 2 (iy - R))
-  const int r_s = j + iy;                                // row of the staged `second` tile (tile row 0 = parity row yp0 - R)
+  const int r = k >> 1, hf = k & 1;                       // row of the staged `second` tile, displacement half
+  const bool do0 = r <= 2 * kC2R, do1 = r >= 1;           // (j = 0, iy = r), (j = 1, iy = r - 1)
   if (t == 0) {
-    for (int i = 0; i < kC2NST; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < kC2hNST; ++i) mbar_init(&full[i], 1);
     fence_mbar_init();
   }
   __syncthreads();
   const int nst = (C + kC2CK - 1) / kC2CK;
   auto issue = [&](int st) {
-    uint8_t* buf = smem + (size_t)(st % kC2NST) * kC2StageBytes;
-    mbar_arrive_expect_tx(&full[st % kC2NST], (uint32_t)((kC2F1Stage + kC2F2Stage) * 4));
-    tma_load_4d(buf, &map1, &full[st % kC2NST], x0, 2 * yp0 + py, st * kC2CK, b);
-    tma_load_4d(buf + kC2F1Bytes, &map2, &full[st % kC2NST], x0 - 2 * kC2R, 2 * (yp0 - kC2R) + py, st * kC2CK, b);
+    uint8_t* buf = smem + (size_t)(st % kC2hNST) * kC2StageBytes;
+    mbar_arrive_expect_tx(&full[st % kC2hNST], (uint32_t)((kC2F1Stage + kC2F2Stage) * 4));
+    tma_load_4d(buf, &map1, &full[st % kC2hNST], x0, 2 * yp0 + py, st * kC2CK, b);
+    tma_load_4d(buf + kC2F1Bytes, &map2, &full[st % kC2hNST], x0 - 2 * kC2R, 2 * (yp0 - kC2R) + py, st * kC2CK, b);
   };
   if (t == 0)
-    for (int i = 0; i < kC2NST - 1 && i < nst; ++i) issue(i);
-  float acc[4][kC2D];
+    for (int i = 0; i < kC2hNST - 1 && i < nst; ++i) issue(i);
+  float acc0[4][kC2hD], acc1[4][kC2hD];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int d = 0; d < kC2D; ++d) acc[a][d] = 0.0f;
+    for (int d = 0; d < kC2hD; ++d) acc0[a][d] = acc1[a][d] = 0.0f;
   for (int st = 0; st < nst; ++st) {
-    if (t == 0 && st + kC2NST - 1 < nst) issue(st + kC2NST - 1);
-    mbar_wait(&full[st % kC2NST], (uint32_t)((st / kC2NST) & 1));
-    const uint32_t s1 = smem_u32(smem) + (uint32_t)(st % kC2NST) * (uint32_t)kC2StageBytes + (uint32_t)(j * kC2TX + 4 * g) * 4u;
-    const uint32_t s2 = smem_u32(smem) + (uint32_t)(st % kC2NST) * (uint32_t)kC2StageBytes + (uint32_t)kC2F1Bytes +
-                        (uint32_t)(r_s * kC2F2Cols + 4 * g) * 4u;
+    if (t == 0 && st + kC2hNST - 1 < nst) issue(st + kC2hNST - 1);
+    mbar_wait(&full[st % kC2hNST], (uint32_t)((st / kC2hNST) & 1));
+    const uint32_t sb = smem_u32(smem) + (uint32_t)(st % kC2hNST) * (uint32_t)kC2StageBytes;
+    const uint32_t s1 = sb + (uint32_t)(4 * g) * 4u;
+    const uint32_t s2 = sb + (uint32_t)kC2F1Bytes + (uint32_t)(r * kC2F2Cols + 4 * g + 2 * kC2R * hf) * 4u;
+#pragma unroll kC2hUnr
     for (int cc = 0; cc < kC2CK; ++cc) {
-      const uint32_t q2 = s2 + (uint32_t)(cc * (kC2F2Rows * kC2F2Cols)) * 4u;
-      const float4 a4 = lds_f4s(s1 + (uint32_t)(cc * (kC2TY * kC2TX)) * 4u);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-      float w[44];
+      const uint32_t q2 = s2 + (uint32_t)(cc * (kC2F2Rows * kC2F2Cols)) * 4u, q1 = s1 + (uint32_t)(cc * (kC2TY * kC2TX)) * 4u;
+      const float4 a4 = lds_f4s(q1), b4 = lds_f4s(q1 + (uint32_t)kC2TX * 4u);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      float w[24];
 #pragma unroll
-      for (int i = 0; i < 11; ++i) {
+      for (int i = 0; i < 6; ++i) {
         const float4 v = lds_f4s(q2 + 16u * i);
         w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
       }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int d = 0; d < kC2D; ++d) acc[a][d] = fmaf(av[a], w[a + 2 * d], acc[a][d]);
+        for (int d = 0; d < kC2hD; ++d) {
+          acc0[a][d] = fmaf(av[a], w[a + 2 * d], acc0[a][d]);
+          acc1[a][d] = fmaf(bv[a], w[a + 2 * d], acc1[a][d]);
+        }
     }
     __syncthreads();
   }
   const float cf = (float)C;
-  const bool pow2 = (C & (C - 1)) == 0;     // x / C == x * (1 / C) exactly for a power of two (see correlation_tma_kernel)
+  const bool pow2 = (C & (C - 1)) == 0;
   const float inv = 1.0f / cf;
   auto mean = [&](float v) { return pow2 ? v * inv : __fdiv_rn(v, cf); };
-  const int y = 2 * (yp0 + j) + py;
   const int x = x0 + 4 * g;
-  if (y < H && x < W) {
+  if (x < W) {
     const size_t HW = (size_t)H * W;
-    float* o = out + ((size_t)b * kC2D * kC2D + (size_t)iy * kC2D) * HW + (size_t)y * W + x;
 #pragma unroll
-    for (int d = 0; d < kC2D; ++d)
-      *reinterpret_cast<float4*>(o + (size_t)d * HW) =
-          make_float4(mean(acc[0][d]), mean(acc[1][d]), mean(acc[2][d]), mean(acc[3][d]));
+    for (int j = 0; j < 2; ++j) {
+      if (j == 0 ? !do0 : !do1) continue;
+      const int y = 2 * (yp0 + j) + py;
+      if (y >= H) continue;
+      const int iy = r - j;
+      float* o = out + ((size_t)b * kC2D * kC2D + (size_t)iy * kC2D + (size_t)(kC2R * hf)) * HW + (size_t)y * W + x;
+#pragma unroll
+      for (int d = 0; d < kC2hD; ++d) {
+        if (d == 0 && hf) continue;   // d = 10 belongs to the lower half
+        float4 v;
+        if (j == 0)
+          v = make_float4(mean(acc0[0][d]), mean(acc0[1][d]), mean(acc0[2][d]), mean(acc0[3][d]));
+        else
+          v = make_float4(mean(acc1[0][d]), mean(acc1[1][d]), mean(acc1[2][d]), mean(acc1[3][d]));
+        *reinterpret_cast<float4*>(o + (size_t)d * HW) = v;
+      }
+    }
   }
 }
 
@@ -281,8 +307,8 @@ cudaError_t launch_correlation_tma(const CUtensorMap& map1, const CUtensorMap& m
     }
     const int Hp = (H + 1) / 2;   // rows of one parity class (class 0; class 1 is not larger)
     const int tiles_x = (W + kC2TX - 1) / kC2TX, tiles_y = (Hp + kC2TY - 1) / kC2TY;
-    correlation_tma_s2_kernel<<<(unsigned)(B * tiles_x * tiles_y * 2), kC2Threads, kC2Smem, st>>>(map1, map2, out, B, C, H, W, tiles_x,
-                                                                                                  tiles_y);
+    correlation_tma_s2_kernel<<<(unsigned)(B * tiles_x * tiles_y * 2), kC2hThreads, kC2hSmem, st>>>(map1, map2, out, B, C, H, W, tiles_x,
+                                                                                                   tiles_y);
     return cudaGetLastError();
   }
   switch (ct_pick_tx(W)) {
