@@ -129,6 +129,14 @@ __global__ void __launch_bounds__(CtCfg<TXG, TY, NST>::Threads, (CtCfg<TXG, TY, 
       if (y >= H) continue;
       const int iy = h == 0 ? ri : ri - 1;   // dy + R
       float* o = out + ((size_t)b * kCtD * kCtD + (size_t)iy * kCtD) * HW + (size_t)y * W + x;
+      if (pow2) {   // the common case compiled without the division's slow path in its instruction stream
+#pragma unroll
+        for (int d = 0; d < kCtD; ++d)
+          *reinterpret_cast<float4*>(o + (size_t)d * HW) =
+              h == 0 ? make_float4(acc0[0][d] * inv, acc0[1][d] * inv, acc0[2][d] * inv, acc0[3][d] * inv)
+                     : make_float4(acc1[0][d] * inv, acc1[1][d] * inv, acc1[2][d] * inv, acc1[3][d] * inv);
+        continue;
+      }
 #pragma unroll
       for (int d = 0; d < kCtD; ++d) {
         float4 v;
@@ -244,6 +252,16 @@ __global__ void __launch_bounds__(kC2hThreads, 1) correlation_tma_s2_kernel(cons
       if (y >= H) continue;
       const int iy = r - j;
       float* o = out + ((size_t)b * kC2D * kC2D + (size_t)iy * kC2D + (size_t)(kC2R * hf)) * HW + (size_t)y * W + x;
+      if (pow2) {
+#pragma unroll
+        for (int d = 0; d < kC2hD; ++d) {
+          if (d == 0 && hf) continue;
+          *reinterpret_cast<float4*>(o + (size_t)d * HW) =
+              j == 0 ? make_float4(acc0[0][d] * inv, acc0[1][d] * inv, acc0[2][d] * inv, acc0[3][d] * inv)
+                     : make_float4(acc1[0][d] * inv, acc1[1][d] * inv, acc1[2][d] * inv, acc1[3][d] * inv);
+        }
+        continue;
+      }
 #pragma unroll
       for (int d = 0; d < kC2hD; ++d) {
         if (d == 0 && hf) continue;   // d = 10 belongs to the lower half
